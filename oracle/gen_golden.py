@@ -1,0 +1,259 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.json from the UNMODIFIED reference.
+
+Run in the build container (the only place /root/reference exists):
+
+    python -m oracle.gen_golden
+
+Everything written here comes from importing bestquark/mentpy as-is (through oracle/ref_shim.py)
+and calling its public API: templates, MBQCircuit attributes, PatternSimulator(numpy-sv|numpy-dm),
+mentpy.gradients.get_gradient, mentpy.optimizers.*.  The fixtures are what pins the oracles
+(oracle/dense_port.py, oracle/matrix_free.py) and, through them and directly, the CUDA path.
+Angles follow SURVEY.md section 8d: np.random.default_rng(seed).uniform(0, 2*pi, T).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle.ref_shim import import_reference  # noqa: E402
+from oracle.pattern_data import PatternData  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def cplx(a):
+    a = np.asarray(a, dtype=complex)
+    return {"shape": list(a.shape), "re": a.real.reshape(-1).tolist(), "im": a.imag.reshape(-1).tolist()}
+
+
+def template_specs():
+    specs = []
+    for n in range(2, 10):
+        specs.append(("linear_cluster", [n], {}))
+    for r in range(1, 5):
+        for c in range(2, 9):
+            if r * c <= 28:
+                specs.append(("grid_cluster", [r, c], {}))
+    specs.append(("grid_cluster", [3, 4], {"periodic": True}))
+    specs.append(("grid_cluster", [4, 5], {}))
+    for wires in ([2, 3, 4], [3, 3], [5, 2, 2], [4]):
+        specs.append(("many_wires", [wires], {}))
+    specs.append(("muta", [2, 1], {}))
+    specs.append(("muta", [2, 1], {"one_column": True}))
+    specs.append(("muta", [2, 2], {"one_column": True}))
+    specs.append(("muta", [3, 1], {"one_column": True}))
+    specs.append(("muta", [3, 1], {}))
+    seen, out = set(), []
+    for s in specs:
+        key = json.dumps(s)
+        if key not in seen:
+            seen.add(key)
+            out.append(s)
+    return out
+
+
+def build(mp, spec):
+    name, args, kwargs = spec
+    return getattr(mp.templates, name)(*args, **kwargs)
+
+
+def structure_record(mp, spec):
+    gs = build(mp, spec)
+    pat = PatternData.from_circuit(gs)
+    rec = {"spec": spec, "pattern": pat.to_json()}
+    rec["nodes"] = [int(v) for v in gs.graph.nodes()]
+    rec["flow"] = {str(v): int(gs.flow(v)) for v in gs.outputc} if gs.flow is not None else None
+    rec["layers"] = [[int(v) for v in layer] for layer in gs.gflow.layers] if gs.gflow.layers else None
+    rec["depth"] = int(gs.depth) if gs.flow is not None else None
+    rec["planes"] = {str(k): v for k, v in gs.planes.items()}
+    rec["outputc"] = [int(v) for v in gs.outputc]
+    rec["inputc"] = [int(v) for v in gs.inputc]
+    return rec
+
+
+def haar_state(nq, seed):
+    from scipy.stats import unitary_group
+
+    return unitary_group.rvs(2**nq, random_state=seed)[:, 0]
+
+
+def sim_case(mp, spec, backend, seed, window_size=None, x_nodes=(), fixed=None, haar=False,
+             output_form="sv", trace=False):
+    gs = build(mp, spec)
+    for v in x_nodes:
+        gs[v] = mp.Ment("X")
+    for v, (ang, plane) in (fixed or {}).items():
+        gs[int(v)] = mp.Ment(ang, plane)
+    T = len(gs.trainable_nodes)
+    angles = np.random.default_rng(seed).uniform(0, 2 * np.pi, T)
+    kw = {}
+    if window_size is not None:
+        kw["window_size"] = window_size
+    inp = haar_state(len(gs.input_nodes), seed) if haar else None
+    ps = mp.PatternSimulator(gs, input_state=inp, backend=backend, **kw)
+    rec = {
+        "spec": spec, "backend": backend, "seed": seed, "window_size": int(ps.window_size),
+        "x_nodes": [int(v) for v in x_nodes],
+        "fixed": {str(k): [v[0], v[1]] for k, v in (fixed or {}).items()},
+        "pattern": PatternData.from_circuit(gs).to_json(),
+        "angles": angles.tolist(),
+        "input_state": None if inp is None else cplx(inp),
+    }
+    if trace:
+        steps = []
+        ps.reset()
+        for node in ps.schedule_measure:
+            a = angles[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else gs[node].angle
+            st, _ = ps.measure(a)
+            steps.append(cplx(st))
+        rec["trace"] = steps
+        ps.reset()
+    if backend == "numpy-sv":
+        out = ps.run(angles, output_form=output_form)
+        rec["output_form"] = output_form
+    else:
+        out = ps.run(angles)
+        rec["output_form"] = "dm"
+        rec["outcomes"] = {str(k): int(v) for k, v in ps.outcomes.items()}
+    rec["output"] = cplx(out)
+    return rec
+
+
+def main():
+    mp = import_reference()
+    os.makedirs(GOLDEN, exist_ok=True)
+
+    # 1. structure tables (integer indexing must be bit-exact)
+    structures = [structure_record(mp, s) for s in template_specs()]
+    with open(os.path.join(GOLDEN, "structures.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py", "source": "bestquark/mentpy (unmodified)",
+                   "records": structures}, f)
+
+    # 2. simulator known answers
+    cases = []
+    # BASELINE.json configs C1, C2, C4 (SV) and C3 (DM), seeds per SURVEY 8d
+    cases.append(sim_case(mp, ("linear_cluster", [5], {}), "numpy-sv", 0, trace=True))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 6], {}), "numpy-sv", 1, trace=True))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 6], {}), "numpy-sv", 1, output_form="dm"))
+    cases.append(sim_case(mp, ("grid_cluster", [3, 8], {}), "numpy-dm", 2))
+    cases.append(sim_case(mp, ("grid_cluster", [4, 5], {}), "numpy-sv", 3))
+    # Haar inputs, other windows, fixed-angle / X / Y nodes, muta (tests/test_simulators.py:33-64)
+    cases.append(sim_case(mp, ("linear_cluster", [7], {}), "numpy-sv", 10, haar=True))
+    cases.append(sim_case(mp, ("linear_cluster", [7], {}), "numpy-sv", 11, window_size=4, haar=True))
+    cases.append(sim_case(mp, ("linear_cluster", [6], {}), "numpy-dm", 12, window_size=3, haar=True))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 5], {}), "numpy-sv", 13, window_size=5, x_nodes=(1, 7), haar=True))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 5], {}), "numpy-dm", 13, window_size=5, x_nodes=(1, 7), haar=True))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 4], {}), "numpy-sv", 14, window_size=4,
+                          fixed={2: (0.3, "XY"), 5: (None, "Y")}))
+    cases.append(sim_case(mp, ("grid_cluster", [2, 4], {}), "numpy-dm", 14, window_size=4,
+                          fixed={2: (0.3, "XY"), 5: (None, "Y")}))
+    cases.append(sim_case(mp, ("grid_cluster", [3, 5], {}), "numpy-sv", 15, haar=True, trace=True))
+    cases.append(sim_case(mp, ("grid_cluster", [3, 4], {}), "numpy-dm", 16, haar=True))
+    cases.append(sim_case(mp, ("grid_cluster", [3, 4], {"periodic": True}), "numpy-sv", 17, window_size=5))
+    cases.append(sim_case(mp, ("many_wires", [[2, 3, 4]], {}), "numpy-sv", 18, haar=True))
+    cases.append(sim_case(mp, ("many_wires", [[2, 3, 4]], {}), "numpy-dm", 18, haar=True))
+    cases.append(sim_case(mp, ("muta", [2, 1], {}), "numpy-sv", 19, window_size=5, haar=True))
+    cases.append(sim_case(mp, ("muta", [2, 1], {}), "numpy-dm", 19, window_size=5, haar=True))
+    cases.append(sim_case(mp, ("muta", [2, 1], {"one_column": True}), "numpy-sv", 20, window_size=4))
+    # too-small window: reference silently drops CZs -- reproducible quirk
+    cases.append(sim_case(mp, ("muta", [2, 1], {"one_column": True}), "numpy-sv", 21))
+    # DM planes beyond XY (deterministic under force0): XZ, YZ fixed + trainable
+    cases.append(sim_case(mp, ("grid_cluster", [2, 4], {}), "numpy-dm", 22, window_size=4,
+                          fixed={1: (0.7, "XZ"), 4: (None, "YZ")}))
+    with open(os.path.join(GOLDEN, "sim_cases.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py", "source": "bestquark/mentpy (unmodified)",
+                   "cases": cases}, f)
+
+    # 2b. DM outcome-1 quirk (np_simulator_dm.py:335-338): window_size == |I| means the first
+    # measurement hits the bare input; with input |-> x |+> and angle 0 on node 0, prob0 = 0.
+    gs = mp.templates.many_wires([3, 3])
+    minus = np.array([1.0, -1.0]) / np.sqrt(2)
+    plus = np.array([1.0, 1.0]) / np.sqrt(2)
+    inp = np.kron(minus, plus)
+    ps = mp.PatternSimulator(gs, input_state=inp, backend="numpy-dm", window_size=2)
+    quirk = []
+    for ang in ([0.0, 0.4, 1.3, 2.2], [1e-3, 0.4, 1.3, 2.2], [0.5, 0.4, np.pi, 2.2]):
+        ps.reset()
+        out = ps.run(np.array(ang))
+        quirk.append({"angles": ang, "output": cplx(out),
+                      "outcomes": {str(k): int(v) for k, v in ps.outcomes.items()}})
+    with open(os.path.join(GOLDEN, "dm_outcome_quirk.json"), "w") as f:
+        json.dump({"spec": ("many_wires", [[3, 3]], {}), "window_size": 2,
+                   "pattern": PatternData.from_circuit(gs).to_json(),
+                   "input_state": cplx(inp), "runs": quirk}, f)
+
+    # 3. gradient + optimiser known answers: grid_cluster(4,5), cost 1 - <t|rho|t>
+    gs = mp.templates.grid_cluster(4, 5)
+    ps = mp.PatternSimulator(gs, backend="numpy-sv")
+    tgt = np.full(16, 0.25)
+
+    def cost(x):
+        ps.reset()
+        rho = ps.run(x)
+        return float(1 - np.real(tgt.conj() @ rho @ tgt))
+
+    x0 = np.random.default_rng(4).uniform(0, 2 * np.pi, 16)
+    grad_psr = mp.gradients.get_gradient(cost, x0)
+    grad_fd = mp.gradients.get_gradient(cost, x0, method="fd")
+    rec = {"spec": ("grid_cluster", [4, 5], {}), "x": x0.tolist(), "target": cplx(tgt),
+           "cost": cost(x0), "psr": grad_psr.tolist(), "fd": grad_fd.tolist()}
+
+    gs_s = mp.templates.grid_cluster(2, 4)
+    ps_s = mp.PatternSimulator(gs_s, backend="numpy-sv")
+    tgt_s = haar_state(2, 5)
+
+    def cost_s(x):
+        ps_s.reset()
+        rho = ps_s.run(x)
+        return float(1 - np.real(tgt_s.conj() @ rho @ tgt_s))
+
+    xs = np.random.default_rng(5).uniform(0, 2 * np.pi, len(gs_s.trainable_nodes))
+    opt_rec = {"spec": ("grid_cluster", [2, 4], {}), "x": xs.tolist(), "target": cplx(tgt_s),
+               "cost": cost_s(xs), "psr": mp.gradients.get_gradient(cost_s, xs).tolist()}
+    opt_rec["hessian_psr_00_01"] = [float(v) for v in mp.gradients.get_hessian(cost_s, xs)[0, :2]]
+    adam = mp.optimizers.AdamOptimizer(step_size=0.1)
+    opt_rec["adam_5"] = adam.optimize(cost_s, xs.copy(), num_iters=5).tolist()
+    sgd = mp.optimizers.SGDOptimizer(step_size=0.2, momentum=0.9)
+    opt_rec["sgd_mom_5"] = sgd.optimize(cost_s, xs.copy(), num_iters=5).tolist()
+    sgdn = mp.optimizers.SGDOptimizer(step_size=0.2, momentum=0.9, nesterov=True)
+    opt_rec["sgd_nesterov_5"] = sgdn.optimize(cost_s, xs.copy(), num_iters=5).tolist()
+    import random
+
+    random.seed(7)
+    rcd = mp.optimizers.RCDOptimizer(step_size=0.3, adaptive=True)
+    opt_rec["rcd_seed7_6"] = rcd.optimize(cost_s, xs.copy(), num_iters=6).tolist()
+    with open(os.path.join(GOLDEN, "gradients.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py", "c4": rec, "small": opt_rec}, f)
+
+    # 4. helper known answers (calculator / Ment)
+    helpers = {}
+    st = haar_state(3, 31)
+    helpers["sum_trace_pure"] = {"psi": cplx(st), "idx0": cplx(mp.calculator.partial_trace(st, [0])),
+                                 "idx1": cplx(mp.calculator.partial_trace(st, [1]))}
+    rho = np.outer(st, st.conj())
+    helpers["trace_mixed"] = {"idx0": cplx(mp.calculator.partial_trace(rho, [0])),
+                              "idx2": cplx(mp.calculator.partial_trace(rho, [2]))}
+    helpers["ment"] = []
+    for plane, ang in (("XY", 0.4), ("XZ", 1.2), ("YZ", -0.7), ("X", None), ("Y", None), ("Z", None)):
+        m = mp.Ment(plane) if ang is None else mp.Ment(ang, plane)
+        p0, p1 = m.get_povm()
+        helpers["ment"].append({"plane": plane, "angle": ang, "matrix": cplx(m.matrix()),
+                                "p0": cplx(p0), "p1": cplx(p1), "trainable": bool(mp.Ment(plane).is_trainable())})
+    helpers["swap_sequence"] = []
+    ps = mp.PatternSimulator(mp.templates.linear_cluster(3), backend="numpy-sv")
+    for src, dst in (([3, 1, 2, 0], [0, 1, 2, 3]), ([5, 9], [9, 5]), ([0, 1, 2], [2, 0, 1])):
+        helpers["swap_sequence"].append({"src": src, "dst": dst, "swaps": [list(s) for s in ps.find_swaps(src, dst)]})
+    with open(os.path.join(GOLDEN, "helpers.json"), "w") as f:
+        json.dump(helpers, f)
+    print("golden fixtures written to", GOLDEN)
+    for name in sorted(os.listdir(GOLDEN)):
+        print(f"  {name}: {os.path.getsize(os.path.join(GOLDEN, name))} bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,50 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def from_cplx(d):
+    if d is None:
+        return None
+    a = np.asarray(d["re"], dtype=float) + 1j * np.asarray(d["im"], dtype=float)
+    return a.reshape(d["shape"])
+
+
+def infidelity_pure(a, b):
+    """1 - |<a|b>|^2 / (<a|a><b|b>)"""
+    a = np.asarray(a).reshape(-1)
+    b = np.asarray(b).reshape(-1)
+    return abs(1.0 - abs(np.vdot(a, b)) ** 2 / (np.vdot(a, a).real * np.vdot(b, b).real))
+
+
+def dm_distance(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))))
+
+
+@pytest.fixture(scope="session")
+def golden_sim_cases():
+    return load_golden("sim_cases.json")["cases"]
+
+
+@pytest.fixture(scope="session")
+def golden_structures():
+    return load_golden("structures.json")["records"]
