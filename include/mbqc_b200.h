@@ -1,0 +1,137 @@
+/*
+ * mbqc_b200.h -- C ABI of the B200-native MBQC pattern-simulation hot path.
+ *
+ * The reference (bestquark/mentpy) is pure Python and has no FFI; its boundary for this path is the
+ * `BaseSimulator` ABC (mentpy/simulators/base_simulator.py:13-101) behind the `PatternSimulator`
+ * facade (mentpy/simulators/pattern_simulator.py:38-88).  Each entry point below names the
+ * reference method(s) whose arithmetic it replaces.  The Python backend classes
+ * (mentpy_b200/simulators/) bind these with ctypes; INTEGRATION.md shows the stub a mentpy
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative MBQC_E_* code on failure; mbqc_last_error()
+ *     returns a thread-local message for the last failure.
+ *   - the caller owns every device buffer; the library owns only the opaque, immutable plan
+ *     (a few hundred bytes of device memory).  No hidden allocation in any run/step call.
+ *   - every run/step call is asynchronous on the `stream` argument (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream).
+ *   - complex numbers are interleaved (re, im) pairs of the plan's real type (double by default).
+ *   - a "slot" is a bit position of the state index (0 = least significant).  Qubits are never
+ *     shifted: the qubit appended after a measurement re-uses the measured qubit's slot.
+ */
+#ifndef MBQC_B200_H
+#define MBQC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MBQC_OK 0
+#define MBQC_E_ARG (-1)      /* invalid argument (maps to ValueError) */
+#define MBQC_E_CUDA (-2)     /* CUDA runtime / launch failure (maps to RuntimeError) */
+#define MBQC_E_UNSUPPORTED (-3) /* window / size outside what the kernels cover */
+
+/* measurement planes after host lowering: X and Y are fixed-angle XY (ment.py:233-235) */
+#define MBQC_PLANE_XY 0
+#define MBQC_PLANE_XZ 1
+#define MBQC_PLANE_YZ 2
+
+#define MBQC_STEP_APPEND 1u /* a |+> qubit enters the freed slot and is CZ'ed with nbr_mask */
+
+/* per-sample status bits written by the batched kernels */
+#define MBQC_STATUS_OK 0
+#define MBQC_STATUS_BAD_NORM 1   /* zero / non-finite norm or trace (np_simulator_dm.py:179-182) */
+#define MBQC_STATUS_OUTCOME1 2   /* DM: some step took outcome 1 (np_simulator_dm.py:335-338) */
+
+#define MBQC_OUT_SV 0 /* [B][2^k] amplitudes            (np_simulator_sv.py:294-295) */
+#define MBQC_OUT_DM 1 /* [B][2^k][2^k] density matrices (np_simulator_sv.py:292-293) */
+
+#define MBQC_INPUT_PLUS 0   /* |+>^{|I|}                    (pattern_simulator.py:58-61) */
+#define MBQC_INPUT_SHARED 1 /* one [2^|I|] state for all samples */
+#define MBQC_INPUT_BATCH 2  /* [B][2^|I|], one state per sample */
+
+#define MBQC_MAX_WINDOW_REG 5    /* state-vector window held in registers, one thread per sample */
+#define MBQC_MAX_WINDOW_SMEM_SV 12
+#define MBQC_MAX_WINDOW_SMEM_DM 6
+#define MBQC_MAX_WINDOW 40       /* streaming / sharded regime (slots fit a uint64 mask) */
+
+/* One measurement of the pattern = one iteration of NumpySimulatorSV.measure
+ * (np_simulator_sv.py:164-225) / NumpySimulatorDM.measure (np_simulator_dm.py:151-216). */
+typedef struct mbqc_step {
+    int32_t slot;       /* slot of the measured qubit */
+    int32_t angle_idx;  /* >= 0: column of the angle matrix; -1: fixed angle below */
+    int32_t plane;      /* MBQC_PLANE_* (SV path accepts XY only, np_simulator_sv.py:54-59) */
+    uint32_t flags;     /* MBQC_STEP_APPEND */
+    double fixed_cos;   /* cos/sin of the fixed angle, evaluated on the host exactly as the */
+    double fixed_sin;   /*   reference does (np.cos/np.sin, or exact 1,0 / 0,1 for planes X / Y) */
+    uint64_t nbr_mask;  /* slots of the appended qubit's in-window neighbours */
+} mbqc_step;
+
+/* Single-qubit channel in block form on (rho00, rho01, rho10, rho11) of the affected qubit:
+ *   rho00' = pop[0] rho00 + pop[1] rho11      rho01' = coh_g rho01 + coh_d rho10
+ *   rho11' = pop[2] rho00 + pop[3] rho11      rho10' = coh_g rho10 + coh_d rho01
+ * Covers depolarizing, phase/bit flip, amplitude / phase damping and generalized amplitude
+ * damping (the channel list of mentpy/simulators/pennylane_simulator.py:123-136).  Applied to
+ * every measured qubit right before its measurement and to every output qubit at the end. */
+typedef struct mbqc_noise {
+    double pop[4];
+    double coh_g;
+    double coh_d;
+} mbqc_noise;
+
+typedef struct mbqc_plan mbqc_plan;
+
+/* Lowered pattern.  Replaces the per-run bookkeeping of NumpySimulatorSV.__init__/reset
+ * (np_simulator_sv.py:38-128, :299-320: window seeding, cached initial CZ product) and the
+ * output reordering (np_simulator_sv.py:286-290, np_simulator_dm.py:267-273).
+ *   input_slot[q]   slot of input qubit q (q = 0 is the MSB of the caller's input index)
+ *   init_cz_mask[a] for slot a: mask of slots b > a CZ'ed with a in the first window
+ *   output_slot[q]  slot of output qubit q (q = 0 is the MSB of the output index)
+ *   noise           NULL for the noiseless path */
+int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                     int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                     const uint64_t* init_cz_mask, const int32_t* output_slot,
+                     const mbqc_noise* noise, mbqc_plan** out);
+void mbqc_plan_destroy(mbqc_plan* plan);
+
+/* NumpySimulatorSV.run over a batch (np_simulator_sv.py:227-297): angles [B][T] (row stride
+ * `angle_stride` doubles) -> out.  Amplitudes carry the reference's global phase
+ * prod_j (1+e^{i th_j})/|1+e^{i th_j}| so that 'sv' outputs compare amplitude by amplitude.
+ */
+int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                      int32_t out_form, int32_t* d_status, void* stream);
+
+/* NumpySimulatorDM.run over a batch (np_simulator_dm.py:218-283), optional noise from the plan:
+ * out [B][2^k][2^k]; d_outcomes (may be NULL) [B][n_steps] int8 receives the outcome record
+ * (simulator.outcomes). */
+int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                      int8_t* d_outcomes, int32_t* d_status, void* stream);
+
+/* Batched parameter-shift / central-difference gradient of cost(x) = 1 - |<target|psi(x)>|^2:
+ * grad[b][i] = (cost(x_b + s e_i) - cost(x_b - s e_i)) / (2 s)
+ * (gradients/_parameter_shift.py:9-25 with s = 1.5; _finite_difference.py:9-25 central with
+ * s = h).  d_cost (may be NULL) [B] receives cost(x_b).  d_target [2^k] complex. */
+int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                        const void* d_inputs, int32_t input_mode, int64_t batch,
+                        const void* d_target, double shift, double* d_grad, double* d_cost,
+                        int32_t* d_status, void* stream);
+
+/* plan introspection (used by the host mirror and the tests) */
+int32_t mbqc_plan_window(const mbqc_plan* plan);
+int32_t mbqc_plan_num_steps(const mbqc_plan* plan);
+int32_t mbqc_plan_num_outputs(const mbqc_plan* plan);
+
+/* number of kernels this library has launched in the calling process (bench gpu_launches) */
+int64_t mbqc_launch_count(void);
+
+const char* mbqc_last_error(void);
+const char* mbqc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MBQC_B200_H */

@@ -1,0 +1,11 @@
+"""mentpy_b200 -- B200-native MBQC pattern simulator behind MentPy's simulator API.
+
+Importing the package never needs a GPU (the host-side pattern layer is pure Python); any call
+that simulates needs the in-tree CUDA library and a CUDA device and raises otherwise.
+"""
+from . import mbqc
+from .mbqc import (GraphState, MBQCircuit, Measurement, Ment, hstack, merge, templates, vstack)
+from . import simulators
+from .simulators import BaseSimulator, CudaSimulatorDM, CudaSimulatorSV, PatternSimulator
+
+__version__ = "0.1.0"

@@ -1,0 +1,92 @@
+"""ctypes binding of the C ABI declared in include/mbqc_b200.h.
+
+The shared library is built in-tree by `build.sh` / `__graft_entry__.build()` (nvcc, sm_100a).
+There is deliberately NO fallback: if the library is missing or a call fails, the product raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_mbqc_b200.so")
+
+MBQC_OK, MBQC_E_ARG, MBQC_E_CUDA, MBQC_E_UNSUPPORTED = 0, -1, -2, -3
+PLANE_XY, PLANE_XZ, PLANE_YZ = 0, 1, 2
+STEP_APPEND = 1
+STATUS_BAD_NORM, STATUS_OUTCOME1 = 1, 2
+OUT_SV, OUT_DM = 0, 1
+INPUT_PLUS, INPUT_SHARED, INPUT_BATCH = 0, 1, 2
+MAX_WINDOW_REG, MAX_WINDOW_SMEM_SV, MAX_WINDOW_SMEM_DM, MAX_WINDOW = 5, 12, 6, 40
+MAX_IO = 16
+
+
+class Step(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("angle_idx", C.c_int32), ("plane", C.c_int32),
+                ("flags", C.c_uint32), ("fixed_cos", C.c_double), ("fixed_sin", C.c_double),
+                ("nbr_mask", C.c_uint64)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("pop", C.c_double * 4), ("coh_g", C.c_double), ("coh_d", C.c_double)]
+
+
+_SIGNATURES = {
+    "mbqc_plan_create": (C.c_int, [C.POINTER(Step), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_int32), C.POINTER(Noise), C.POINTER(C.c_void_p)]),
+    "mbqc_plan_destroy": (None, [C.c_void_p]),
+    "mbqc_run_batch_sv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                    C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mbqc_run_batch_dm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                    C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                      C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "mbqc_plan_window": (C.c_int32, [C.c_void_p]),
+    "mbqc_plan_num_steps": (C.c_int32, [C.c_void_p]),
+    "mbqc_plan_num_outputs": (C.c_int32, [C.c_void_p]),
+    "mbqc_launch_count": (C.c_int64, []),
+    "mbqc_last_error": (C.c_char_p, []),
+    "mbqc_version": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built "
+            "(run ./build.sh or `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "mentpy_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def check(rc: int):
+    """Map a C status code to the exception the reference would raise for the same misuse."""
+    if rc == MBQC_OK:
+        return
+    msg = load().mbqc_last_error().decode()
+    if rc == MBQC_E_ARG:
+        raise ValueError(msg)
+    if rc == MBQC_E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def launch_count() -> int:
+    return int(load().mbqc_launch_count())

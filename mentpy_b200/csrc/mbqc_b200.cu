@@ -1,0 +1,316 @@
+// C ABI of the MBQC hot path (include/mbqc_b200.h): plan lowering tables + kernel launches.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "dm_batch.cuh"
+#include "grad_batch.cuh"
+#include "sv_batch.cuh"
+
+using namespace mbqc;
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MBQC_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CUDA_TRY(x)                                        \
+    do {                                                   \
+        cudaError_t _e = (x);                              \
+        if (_e != cudaSuccess) return cuda_fail(_e, #x);   \
+    } while (0)
+
+int after_launch(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, name);
+    return MBQC_OK;
+}
+
+int ilog2_ceil(unsigned v) {
+    int l = 0;
+    while ((1u << l) < v) ++l;
+    return l;
+}
+}  // namespace
+
+extern "C" {
+
+const char* mbqc_last_error(void) { return g_err; }
+const char* mbqc_version(void) { return "mentpy_b200 0.1 (sm_100a)"; }
+int64_t mbqc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                     int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                     const uint64_t* init_cz_mask, const int32_t* output_slot,
+                     const mbqc_noise* noise, mbqc_plan** out) {
+    if (!out) return fail(MBQC_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (window < 1 || window > MBQC_MAX_WINDOW) return fail(MBQC_E_ARG, "window %d out of range [1,%d]", window, MBQC_MAX_WINDOW);
+    if (n_steps < 0 || (n_steps > 0 && !steps)) return fail(MBQC_E_ARG, "bad step list");
+    if (n_inputs < 0 || n_inputs > window || n_inputs > kMaxIO) return fail(MBQC_E_ARG, "n_inputs %d not in [0, min(window,%d)]", n_inputs, kMaxIO);
+    if (n_outputs < 0 || n_outputs > window || n_outputs > kMaxIO) return fail(MBQC_E_ARG, "n_outputs %d not in [0, min(window,%d)]", n_outputs, kMaxIO);
+    if (n_angles < 0) return fail(MBQC_E_ARG, "n_angles < 0");
+    if ((n_inputs && !input_slot) || (n_outputs && !output_slot) || !init_cz_mask) return fail(MBQC_E_ARG, "NULL slot table");
+    const uint64_t wmask = (window >= 64) ? ~0ull : ((1ull << window) - 1ull);
+    uint64_t seen = 0;
+    for (int q = 0; q < n_inputs; ++q) {
+        if (input_slot[q] < 0 || input_slot[q] >= window || ((seen >> input_slot[q]) & 1)) return fail(MBQC_E_ARG, "input_slot[%d] invalid", q);
+        seen |= 1ull << input_slot[q];
+    }
+    seen = 0;
+    for (int q = 0; q < n_outputs; ++q) {
+        if (output_slot[q] < 0 || output_slot[q] >= window || ((seen >> output_slot[q]) & 1)) return fail(MBQC_E_ARG, "output_slot[%d] invalid", q);
+        seen |= 1ull << output_slot[q];
+    }
+    for (int m = 0; m < n_steps; ++m) {
+        const mbqc_step& s = steps[m];
+        if (s.slot < 0 || s.slot >= window) return fail(MBQC_E_ARG, "step %d: slot %d outside window", m, s.slot);
+        if (s.angle_idx < -1 || s.angle_idx >= n_angles) return fail(MBQC_E_ARG, "step %d: angle_idx %d outside [ -1, %d)", m, s.angle_idx, n_angles);
+        if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_YZ) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
+        if (s.nbr_mask & ~wmask) return fail(MBQC_E_ARG, "step %d: nbr_mask outside window", m);
+        if ((s.nbr_mask >> s.slot) & 1ull) return fail(MBQC_E_ARG, "step %d: nbr_mask contains the step's own slot", m);
+    }
+    mbqc_plan* pl = new (std::nothrow) mbqc_plan();
+    if (!pl) return fail(MBQC_E_CUDA, "out of host memory");
+    memset(&pl->tab, 0, sizeof(pl->tab));
+    PlanTables& t = pl->tab;
+    t.window = window;
+    t.n_steps = n_steps;
+    t.n_in = n_inputs;
+    t.n_out = n_outputs;
+    t.n_angles = n_angles;
+    t.has_noise = noise ? 1 : 0;
+    if (noise) t.noise = *noise;
+    t.init_scale = std::exp2(-0.5 * (window - n_inputs));
+    for (int q = 0; q < n_inputs; ++q) t.in_slot[q] = input_slot[q];
+    for (int q = 0; q < n_outputs; ++q) t.out_slot[q] = output_slot[q];
+    if (window <= kMaxSlotsSmall)
+        for (int a = 0; a < window; ++a) t.init_cz[a] = init_cz_mask[a] & wmask;
+    if (window <= MBQC_MAX_WINDOW_REG) {
+        uint64_t outmask = 0;
+        for (int q = 0; q < n_outputs; ++q) outmask |= 1ull << output_slot[q];
+        for (uint32_t i = 0; i < (1u << window); ++i) {
+            t.init_src[i] = (uint8_t)init_source_index(t, i);
+            if (init_sign_bit(t, i)) t.init_sign |= 1u << i;
+            if (i & ~outmask) {
+                t.out_dst[i] = -1;
+            } else {
+                uint32_t d = 0;
+                for (int q = 0; q < n_outputs; ++q) d |= ((i >> output_slot[q]) & 1u) << (n_outputs - 1 - q);
+                t.out_dst[i] = (int8_t)d;
+            }
+        }
+    }
+    pl->h_steps = new (std::nothrow) StepDev[n_steps > 0 ? n_steps : 1];
+    for (int m = 0; m < n_steps; ++m) {
+        StepDev& d = pl->h_steps[m];
+        const mbqc_step& s = steps[m];
+        d.slot = s.slot;
+        d.angle_idx = s.angle_idx;
+        d.plane = s.plane;
+        d.flags = s.flags;
+        d.fc = s.fixed_cos;
+        d.fs = s.fixed_sin;
+        d.nbr_mask = (s.flags & MBQC_STEP_APPEND) ? s.nbr_mask : 0ull;
+        d.flipmask = 0;
+        d.pad = 0;
+        if (window <= MBQC_MAX_WINDOW_REG)
+            for (uint32_t i = 0; i < (1u << window); ++i)
+                if (((i >> s.slot) & 1u) && parity64((uint64_t)i & d.nbr_mask)) d.flipmask |= 1u << i;
+    }
+    pl->d_steps = nullptr;
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(StepDev) * (n_steps > 0 ? n_steps : 1));
+    if (e == cudaSuccess && n_steps > 0)
+        e = cudaMemcpy(pl->d_steps, pl->h_steps, sizeof(StepDev) * n_steps, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (pl->d_steps) cudaFree(pl->d_steps);
+        delete[] pl->h_steps;
+        delete pl;
+        return cuda_fail(e, "plan upload");
+    }
+    *out = pl;
+    return MBQC_OK;
+}
+
+void mbqc_plan_destroy(mbqc_plan* plan) {
+    if (!plan) return;
+    if (plan->d_steps) cudaFree(plan->d_steps);
+    delete[] plan->h_steps;
+    delete plan;
+}
+
+int32_t mbqc_plan_window(const mbqc_plan* plan) { return plan ? plan->tab.window : -1; }
+int32_t mbqc_plan_num_steps(const mbqc_plan* plan) { return plan ? plan->tab.n_steps : -1; }
+int32_t mbqc_plan_num_outputs(const mbqc_plan* plan) { return plan ? plan->tab.n_out : -1; }
+
+}  // extern "C"
+
+static int check_batch_args(const mbqc_plan* plan, const double* d_angles, int64_t stride,
+                            const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out) {
+    if (!plan) return fail(MBQC_E_ARG, "plan is NULL");
+    if (batch < 0) return fail(MBQC_E_ARG, "batch < 0");
+    if (plan->tab.n_angles > 0 && !d_angles) return fail(MBQC_E_ARG, "d_angles is NULL");
+    if (stride < plan->tab.n_angles) return fail(MBQC_E_ARG, "angle_stride %lld < n_angles %d", (long long)stride, plan->tab.n_angles);
+    if (input_mode < MBQC_INPUT_PLUS || input_mode > MBQC_INPUT_BATCH) return fail(MBQC_E_ARG, "input_mode %d unknown", input_mode);
+    if (input_mode != MBQC_INPUT_PLUS && !d_inputs) return fail(MBQC_E_ARG, "d_inputs is NULL");
+    if (!d_out) return fail(MBQC_E_ARG, "d_out is NULL");
+    return MBQC_OK;
+}
+
+static void fill_sv_params(SvBatchParams& p, const mbqc_plan* plan, const double* d_angles,
+                           int64_t stride, const void* d_inputs, int32_t input_mode, int64_t batch,
+                           void* d_out, int32_t* d_status) {
+    memset(&p, 0, sizeof(p));
+    p.tab = plan->tab;
+    p.steps = plan->d_steps;
+    p.angles = d_angles;
+    p.stride = stride;
+    p.inputs = (const double2*)d_inputs;
+    p.input_mode = input_mode;
+    p.batch = batch;
+    p.out = (double2*)d_out;
+    p.status = d_status;
+}
+
+template <bool DM>
+static int launch_sv_reg(const SvBatchParams& p, cudaStream_t st) {
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
+    const size_t smem = DM ? ((size_t)threads << p.tab.n_out) * sizeof(double2) : 0;
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, threads, smem, st>>>(p);
+        return after_launch("sv_reg_kernel");
+    };
+    switch (p.tab.window) {
+        case 1: return go(sv_reg_kernel<1, DM>);
+        case 2: return go(sv_reg_kernel<2, DM>);
+        case 3: return go(sv_reg_kernel<3, DM>);
+        case 4: return go(sv_reg_kernel<4, DM>);
+        default: return go(sv_reg_kernel<5, DM>);
+    }
+}
+
+static int launch_sv(const SvBatchParams& p, int out_form, cudaStream_t st) {
+    const int w = p.tab.window;
+    if (w <= MBQC_MAX_WINDOW_REG)
+        return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, st) : launch_sv_reg<false>(p, st);
+    if (w > MBQC_MAX_WINDOW_SMEM_SV)
+        return fail(MBQC_E_UNSUPPORTED, "batched SV covers window <= %d (got %d); use the streaming calls", MBQC_MAX_WINDOW_SMEM_SV, w);
+    // threads per sample: one per pair up to 256
+    int tps_log2 = w - 1;
+    if (tps_log2 > 8) tps_log2 = 8;
+    const int tps = 1 << tps_log2;
+    int spb = 256 / tps;
+    if (spb < 1) spb = 1;
+    const size_t smem = (size_t)spb * (16ull << w);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)((p.batch + spb - 1) / spb);
+    sv_smem_kernel<<<blocks, tps * spb, smem, st>>>(p, tps_log2, spb, out_form == MBQC_OUT_DM ? 1 : 0);
+    return after_launch("sv_smem_kernel");
+}
+
+extern "C" {
+
+int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                      int32_t out_form, int32_t* d_status, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
+    if (rc) return rc;
+    if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
+    if (batch == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
+    return launch_sv(p, out_form, (cudaStream_t)stream);
+}
+
+int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                      int8_t* d_outcomes, int32_t* d_status, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
+    if (rc) return rc;
+    const int w = plan->tab.window;
+    if (w > MBQC_MAX_WINDOW_SMEM_DM)
+        return fail(MBQC_E_UNSUPPORTED, "batched DM covers window <= %d (got %d)", MBQC_MAX_WINDOW_SMEM_DM, w);
+    if (batch == 0) return MBQC_OK;
+    DmBatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.tab = plan->tab;
+    p.steps = plan->d_steps;
+    p.angles = d_angles;
+    p.stride = angle_stride;
+    p.inputs = (const double2*)d_inputs;
+    p.input_mode = input_mode;
+    p.batch = batch;
+    p.out = (double2*)d_out;
+    p.outcomes = d_outcomes;
+    p.status = d_status;
+    const unsigned ngroups = 1u << (2 * w - 2);
+    int tps_log2 = ilog2_ceil((ngroups + 1) / 2);  // two 4-groups per thread
+    if (tps_log2 > 8) tps_log2 = 8;
+    const int tps = 1 << tps_log2;
+    const size_t per_sample = ((size_t)(1u << (2 * w)) + (1u << w)) * 16;
+    int spb = 256 / tps;
+    while (spb > 1 && spb * per_sample > 96 * 1024) spb >>= 1;
+    if (spb < 1) spb = 1;
+    const size_t smem = spb * per_sample;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(dm_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
+    dm_smem_kernel<<<blocks, tps * spb, smem, (cudaStream_t)stream>>>(p, tps_log2, spb);
+    return after_launch("dm_smem_kernel");
+}
+
+int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                        const void* d_inputs, int32_t input_mode, int64_t batch,
+                        const void* d_target, double shift, double* d_grad, double* d_cost,
+                        int32_t* d_status, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_grad);
+    if (rc) return rc;
+    if (!d_target) return fail(MBQC_E_ARG, "d_target is NULL");
+    if (!(shift != 0.0)) return fail(MBQC_E_ARG, "shift must be non-zero");
+    const int w = plan->tab.window;
+    if (w > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "fused gradient covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
+    if (batch == 0 || plan->tab.n_angles == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, nullptr, d_status);
+    p.target = (const double2*)d_target;
+    p.shift = shift;
+    p.grad = d_grad;
+    p.cost = d_cost;
+    const int threads = 128;
+    const int64_t total = batch * plan->tab.n_angles;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (w) {
+        case 1: sv_reg_grad_kernel<1><<<blocks, threads, 0, st>>>(p); break;
+        case 2: sv_reg_grad_kernel<2><<<blocks, threads, 0, st>>>(p); break;
+        case 3: sv_reg_grad_kernel<3><<<blocks, threads, 0, st>>>(p); break;
+        case 4: sv_reg_grad_kernel<4><<<blocks, threads, 0, st>>>(p); break;
+        default: sv_reg_grad_kernel<5><<<blocks, threads, 0, st>>>(p); break;
+    }
+    return after_launch("sv_reg_grad_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,299 @@
+// Batched state-vector pattern kernels: the whole pattern (all measurements) in ONE launch.
+//
+//   sv_reg_kernel<W>   w <= 5: one thread per angle set, the 2^w amplitudes live in registers
+//   sv_smem_kernel     6 <= w <= 12: one thread group per angle set, amplitudes in shared memory
+//
+// Replaces NumpySimulatorSV.run / measure / measure_ment / reset and the helpers they call
+// (mentpy/simulators/np_simulator_sv.py:164-358, calculator/state_ops.py:42-74,
+// operators/gates.py:62-72,127-143) -- see common.cuh for the per-measurement identity.
+#pragma once
+#include "common.cuh"
+
+namespace mbqc {
+
+struct SvBatchParams {
+    PlanTables tab;
+    const StepDev* __restrict__ steps;
+    const double* __restrict__ angles;  // [B][stride]
+    int64_t stride;
+    const double2* __restrict__ inputs;
+    int32_t input_mode;
+    int64_t batch;
+    double2* __restrict__ out;  // [B][2^k]
+    int32_t* __restrict__ status;
+    // parameter-shift support (grad kernels): unused by the plain run
+    const double2* __restrict__ target;
+    double shift;
+    double* __restrict__ grad;
+    double* __restrict__ cost;
+};
+
+// ---- one measurement on a register-resident window ---------------------------------------------
+template <int W, int S>
+__device__ __forceinline__ void reg_stage(double (&re)[1 << W], double (&im)[1 << W], double c,
+                                          double s, uint32_t flipmask) {
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) {
+        if (i & (1 << S)) continue;
+        const int j = i | (1 << S);
+        // t = a_i + (c - i s) a_j
+        const double tr = fma(c, re[j], fma(s, im[j], re[i]));
+        const double ti = fma(c, im[j], fma(-s, re[j], im[i]));
+        re[i] = tr;
+        im[i] = ti;
+        const uint32_t sb = (flipmask << (31 - j)) & 0x80000000u;
+        re[j] = flip_sign(tr, sb);
+        im[j] = flip_sign(ti, sb);
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void reg_step(double (&re)[1 << W], double (&im)[1 << W], int slot,
+                                         double c, double s, uint32_t flipmask) {
+    switch (slot) {
+        case 0: reg_stage<W, 0>(re, im, c, s, flipmask); break;
+        case 1: if constexpr (W > 1) reg_stage<W, 1>(re, im, c, s, flipmask); break;
+        case 2: if constexpr (W > 2) reg_stage<W, 2>(re, im, c, s, flipmask); break;
+        case 3: if constexpr (W > 3) reg_stage<W, 3>(re, im, c, s, flipmask); break;
+        case 4: if constexpr (W > 4) reg_stage<W, 4>(re, im, c, s, flipmask); break;
+        default: break;
+    }
+}
+
+// Evolve one sample through the whole pattern.  Returns the squared norm over the output entries;
+// (zr, zi) accumulates the unnormalised reference phase prod (1 + e^{i theta}).
+template <int W>
+__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, int64_t b, int shift_col,
+                                                double shift, double (&re)[1 << W],
+                                                double (&im)[1 << W], double& zr, double& zi) {
+    constexpr int N = 1 << W;
+    const PlanTables& t = p.tab;
+    if (p.input_mode == MBQC_INPUT_PLUS) {
+        const double a = t.init_scale * exp2(-0.5 * t.n_in);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            re[i] = flip_sign(a, (t.init_sign << (31 - i)) & 0x80000000u);
+            im[i] = 0.0;
+        }
+    } else {
+        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double2 v = __ldg(in + t.init_src[i]);
+            const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
+            re[i] = flip_sign(v.x * t.init_scale, sb);
+            im[i] = flip_sign(v.y * t.init_scale, sb);
+        }
+    }
+    zr = 1.0;
+    zi = 0.0;
+    const double* row = p.angles + b * p.stride;
+    const int M = t.n_steps;
+    for (int m = 0; m < M; ++m) {
+        const StepDev st = p.steps[m];
+        double c = st.fc, s = st.fs;
+        if (st.angle_idx >= 0) {
+            double th = __ldg(row + st.angle_idx);
+            if (st.angle_idx == shift_col) th += shift;
+            sincos(th, &s, &c);
+        }
+        // reference global phase factor (1 + e^{i theta}), normalised at the end
+        const double pr = 1.0 + c, pi = s;
+        const double nzr = zr * pr - zi * pi;
+        zi = zr * pi + zi * pr;
+        zr = nzr;
+        reg_step<W>(re, im, st.slot, c, s, st.flipmask);
+        if ((m & 15) == 15) {  // keep magnitudes bounded on long patterns
+            double n2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+            const double r = rsqrt(n2);
+            const double rz = rsqrt(zr * zr + zi * zi);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                re[i] *= r;
+                im[i] *= r;
+            }
+            zr *= rz;
+            zi *= rz;
+        }
+    }
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (t.out_dst[i] >= 0) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+    return n2;
+}
+
+// DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
+// (np_simulator_sv.py:292-293, the reference's default output form); the CTA stages its
+// normalised amplitudes in shared memory and writes the outer products fully coalesced.
+template <int W, bool DM>
+__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvBatchParams p) {
+    constexpr int N = 1 << W;
+    extern __shared__ double2 stage[];  // DM only: [blockDim][2^k]
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b < p.batch;
+    const int k = p.tab.n_out;
+    if (live) {
+        double re[N], im[N], zr, zi;
+        const double n2 = sv_reg_evolve<W>(p, b, -1, 0.0, re, im, zr, zi);
+        const double zn = zr * zr + zi * zi;
+        const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
+        if (p.status) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+        const double r = rsqrt(n2) * rsqrt(zn);
+        const double ur = zr * r, ui = zi * r;  // unit phase / norm
+        double2* o = DM ? (stage + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int d = p.tab.out_dst[i];
+            if (d >= 0) o[d] = make_double2(re[i] * ur - im[i] * ui, re[i] * ui + im[i] * ur);
+        }
+    }
+    if constexpr (DM) {
+        __syncthreads();
+        const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+        const int64_t nlive = min((int64_t)blockDim.x, p.batch - b0);
+        const int64_t total = nlive << (2 * k);
+        double2* o = p.out + (b0 << (2 * k));
+        const uint32_t km = (1u << k) - 1u;
+        for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+            const double2* sv = stage + ((e >> (2 * k)) << k);
+            const double2 x = sv[(e >> k) & km], y = sv[e & km];
+            o[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
+        }
+    }
+}
+
+// ---- shared-memory variant for 6 <= w <= 12 -----------------------------------------------------
+// A group of TPS = 2^tps_log2 threads cooperates on one sample; SPB samples per CTA.
+
+// sum over the threads of one sample group (all threads of the CTA must call this)
+__device__ __forceinline__ double group_sum(double v, int tps_log2, int ls, double* red) {
+    if (tps_log2 <= 5) {
+        for (int o = (1 << tps_log2) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const int w0 = (ls << tps_log2) >> 5, nw = 1 << (tps_log2 - 5);
+    double tot = 0.0;
+    for (int k = 0; k < nw; ++k) tot += red[w0 + k];
+    return tot;
+}
+
+__global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_log2, int spb, int dm_out) {
+    extern __shared__ double2 smem[];
+    __shared__ double red[32];
+    const PlanTables& t = p.tab;
+    const int w = t.window;
+    const int tps = 1 << tps_log2;
+    const int ls = threadIdx.x >> tps_log2;
+    const int tid = threadIdx.x & (tps - 1);
+    const int64_t b = (int64_t)blockIdx.x * spb + ls;
+    const bool live = b < p.batch;
+    double2* psi = smem + ((size_t)ls << w);
+    const uint64_t n = 1ull << w;
+    if (live) {
+        const double2* in = (p.input_mode == MBQC_INPUT_PLUS)
+                                ? nullptr
+                                : p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+        const double a0 = t.init_scale * exp2(-0.5 * t.n_in);
+        for (uint64_t i = tid; i < n; i += tps) {
+            double2 v = make_double2(a0, 0.0);
+            if (in) {
+                v = __ldg(in + init_source_index(t, i));
+                v.x *= t.init_scale;
+                v.y *= t.init_scale;
+            }
+            if (init_sign_bit(t, i)) {
+                v.x = -v.x;
+                v.y = -v.y;
+            }
+            psi[i] = v;
+        }
+    }
+    __syncthreads();
+    double zr = 1.0, zi = 0.0;
+    const double* row = p.angles + (live ? b : 0) * p.stride;
+    const uint64_t half = n >> 1;
+    for (int m = 0; m < t.n_steps; ++m) {
+        const StepDev st = p.steps[m];
+        double c = st.fc, s = st.fs;
+        if (st.angle_idx >= 0) sincos(__ldg(row + st.angle_idx), &s, &c);
+        const double pr = 1.0 + c, pi = s;
+        const double nzr = zr * pr - zi * pi;
+        zi = zr * pi + zi * pr;
+        zr = nzr;
+        const uint64_t bit = 1ull << st.slot;
+        if (live) {
+            for (uint64_t g = tid; g < half; g += tps) {
+                const uint64_t i0 = insert_zero(g, st.slot);
+                const double2 a = psi[i0], bb = psi[i0 | bit];
+                double2 tt;
+                tt.x = fma(c, bb.x, fma(s, bb.y, a.x));
+                tt.y = fma(c, bb.y, fma(-s, bb.x, a.y));
+                psi[i0] = tt;
+                if (parity64(i0 & st.nbr_mask)) {
+                    tt.x = -tt.x;
+                    tt.y = -tt.y;
+                }
+                psi[i0 | bit] = tt;
+            }
+        }
+        __syncthreads();
+        if ((m & 7) == 7) {  // keep magnitudes bounded on long patterns
+            double n2 = 0.0;
+            if (live)
+                for (uint64_t i = tid; i < n; i += tps) {
+                    const double2 v = psi[i];
+                    n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
+                }
+            n2 = group_sum(n2, tps_log2, ls, red);
+            const double r = rsqrt(n2);
+            if (live)
+                for (uint64_t i = tid; i < n; i += tps) {
+                    psi[i].x *= r;
+                    psi[i].y *= r;
+                }
+            const double rz = rsqrt(zr * zr + zi * zi);
+            zr *= rz;
+            zi *= rz;
+            __syncthreads();
+        }
+    }
+    // output gather + norm over the output entries
+    const uint32_t no = 1u << t.n_out;
+    double n2 = 0.0;
+    if (live)
+        for (uint32_t o = tid; o < no; o += tps) {
+            const double2 v = psi[output_state_index(t, o)];
+            n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
+        }
+    n2 = group_sum(n2, tps_log2, ls, red);
+    if (!live) return;
+    const double zn = zr * zr + zi * zi;
+    const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
+    if (p.status && tid == 0) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+    const double r = rsqrt(n2) * rsqrt(zn);
+    const double ur = zr * r, ui = zi * r;
+    if (!dm_out) {
+        double2* o = p.out + (b << t.n_out);
+        for (uint32_t k = tid; k < no; k += tps) {
+            const double2 v = psi[output_state_index(t, k)];
+            o[k] = make_double2(v.x * ur - v.y * ui, v.x * ui + v.y * ur);
+        }
+    } else {  // |psi><psi|: the global phase cancels
+        const double r2 = r * r * zn;
+        double2* o = p.out + (b << (2 * t.n_out));
+        for (uint32_t e = tid; e < no * no; e += tps) {
+            const double2 x = psi[output_state_index(t, e >> t.n_out)];
+            const double2 y = psi[output_state_index(t, e & (no - 1))];
+            o[e] = make_double2((x.x * y.x + x.y * y.y) * r2, (x.y * y.x - x.x * y.y) * r2);
+        }
+    }
+}
+
+}  // namespace mbqc

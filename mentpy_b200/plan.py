@@ -1,0 +1,284 @@
+"""Lower an MBQCircuit + window + schedule to the flat plan the CUDA kernels execute.
+
+This is the host half of what NumpySimulatorSV/DM.__init__ do per simulator
+(mentpy/simulators/np_simulator_sv.py:38-128, np_simulator_dm.py:33-115): choose the schedule,
+promote the default window, validate sizes (same exceptions), find which qubits sit in the first
+window and which CZs act inside it -- plus the bookkeeping the reference redoes on every
+measurement (np_simulator_sv.py:130-142, :207-223: who is in the window, who is the new qubit,
+which of its neighbours are present), resolved once here into per-step records.
+
+Slot recycling: qubits are never shifted.  The first window puts schedule[p] at slot w-1-p (the
+reference's big-endian layout); afterwards the qubit appended after measurement m takes the slot
+the measured qubit just freed.  The output permutation (np_simulator_sv.py:286-290,
+np_simulator_dm.py:267-273) becomes a slot list.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+_PLANE_CODE = {"XY": _lib.PLANE_XY, "X": _lib.PLANE_XY, "Y": _lib.PLANE_XY,
+               "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ}
+
+
+@dataclass
+class StepRecord:
+    node: int
+    slot: int
+    angle_idx: int          # index into trainable_nodes, or -1
+    plane: int
+    fixed_angle: Optional[float]
+    fixed_cos: float
+    fixed_sin: float
+    append: bool
+    new_node: Optional[int]
+    nbr_mask: int
+    dropped_neighbours: List[int] = field(default_factory=list)
+
+
+@dataclass
+class LoweredPlan:
+    window: int
+    n_nodes: int
+    schedule: List[int]
+    schedule_measure: List[int]
+    steps: List[StepRecord]
+    input_nodes: List[int]
+    input_slot: List[int]
+    init_cz_mask: List[int]
+    output_nodes: List[int]          # order of the output index, first = MSB
+    output_slot: List[int]
+    n_angles: int
+    mixed: bool
+    first_window: List[int]
+
+    def window_nodes_after(self, n_done: int) -> List[int]:
+        """Reference window content (position 0 first) after n_done measurements."""
+        return self.schedule[n_done: n_done + self.window]
+
+    def slot_of_after(self, n_done: int) -> Dict[int, int]:
+        slot = {v: self.window - 1 - p for p, v in enumerate(self.first_window)}
+        for st in self.steps[:n_done]:
+            del slot[st.node]
+            if st.append:
+                slot[st.new_node] = st.slot
+        return slot
+
+
+def _fixed_cos_sin(plane: str, angle):
+    # exact values for the Pauli planes (the reference uses the Pauli matrices directly,
+    # mentpy/operators/ment.py:233-235); np.cos/np.sin otherwise, as ment.py:230 does
+    if plane == "X":
+        return 1.0, 0.0
+    if plane == "Y":
+        return 0.0, 1.0
+    return float(np.cos(angle)), float(np.sin(angle))
+
+
+def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = None,
+          mixed: bool = False) -> LoweredPlan:
+    nodes = list(circuit.graph.nodes())
+    n_nodes = len(nodes)
+    outputs_excluded = circuit.quantum_output_nodes if mixed else circuit.output_nodes
+
+    if not mixed:
+        for v in nodes:
+            m = circuit[v]
+            if m is not None and m.plane not in ("X", "Y", "XY"):
+                raise ValueError(f"Node {v} has plane {m.plane}, but only XY plane is supported.")
+
+    if schedule is not None:
+        schedule = list(schedule)
+    elif circuit.measurement_order is not None:
+        schedule = list(circuit.measurement_order)
+        if window_size == 1 and circuit.flow is not None:
+            window_size = len(circuit.input_nodes) + 1
+    else:
+        raise ValueError(
+            "Schedule must be provided for numpy simulator as the MBQCircuit does not have a flow."
+        )
+    schedule_measure = [v for v in schedule if v not in outputs_excluded]
+
+    n_in = len(circuit.input_nodes)
+    if n_in > window_size:
+        raise ValueError(
+            f"Input state has {n_in} qubits, but window size is set to {window_size}."
+            " Input state must have at most as many qubits as the window size minus one."
+        )
+    if window_size > len(schedule_measure):
+        raise ValueError(
+            f"Window size is set to {window_size}, but schedule only has {len(schedule_measure)} measurements."
+        )
+    if sorted(schedule) != sorted(nodes):
+        raise ValueError("The schedule must visit every node of the graph exactly once.")
+    n_meas = len(schedule_measure)
+    if schedule[:n_meas] != schedule_measure:
+        # the reference would measure window position 0 with another node's Ment here
+        # (np_simulator_sv.py:169-172 vs :130-135); refuse instead of reproducing garbage
+        raise ValueError("Unmeasured output nodes must come last in the schedule.")
+    if set(schedule[:n_in]) != set(circuit.input_nodes):
+        raise ValueError(
+            f"Both lists must have the same elements, but source={circuit.input_nodes} "
+            f"and target={schedule[:n_in]}"
+        )
+    if not mixed:
+        for v in circuit.output_nodes:
+            if circuit[v] is not None:
+                raise NotImplementedError(
+                    "Measured output nodes are not supported on the state-vector path "
+                    "(the reference indexes them by node label, np_simulator_sv.py:279-284)."
+                )
+    if window_size > _lib.MAX_WINDOW:
+        raise NotImplementedError(f"window_size {window_size} > {_lib.MAX_WINDOW}")
+
+    w = window_size
+    first_window = schedule[:w]
+    slot_of: Dict[int, int] = {v: w - 1 - p for p, v in enumerate(first_window)}
+    init_cz = [0] * w
+    for a, b in circuit.graph.edges():
+        if a in slot_of and b in slot_of and a != b:
+            lo, hi = sorted((slot_of[a], slot_of[b]))
+            init_cz[lo] ^= 1 << hi
+    input_slot = [slot_of[v] for v in circuit.input_nodes]
+
+    trainable = list(circuit.trainable_nodes)
+    steps: List[StepRecord] = []
+    for m, node in enumerate(schedule_measure):
+        ment = circuit[node]
+        plane = ment.plane
+        if plane not in _PLANE_CODE:
+            raise NotImplementedError(
+                f"Node {node}: plane {plane} is not supported on the CUDA path "
+                "(plane Z is sampled by the reference even under force0, np_simulator_dm.py:329-333)."
+            )
+        if node in trainable:
+            angle_idx, fixed, fc, fs = trainable.index(node), None, 1.0, 0.0
+        else:
+            if ment.angle is None:
+                raise ValueError(f"Node {node} is not trainable but has no fixed angle.")
+            angle_idx, fixed = -1, ment.angle
+            fc, fs = _fixed_cos_sin(plane, ment.angle)
+        slot = slot_of.pop(node)
+        done = m + 1
+        append = done + w <= n_nodes
+        new_node, mask, dropped = None, 0, []
+        if append:
+            new_node = schedule[done + w - 1]
+            for nb in circuit.graph.neighbors(new_node):
+                if nb in slot_of:
+                    mask |= 1 << slot_of[nb]
+                elif nb in schedule[:done]:
+                    dropped.append(nb)  # already measured: the reference silently skips this CZ
+            slot_of[new_node] = slot
+        steps.append(StepRecord(node, slot, angle_idx, _PLANE_CODE[plane], fixed, fc, fs, append,
+                                new_node, mask, dropped))
+
+    remaining = schedule[n_meas:]
+    out_order = list(circuit.quantum_output_nodes if mixed else circuit.output_nodes)
+    if set(out_order) != set(remaining):
+        raise ValueError(f"Both lists must have the same elements, but source={remaining} and target={out_order}")
+    output_slot = [slot_of[v] for v in out_order]
+    if len(out_order) > _lib.MAX_IO or n_in > _lib.MAX_IO:
+        raise NotImplementedError(f"more than {_lib.MAX_IO} input/output qubits")
+    return LoweredPlan(w, n_nodes, schedule, schedule_measure, steps, list(circuit.input_nodes),
+                       input_slot, init_cz, out_order, output_slot, len(trainable), mixed,
+                       first_window)
+
+
+def window_is_valid(plan: LoweredPlan) -> bool:
+    """True when no CZ was dropped because a neighbour had already left the window."""
+    return all(not st.dropped_neighbours for st in plan.steps)
+
+
+# ---------------------------------------------------------------------------------------------
+# noise: Kraus set -> block-form coefficients (include/mbqc_b200.h: mbqc_noise)
+# ---------------------------------------------------------------------------------------------
+def kraus_set(kind: str, p: float = 0.0, gamma: Optional[float] = None, p_gad: float = 0.5):
+    """Kraus operators of the single-qubit channels the reference can request from PennyLane
+    (mentpy/simulators/pennylane_simulator.py:123-136; PennyLane's published definitions)."""
+    eye = np.eye(2, dtype=complex)
+    x = np.array([[0, 1], [1, 0]], dtype=complex)
+    y = np.array([[0, -1j], [1j, 0]], dtype=complex)
+    z = np.array([[1, 0], [0, -1]], dtype=complex)
+    g = p if gamma is None else gamma
+    if kind == "depolarizing":
+        return [np.sqrt(1 - p) * eye, np.sqrt(p / 3) * x, np.sqrt(p / 3) * y, np.sqrt(p / 3) * z]
+    if kind == "phase_flip":
+        return [np.sqrt(1 - p) * eye, np.sqrt(p) * z]
+    if kind == "bit_flip":
+        return [np.sqrt(1 - p) * eye, np.sqrt(p) * x]
+    damp0 = np.array([[1, 0], [0, np.sqrt(1 - g)]], dtype=complex)
+    if kind == "amplitude_damping":
+        return [damp0, np.array([[0, np.sqrt(g)], [0, 0]], dtype=complex)]
+    if kind == "phase_damping":
+        return [damp0, np.array([[0, 0], [0, np.sqrt(g)]], dtype=complex)]
+    if kind == "generalized_amplitude_damping":
+        return [np.sqrt(p_gad) * damp0,
+                np.sqrt(p_gad) * np.array([[0, np.sqrt(g)], [0, 0]], dtype=complex),
+                np.sqrt(1 - p_gad) * np.array([[np.sqrt(1 - g), 0], [0, 1]], dtype=complex),
+                np.sqrt(1 - p_gad) * np.array([[0, 0], [np.sqrt(g), 0]], dtype=complex)]
+    raise ValueError(f"Unrecognized circuit noise: {kind}")
+
+
+def noise_from_kraus(kraus) -> "_lib.Noise":
+    """Superoperator sum_k K (x) conj(K) -> the 6 real block coefficients; rejects channels whose
+    block form needs more (populations feeding coherences, complex couplings)."""
+    s = np.zeros((4, 4), dtype=complex)  # (a,b) <- (c,d): sum K[a,c] conj(K[b,d])
+    for k in kraus:
+        k = np.asarray(k, dtype=complex)
+        s += np.kron(k, np.conj(k))
+    allowed = np.zeros((4, 4), dtype=bool)
+    for i, j in ((0, 0), (0, 3), (3, 0), (3, 3), (1, 1), (1, 2), (2, 1), (2, 2)):
+        allowed[i, j] = True
+    if np.abs(s[~allowed]).max() > 1e-14 or np.abs(s.imag).max() > 1e-14:
+        raise NotImplementedError("channel does not have the supported block form")
+    if abs(s[1, 1] - s[2, 2]) > 1e-14 or abs(s[1, 2] - s[2, 1]) > 1e-14:
+        raise NotImplementedError("channel does not have the supported block form")
+    if abs(s[0, 0] + s[3, 0] - 1) > 1e-12 or abs(s[0, 3] + s[3, 3] - 1) > 1e-12:
+        raise ValueError("channel is not trace preserving")
+    nz = _lib.Noise()
+    nz.pop[0], nz.pop[1], nz.pop[2], nz.pop[3] = s[0, 0].real, s[0, 3].real, s[3, 0].real, s[3, 3].real
+    nz.coh_g, nz.coh_d = s[1, 1].real, s[1, 2].real
+    return nz
+
+
+# ---------------------------------------------------------------------------------------------
+# device plan handle
+# ---------------------------------------------------------------------------------------------
+class DevicePlan:
+    """Owns the opaque mbqc_plan* created on the current CUDA device."""
+
+    def __init__(self, plan: LoweredPlan, noise: Optional["_lib.Noise"] = None,
+                 n_steps: Optional[int] = None, output_slot: Optional[List[int]] = None):
+        lib = _lib.load()
+        steps = plan.steps if n_steps is None else plan.steps[:n_steps]
+        arr = (_lib.Step * max(len(steps), 1))()
+        for i, st in enumerate(steps):
+            arr[i].slot, arr[i].angle_idx, arr[i].plane = st.slot, st.angle_idx, st.plane
+            arr[i].flags = _lib.STEP_APPEND if st.append else 0
+            arr[i].fixed_cos, arr[i].fixed_sin = st.fixed_cos, st.fixed_sin
+            arr[i].nbr_mask = st.nbr_mask
+        out_slot = plan.output_slot if output_slot is None else output_slot
+        in_arr = (C.c_int32 * max(len(plan.input_slot), 1))(*plan.input_slot)
+        cz_arr = (C.c_uint64 * plan.window)(*plan.init_cz_mask)
+        out_arr = (C.c_int32 * max(len(out_slot), 1))(*out_slot)
+        handle = C.c_void_p()
+        _lib.check(lib.mbqc_plan_create(arr, len(steps), plan.window, len(plan.input_slot),
+                                        len(out_slot), plan.n_angles, in_arr, cz_arr, out_arr,
+                                        C.byref(noise) if noise is not None else None,
+                                        C.byref(handle)))
+        self.handle = handle
+        self.n_out = len(out_slot)
+        self.n_steps = len(steps)
+        self._lib = lib
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                self._lib.mbqc_plan_destroy(h)
+            except Exception:
+                pass

@@ -1,0 +1,349 @@
+"""CUDA backends behind the PatternSimulator facade: `cuda-sv` and `cuda-dm`.
+
+Drop-in twins of NumpySimulatorSV (mentpy/simulators/np_simulator_sv.py:35-384) and
+NumpySimulatorDM (np_simulator_dm.py:29-380): same constructor kwargs (`window_size`, `schedule`,
+`force0`, `dev_mode`, `wires`; unknown kwargs ignored), same stateful `measure / run / reset`
+contract and exceptions, same return conventions (fresh complex128 numpy arrays, big-endian
+output order).  All arithmetic runs in the sm_100a kernels through the C ABI
+(include/mbqc_b200.h); there is no CPU path.  Additive API: `run_batch` evaluates B angle vectors
+in one launch (numpy in -> numpy out with host<->device copies; torch CUDA tensor in -> torch out,
+fully asynchronous on the current stream).
+"""
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..plan import DevicePlan, LoweredPlan, kraus_set, lower, noise_from_kraus
+from .backend_base import BaseSimulator
+
+_NOISE_KINDS = ("depolarizing", "amplitude_damping", "phase_damping", "phase_flip", "bit_flip",
+                "generalized_amplitude_damping")
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mentpy_b200 needs a CUDA device: there is no CPU fallback.")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class _CudaPatternBase(BaseSimulator):
+    mixed = False
+
+    def __init__(self, mbqcircuit, input_state: np.ndarray = None, **kwargs) -> None:
+        super().__init__(mbqcircuit, input_state)
+        self.window_size = kwargs.pop("window_size", 1)
+        self.schedule = kwargs.pop("schedule", None)
+        self.force0 = kwargs.pop("force0", True)
+        self.dev_mode = kwargs.pop("dev_mode", False)
+        self.wires = kwargs.pop("wires", None)
+        self.device = kwargs.pop("device", None)
+        if not self.force0:
+            raise NotImplementedError("Numpy simulator does not support force0=False.")
+        if self.dev_mode:
+            raise NotImplementedError("dev_mode scheduling is not supported by the CUDA backends.")
+        self._noise = self._parse_noise(kwargs)
+        self.plan: LoweredPlan = lower(mbqcircuit, self.window_size, self.schedule, mixed=self.mixed)
+        self.window_size = self.plan.window
+        self.schedule = self.plan.schedule
+        self.schedule_measure = self.plan.schedule_measure
+        if input_state is None:
+            n_in = len(mbqcircuit.input_nodes)
+            input_state = np.full(2**n_in, 2.0 ** (-n_in / 2))
+        self.input_state = np.asarray(input_state)
+        self.current_measurement = 0
+        self._angles_seen = np.zeros(max(self.plan.n_angles, 1))
+        self._full: Optional[DevicePlan] = None
+        self._prefix = {}
+        self._d_input = None
+        self.last_status = None
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _parse_noise(self, kwargs):
+        return None
+
+    def _dev(self) -> torch.device:
+        _require_cuda()
+        if self.device is None:
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self.device)
+
+    def _full_plan(self) -> DevicePlan:
+        if self._full is None:
+            with torch.cuda.device(self._dev()):
+                self._full = DevicePlan(self.plan, self._noise)
+        return self._full
+
+    def _prefix_plan(self, n_done: int) -> Tuple[DevicePlan, List[int]]:
+        """Plan of the first n_done measurements whose 'outputs' are the whole live window in the
+        reference's order (position 0 = MSB) -- backs `measure()` / `qstate`."""
+        if n_done not in self._prefix:
+            nodes = self.plan.window_nodes_after(n_done)
+            slot = self.plan.slot_of_after(n_done)
+            with torch.cuda.device(self._dev()):
+                self._prefix[n_done] = (DevicePlan(self.plan, self._noise_for_prefix(), n_steps=n_done,
+                                                   output_slot=[slot[v] for v in nodes]), nodes)
+        return self._prefix[n_done]
+
+    def _noise_for_prefix(self):
+        return None
+
+    def _device_input(self, dev):
+        st = np.ascontiguousarray(self.input_state, dtype=np.complex128)
+        if st.shape != (2 ** len(self.plan.input_nodes),):
+            raise ValueError(
+                f"Input state has shape {st.shape}, expected ({2 ** len(self.plan.input_nodes)},)."
+            )
+        return torch.from_numpy(st).to(dev)
+
+    def _stage_inputs(self, input_states, batch, dev):
+        """-> (tensor|None, input_mode)"""
+        if input_states is None:
+            if self._d_input is None or self._d_input.device != dev:
+                self._d_input = self._device_input(dev)
+            return self._d_input, _lib.INPUT_SHARED
+        if isinstance(input_states, torch.Tensor):
+            t = input_states.to(device=dev, dtype=torch.complex128).contiguous()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(input_states, dtype=np.complex128)).to(dev)
+        dim = 2 ** len(self.plan.input_nodes)
+        if t.dim() == 1:
+            if t.shape[0] != dim:
+                raise ValueError(f"input state must have {dim} amplitudes")
+            return t, _lib.INPUT_SHARED
+        if t.shape != (batch, dim):
+            raise ValueError(f"input_states must have shape ({batch}, {dim}) or ({dim},)")
+        return t, _lib.INPUT_BATCH
+
+    def _stage_angles(self, angles, dev):
+        if isinstance(angles, torch.Tensor):
+            a = angles.to(device=dev, dtype=torch.float64)
+            if a.dim() == 1:
+                a = a[None, :]
+            if a.stride(-1) != 1:
+                a = a.contiguous()
+            on_host = False
+        else:
+            a = np.asarray(angles, dtype=np.float64)
+            if a.ndim == 1:
+                a = a[None, :]
+            a = torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
+            on_host = True
+        if a.dim() != 2 or a.shape[1] != self.plan.n_angles:
+            raise ValueError(
+                f"Number of angles ({a.shape[-1]}) does not match number of trainable nodes ({self.plan.n_angles})."
+            )
+        return a, on_host
+
+    def _check_status(self, status: torch.Tensor):
+        st = status.cpu().numpy()
+        self.last_status = st
+        if (st & _lib.STATUS_BAD_NORM).any():
+            raise ValueError("qstate has nan, you might want to increase the window size")
+        return st
+
+    # -- reference-compatible state machine -----------------------------------------------------
+    def reset(self, input_state: np.ndarray = None):
+        self.current_measurement = 0
+        if input_state is not None:
+            self.input_state = np.asarray(input_state)
+            self._d_input = None
+        self._angles_seen[:] = 0.0
+        self.outcomes = {}
+
+    def current_simulated_nodes(self) -> List[int]:
+        return self.schedule[self.current_measurement: self.current_measurement + self.window_size]
+
+    def current_number_simulated_nodes(self) -> int:
+        return min(self.window_size, len(self.mbqcircuit) - self.current_measurement)
+
+    def _record_angle(self, angle):
+        if self.current_measurement >= len(self.schedule_measure):
+            raise ValueError("No more measurements to be done.")
+        st = self.plan.steps[self.current_measurement]
+        if st.angle_idx >= 0:
+            if angle is None:
+                raise ValueError("Measurement is trainable, please provide an angle.")
+            self._angles_seen[st.angle_idx] = float(angle)
+        elif angle is not None and angle != st.fixed_angle:
+            raise ValueError(f"Measurement has a fixed angle of {round(st.fixed_angle, 4)}")
+        return st
+
+    def find_swaps(self, source, target):
+        """Selection-sort swap list source -> target (np_simulator_sv.py:360-374)."""
+        assert set(source) == set(target), (
+            f"Both lists must have the same elements, but source={source} and target={target}"
+        )
+        work, swaps = list(source), []
+        for i, want in enumerate(target):
+            if work[i] != want:
+                j = work.index(want, i + 1)
+                work[i], work[j] = work[j], work[i]
+                swaps.append((i, j))
+        return swaps
+
+
+class CudaSimulatorSV(_CudaPatternBase):
+    """State-vector backend (`backend="cuda-sv"`)."""
+
+    mixed = False
+
+    def run_batch(self, angles, input_states=None, output_form: str = "sv", check: bool = True):
+        """Evaluate B angle vectors: angles [B,T] -> [B,2^k] ('sv') or [B,2^k,2^k] ('dm')."""
+        form = output_form.lower()
+        if form in ("dm", "densitymatrix"):
+            code = _lib.OUT_DM
+        elif form in ("sv", "statevector"):
+            code = _lib.OUT_SV
+        else:
+            raise ValueError(f"Output form {output_form} is not supported.")
+        return self._run_plan(self._full_plan(), angles, input_states, code, check)
+
+    def _run_plan(self, dplan: DevicePlan, angles, input_states, code, check):
+        dev = self._dev()
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            a, on_host = self._stage_angles(angles, dev)
+            batch = a.shape[0]
+            inp, mode = self._stage_inputs(input_states, batch, dev)
+            dim = 2 ** dplan.n_out
+            shape = (batch, dim) if code == _lib.OUT_SV else (batch, dim, dim)
+            out = torch.empty(shape, dtype=torch.complex128, device=dev)
+            status = torch.empty(batch, dtype=torch.int32, device=dev)
+            _lib.check(lib.mbqc_run_batch_sv(dplan.handle, _ptr(a), a.stride(0), _ptr(inp), mode,
+                                             batch, _ptr(out), code, _ptr(status),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+            if on_host:
+                res = out.cpu().numpy()
+                if check:
+                    self._check_status(status)
+                return res
+            self.last_status = status
+            return out
+
+    def measure(self, angle: float) -> Tuple[np.ndarray, int]:
+        st = self._record_angle(angle)
+        self.current_measurement += 1
+        self.outcomes[st.node] = 0
+        return self.qstate, 0
+
+    @property
+    def qstate(self) -> np.ndarray:
+        """Window state in the reference's layout after `current_measurement` measurements."""
+        dplan, _nodes = self._prefix_plan(self.current_measurement)
+        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, _lib.OUT_SV, True)[0]
+
+    def run(self, angles: List[float], output_form="dm", **kwargs):
+        if kwargs.get("input_state") is not None:
+            self.reset(input_state=kwargs.get("input_state"))
+        if len(angles) != len(self.mbqcircuit.trainable_nodes):
+            raise ValueError(
+                f"Number of angles ({len(angles)}) does not match number of trainable nodes ({len(self.mbqcircuit.trainable_nodes)})."
+            )
+        if self.current_measurement != 0:
+            raise ValueError("No more measurements to be done.")
+        res = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], output_form=output_form)[0]
+        self.current_measurement = len(self.schedule_measure)
+        self._angles_seen[: self.plan.n_angles] = np.asarray(angles, dtype=np.float64)
+        self.outcomes = {v: 0 for v in self.schedule_measure}
+        return res
+
+    def reorder_qubits(self, state, current_order, target_order):
+        """Permute qubits of a host state vector (np_simulator_sv.py:376-384)."""
+        n = len(current_order)
+        t = np.asarray(state).reshape([2] * n)
+        return t.transpose([list(current_order).index(v) for v in target_order]).reshape(-1)
+
+
+class CudaSimulatorDM(_CudaPatternBase):
+    """Density-matrix backend (`backend="cuda-dm"`), optional single-qubit noise
+    (`circuit_noise=<kind>`, `p=`, `gamma=`, `p_gad=` or `kraus=[...]`)."""
+
+    mixed = True
+
+    def _parse_noise(self, kwargs):
+        kind = kwargs.pop("circuit_noise", None)
+        kraus = kwargs.pop("kraus", None)
+        p = kwargs.pop("p", 0.0)
+        gamma = kwargs.pop("gamma", None)
+        p_gad = kwargs.pop("p_gad", 0.5)
+        self.circuit_noise = kind
+        if kraus is not None:
+            return noise_from_kraus(kraus)
+        if kind is None:
+            return None
+        if kind not in _NOISE_KINDS:
+            raise ValueError(f"Unrecognized circuit noise: {kind}")
+        return noise_from_kraus(kraus_set(kind, p=p, gamma=gamma, p_gad=p_gad))
+
+    def _noise_for_prefix(self):
+        return self._noise
+
+    def run_batch(self, angles, input_states=None, check: bool = True, return_outcomes: bool = False):
+        """angles [B,T] -> rho [B,2^k,2^k] (and the outcome record [B,M] if requested)."""
+        return self._run_plan(self._full_plan(), angles, input_states, check, return_outcomes)
+
+    def _run_plan(self, dplan, angles, input_states, check, return_outcomes):
+        dev = self._dev()
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            a, on_host = self._stage_angles(angles, dev)
+            batch = a.shape[0]
+            inp, mode = self._stage_inputs(input_states, batch, dev)
+            dim = 2 ** dplan.n_out
+            out = torch.empty((batch, dim, dim), dtype=torch.complex128, device=dev)
+            status = torch.empty(batch, dtype=torch.int32, device=dev)
+            outc = torch.zeros((batch, max(dplan.n_steps, 1)), dtype=torch.int8, device=dev)
+            _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), a.stride(0), _ptr(inp), mode,
+                                             batch, _ptr(out), _ptr(outc), _ptr(status),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+            if on_host:
+                res = out.cpu().numpy()
+                oc = outc.cpu().numpy()[:, : dplan.n_steps]
+                if check:
+                    self._check_status(status)
+                return (res, oc) if return_outcomes else res
+            self.last_status = status
+            return (out, outc[:, : dplan.n_steps]) if return_outcomes else out
+
+    def measure(self, angle: float, mode="sample") -> Tuple[np.ndarray, int]:
+        st = self._record_angle(angle)
+        self.current_measurement += 1
+        dplan, _nodes = self._prefix_plan(self.current_measurement)
+        rho, oc = self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, True)
+        outcome = int(oc[0, self.current_measurement - 1])
+        self.outcomes[st.node] = outcome
+        return rho[0], outcome
+
+    @property
+    def qstate(self) -> np.ndarray:
+        dplan, _nodes = self._prefix_plan(self.current_measurement)
+        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, False)[0]
+
+    def run(self, angles: List[float], mode="sample", input_state=None):
+        if input_state is not None:
+            self.reset(input_state=input_state)
+        if len(angles) != len(self.mbqcircuit.trainable_nodes):
+            raise ValueError(
+                f"Number of angles ({len(angles)}) does not match number of trainable nodes ({len(self.mbqcircuit.trainable_nodes)})."
+            )
+        if self.current_measurement != 0:
+            raise ValueError("No more measurements to be done.")
+        rho, oc = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], return_outcomes=True)
+        self.current_measurement = len(self.schedule_measure)
+        self._angles_seen[: self.plan.n_angles] = np.asarray(angles, dtype=np.float64)
+        self.outcomes = {v: int(o) for v, o in zip(self.schedule_measure, oc[0])}
+        return rho[0]
+
+    def reorder_qubits(self, state, current_order, target_order):
+        n = len(current_order)
+        perm = [list(current_order).index(v) for v in target_order]
+        st = np.asarray(state)
+        if st.ndim == 1:
+            return st.reshape([2] * n).transpose(perm).reshape(-1)
+        t = st.reshape([2] * (2 * n))
+        return t.transpose(perm + [n + q for q in perm]).reshape(2**n, 2**n)

@@ -1,0 +1,131 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares (no compute calls),
+and the host-side plan lowering reproduces the reference's window bookkeeping."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import mentpy_b200 as mb
+from mentpy_b200 import _lib
+from mentpy_b200.plan import kraus_set, lower, noise_from_kraus, window_is_valid
+from conftest import ROOT, load_golden
+from oracle.pattern_data import PatternData
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mbqc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mbqc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 10
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mbqc_b200.h but not exported"
+    assert sorted(_lib.exported_symbols()) == declared
+    assert b"sm_100a" in lib.mbqc_version()
+
+
+def test_plan_create_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call."""
+    import ctypes as C
+
+    lib = _lib.load()
+    handle = C.c_void_p()
+    step = (_lib.Step * 1)()
+    step[0].slot = 5  # outside a 2-qubit window
+    cz = (C.c_uint64 * 2)(0, 0)
+    io = (C.c_int32 * 1)(0)
+    rc = lib.mbqc_plan_create(step, 1, 2, 1, 1, 1, io, cz, io, None, C.byref(handle))
+    assert rc == _lib.MBQC_E_ARG and b"slot" in lib.mbqc_last_error()
+    rc = lib.mbqc_plan_create(step, 1, 99, 1, 1, 1, io, cz, io, None, C.byref(handle))
+    assert rc == _lib.MBQC_E_ARG
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+
+
+def test_lowering_matches_reference_window_bookkeeping():
+    """Replay the slot plan on the host and compare with the reference's shifting window
+    (np_simulator_sv.py:130-142, :207-223) recorded in the golden patterns."""
+    for rec in load_golden("structures.json")["records"]:
+        name, args, kwargs = rec["spec"]
+        gs = getattr(mb.templates, name)(*args, **kwargs)
+        pat = PatternData.from_json(rec["pattern"])
+        n_meas = len(pat.measurement_order) - len(pat.output_nodes)
+        for w in {len(pat.input_nodes) + 1, min(len(pat.input_nodes) + 3, n_meas)}:
+            if w > n_meas or w < len(pat.input_nodes) or w == 1:
+                continue  # w == 1 is promoted to |I|+1 (np_simulator_sv.py:74-75)
+            pl = lower(gs, window_size=w)
+            sched = pat.measurement_order
+            assert pl.schedule == sched
+            for m, st in enumerate(pl.steps):
+                assert st.node == sched[m]
+                win_after = sched[m + 1: m + 1 + w]
+                assert st.append == (m + 1 + w <= pat.n_nodes)
+                slots = pl.slot_of_after(m + 1)
+                assert sorted(slots) == sorted(win_after)
+                assert len(set(slots.values())) == len(slots)
+                if st.append:
+                    assert st.new_node == win_after[-1]
+                    want = 0
+                    for nb in pat.neighbors(st.new_node):
+                        if nb in win_after[:-1]:
+                            want |= 1 << slots[nb]
+                    assert st.nbr_mask == want
+            assert [pl.slot_of_after(len(pl.steps))[v] for v in pat.output_nodes] == pl.output_slot
+
+
+def test_lowering_errors_mirror_reference():
+    gs = mb.templates.grid_cluster(2, 4)
+    with pytest.raises(ValueError, match="Input state has 2 qubits"):
+        lower(gs, window_size=1, schedule=gs.measurement_order)
+    with pytest.raises(ValueError, match="schedule only has"):
+        lower(gs, window_size=7)
+    gs[1] = mb.Ment(0.2, "XZ")
+    with pytest.raises(ValueError, match="only XY plane is supported"):
+        lower(gs)
+    lower(gs, mixed=True)
+    gs[1] = mb.Ment("Z")
+    with pytest.raises(NotImplementedError):
+        lower(gs, mixed=True)
+    tri = mb.MBQCircuit(mb.GraphState([(0, 1), (1, 2), (2, 0)]), input_nodes=[0], output_nodes=[2])
+    with pytest.raises(ValueError, match="Schedule must be provided"):
+        lower(tri)
+    assert not window_is_valid(lower(mb.templates.muta(2, 1, one_column=True)))
+    assert window_is_valid(lower(mb.templates.muta(2, 1, one_column=True), window_size=4))
+
+
+def test_noise_block_coefficients():
+    nz = noise_from_kraus(kraus_set("depolarizing", p=0.3))
+    assert np.allclose(list(nz.pop), [1 - 0.2, 0.2, 0.2, 1 - 0.2])
+    assert np.isclose(nz.coh_g, 1 - 0.4) and np.isclose(nz.coh_d, 0.0)
+    nz = noise_from_kraus(kraus_set("amplitude_damping", p=0.25))
+    assert np.allclose(list(nz.pop), [1, 0.25, 0, 0.75]) and np.isclose(nz.coh_g, np.sqrt(0.75))
+    nz = noise_from_kraus(kraus_set("bit_flip", p=0.1))
+    assert np.allclose(list(nz.pop), [0.9, 0.1, 0.1, 0.9]) and np.isclose(nz.coh_d, 0.1)
+    with pytest.raises(ValueError):
+        kraus_set("nope")
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)  # unitary mixing populations into coherences
+    with pytest.raises(NotImplementedError):
+        noise_from_kraus([h])
+
+
+def test_facade_contract_without_gpu():
+    gs = mb.templates.linear_cluster(3)
+    with pytest.raises(ValueError, match="not supported"):
+        mb.PatternSimulator(gs, backend="numpy-sv")
+    with pytest.raises(TypeError):
+        mb.PatternSimulator(gs, input_state=[1, 0])
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(gs, backend="cuda-sv", force0=False)
+    ps = mb.PatternSimulator(gs, backend="CUDA-SV", some_unknown_kwarg=3)
+    assert ps.window_size == 2 and ps.mbqcircuit is gs and ps.outcomes == {}
+    assert ps.schedule_measure == [0, 1]
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            ps.run([0.0, 0.0])

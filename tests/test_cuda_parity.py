@@ -1,0 +1,266 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the reference's golden vectors and with
+the oracles on seeded inputs.  Tolerances: infidelity <= 1e-10 in fp64 (BASELINE.json
+north_star); amplitude / matrix-element comparisons use 1e-9 where the reference's own global
+phase is well conditioned."""
+import numpy as np
+import pytest
+import torch
+
+import mentpy_b200 as mb
+from conftest import dm_distance, from_cplx, infidelity_pure, load_golden
+from oracle import matrix_free
+from oracle.pattern_data import PatternData
+
+pytestmark = pytest.mark.gpu
+
+INFID_TOL = 1e-10
+CASES = load_golden("sim_cases.json")["cases"]
+
+
+def _case_id(c):
+    return f"{c['spec'][0]}{c['spec'][1]}-{c['backend']}-s{c['seed']}-w{c['window_size']}"
+
+
+def _build(case):
+    name, args, kwargs = case["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    for v in case["x_nodes"]:
+        gs[v] = mb.Ment("X")
+    for v, (ang, plane) in case["fixed"].items():
+        gs[int(v)] = mb.Ment(ang, plane)
+    return gs
+
+
+def _dm_infidelity(rho, sigma):
+    """1 - tr(rho sigma) for a pure reference sigma; max-abs distance otherwise is used."""
+    return abs(1.0 - np.real(np.trace(rho @ sigma)))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[_case_id(c) for c in CASES])
+def test_golden_cases_through_facade(case):
+    gs = _build(case)
+    inp = from_cplx(case["input_state"])
+    backend = "cuda-sv" if case["backend"] == "numpy-sv" else "cuda-dm"
+    ps = mb.PatternSimulator(gs, input_state=inp, backend=backend, window_size=case["window_size"])
+    assert ps.window_size == case["window_size"]
+    want = from_cplx(case["output"])
+    ang = np.asarray(case["angles"])
+    if backend == "cuda-sv":
+        if "trace" in case:  # stateful measure() path, state after every measurement
+            for node, ref_state in zip(ps.schedule_measure, case["trace"]):
+                a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else gs[node].angle
+                st, outcome = ps.measure(a)
+                ref_state = from_cplx(ref_state)
+                assert outcome == 0 and st.shape == ref_state.shape
+                assert infidelity_pure(st, ref_state) < INFID_TOL
+                assert np.allclose(st, ref_state, atol=1e-9, rtol=0)
+            with pytest.raises(ValueError, match="No more measurements"):
+                ps.measure(0.0)
+            ps.reset()
+        got = ps.run(ang, output_form=case["output_form"])
+        assert got.shape == want.shape and got.dtype == np.complex128
+        if case["output_form"] == "sv":
+            assert infidelity_pure(got, want) < INFID_TOL
+            assert np.allclose(got, want, atol=1e-9, rtol=0)  # including the reference's phase
+        else:
+            assert dm_distance(got, want) < 1e-10
+        assert ps.outcomes == {v: 0 for v in ps.schedule_measure}
+        with pytest.raises(ValueError, match="No more measurements"):
+            ps.run(ang)
+    else:
+        got = ps.run(ang)
+        assert got.shape == want.shape
+        assert dm_distance(got, want) < 1e-10
+        assert {str(k): v for k, v in ps.outcomes.items()} == case["outcomes"]
+
+
+def test_default_output_is_density_matrix_and_call_alias():
+    gs = mb.templates.grid_cluster(2, 4)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    ang = np.random.default_rng(3).uniform(0, 2 * np.pi, len(gs.trainable_nodes))
+    rho = ps(ang)
+    ps.reset()
+    psi = ps.run(ang, output_form="statevector")
+    assert rho.shape == (4, 4) and np.allclose(rho, np.outer(psi, psi.conj()), atol=1e-12)
+    with pytest.raises(ValueError):
+        ps.reset(); ps.run(ang[:-1])
+    with pytest.raises(ValueError):
+        ps.reset(); ps.run(ang, output_form="nope")
+
+
+def test_teleportation_identity_all_backends():
+    """Reference KAT tests/test_simulators.py:13-30 (atol 1e-3 there; 1e-10 here)."""
+    from scipy.stats import unitary_group
+
+    for backend in ("cuda-sv", "cuda-dm"):
+        for i in range(1, 5):
+            gs = mb.templates.linear_cluster(2 * i + 1)
+            ps = mb.PatternSimulator(gs, backend=backend)
+            for s in range(3):
+                st = unitary_group.rvs(2, random_state=10 * i + s)[:, 0]
+                ps.reset(input_state=st)
+                assert len(ps.mbqcircuit.trainable_nodes) == 2 * i
+                out = ps([0] * (2 * i))
+                assert np.allclose(out, np.outer(st, st.conj()), atol=1e-10)
+
+
+@pytest.mark.parametrize("spec,w", [(("linear_cluster", [5]), None), (("grid_cluster", [2, 6]), None),
+                                    (("grid_cluster", [4, 5]), None), (("grid_cluster", [3, 5]), 5),
+                                    (("grid_cluster", [2, 6]), 7), (("grid_cluster", [3, 6]), 9),
+                                    (("linear_cluster", [16]), 12), (("many_wires", [[3, 4, 2]]), None),
+                                    (("muta", [2, 1]), 5)])
+def test_sv_batch_matches_oracle(spec, w):
+    name, args = spec
+    gs = getattr(mb.templates, name)(*args)
+    pat = PatternData.from_circuit(gs)
+    rng = np.random.default_rng(42)
+    B, T = 257, len(gs.trainable_nodes)
+    ang = rng.uniform(0, 2 * np.pi, (B, T))
+    kw = {} if w is None else {"window_size": w}
+    ps = mb.PatternSimulator(gs, backend="cuda-sv", **kw)
+    got = ps.run_batch(ang)
+    want = matrix_free.run_sv_batch(pat, ang, window_size=(w or 1))
+    assert got.shape == want.shape
+    infid = 1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2
+    assert np.max(np.abs(infid)) < INFID_TOL
+    # per-sample Haar inputs and the 'dm' form
+    from scipy.stats import unitary_group
+
+    n_in = len(gs.input_nodes)
+    ins = np.stack([unitary_group.rvs(2**n_in, random_state=s)[:, 0] for s in range(8)])
+    got = ps.run_batch(ang[:8], input_states=ins, output_form="dm")
+    want = matrix_free.run_sv_batch(pat, ang[:8], ins, window_size=(w or 1), output_form="dm")
+    assert dm_distance(got, want) < 1e-10
+    # torch in -> torch out, no host round trip
+    tout = ps.run_batch(torch.from_numpy(ang).cuda())
+    assert isinstance(tout, torch.Tensor) and tout.is_cuda
+    assert np.array_equal(tout.cpu().numpy(), ps.run_batch(ang))
+
+
+@pytest.mark.parametrize("spec,w", [(("grid_cluster", [3, 8]), None), (("grid_cluster", [2, 5]), 5),
+                                    (("linear_cluster", [6]), 3), (("grid_cluster", [2, 6]), 6),
+                                    (("many_wires", [[3, 4, 2]]), None), (("linear_cluster", [4]), 1)])
+def test_dm_batch_matches_oracle(spec, w):
+    name, args = spec
+    gs = getattr(mb.templates, name)(*args)
+    pat = PatternData.from_circuit(gs)
+    rng = np.random.default_rng(7)
+    B, T = 37, len(gs.trainable_nodes)
+    ang = rng.uniform(0, 2 * np.pi, (B, T))
+    kw = {} if w is None else {"window_size": w}
+    ps = mb.PatternSimulator(gs, backend="cuda-dm", **kw)
+    got, oc = ps.run_batch(ang, return_outcomes=True)
+    want, woc = matrix_free.run_dm_batch(pat, ang, window_size=(w or 1), return_outcomes=True)
+    assert dm_distance(got, want) < 1e-10
+    assert np.array_equal(oc, woc)
+    assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind,kw", [("depolarizing", {"p": 0.0}), ("depolarizing", {"p": 0.01}),
+                                     ("depolarizing", {"p": 0.1}), ("amplitude_damping", {"p": 0.2}),
+                                     ("phase_damping", {"p": 0.3}), ("phase_flip", {"p": 0.05}),
+                                     ("generalized_amplitude_damping", {"p": 0.1, "p_gad": 0.3})])
+def test_dm_noise_matches_oracles(kind, kw):
+    """Noise parity is UNPINNED by the reference (PennyLane-only); compare with the windowed
+    numpy restatement and the independent full-graph brute force."""
+    from oracle import fullgraph_noise
+
+    rng = np.random.default_rng(11)
+    for name, args, w in (("grid_cluster", [3, 8], None), ("grid_cluster", [2, 4], 4), ("linear_cluster", [6], 3)):
+        gs = getattr(mb.templates, name)(*args)
+        pat = PatternData.from_circuit(gs)
+        ang = rng.uniform(0, 2 * np.pi, (5, len(gs.trainable_nodes)))
+        ps = mb.PatternSimulator(gs, backend="cuda-dm", circuit_noise=kind, **kw, **({} if w is None else {"window_size": w}))
+        got = ps.run_batch(ang)
+        okw = {"p": kw["p"]}
+        if "p_gad" in kw:
+            okw["p_gad"] = kw["p_gad"]
+        want = matrix_free.run_dm_batch(pat, ang, window_size=(w or 1), noise=kind, noise_kwargs=okw)
+        assert dm_distance(got, want) < 1e-10
+        assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
+        assert np.allclose(got, np.conj(np.swapaxes(got, 1, 2)), atol=1e-12)
+        if pat.n_nodes <= 8:
+            brute = fullgraph_noise.run_fullgraph_dm(pat, ang[0], noise=kind, noise_kwargs=okw)
+            assert dm_distance(got[0], brute) < 1e-10
+    if kw.get("p") == 0.0:
+        clean = mb.PatternSimulator(gs, backend="cuda-dm", window_size=w).run_batch(ang)
+        assert dm_distance(got, clean) < 1e-13
+
+
+def test_depolarizing_three_quarters_is_maximally_mixed():
+    gs = mb.templates.linear_cluster(4)
+    ps = mb.PatternSimulator(gs, backend="cuda-dm", circuit_noise="depolarizing", p=0.75)
+    rho = ps.run_batch(np.random.default_rng(0).uniform(0, 6, (3, 3)))
+    assert np.allclose(rho, np.eye(2) / 2, atol=1e-12)
+
+
+def test_dm_outcome1_quirk():
+    d = load_golden("dm_outcome_quirk.json")
+    name, args, kwargs = d["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    ps = mb.PatternSimulator(gs, input_state=from_cplx(d["input_state"]), backend="cuda-dm",
+                             window_size=d["window_size"])
+    for run in d["runs"]:
+        ps.reset()
+        got = ps.run(np.asarray(run["angles"]))
+        assert dm_distance(got, from_cplx(run["output"])) < 1e-10
+        assert {str(k): v for k, v in ps.outcomes.items()} == run["outcomes"]
+        assert ps.last_status[0] & 2 == (2 if 1 in run["outcomes"].values() else 0)
+
+
+def test_dm_stateful_measure_and_planes():
+    case = next(c for c in CASES if c["backend"] == "numpy-dm" and c["fixed"] and "XZ" in str(c["fixed"]))
+    gs = _build(case)
+    ps = mb.PatternSimulator(gs, backend="cuda-dm", window_size=case["window_size"])
+    ang = np.asarray(case["angles"])
+    for node in ps.schedule_measure:
+        a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else gs[node].angle
+        rho, outcome = ps.measure(a)
+        assert abs(np.trace(rho) - 1) < 1e-12
+    k = len(gs.output_nodes)
+    assert rho.shape == (2**k, 2**k)
+    # after the last measurement the window is the output block in schedule order
+    final = ps.reorder_qubits(rho, ps.current_simulated_nodes(), gs.quantum_output_nodes)
+    assert dm_distance(final, from_cplx(case["output"])) < 1e-10
+    with pytest.raises(ValueError, match="fixed angle"):
+        ps.reset()
+        fixed_first = next(i for i, n in enumerate(ps.schedule_measure) if n not in gs.trainable_nodes)
+        for n in ps.schedule_measure[:fixed_first]:
+            ps.measure(0.1)
+        ps.measure(123.0)
+
+
+def test_full_size_properties_c2():
+    """BASELINE configs[1] at full size: 65,536 angle sets on grid_cluster(2,6); size-independent
+    checks: norms, batch-order independence, agreement of a strided subsample with the oracle."""
+    gs = mb.templates.grid_cluster(2, 6)
+    pat = PatternData.from_circuit(gs)
+    B = 65536
+    ang = np.random.default_rng(1).uniform(0, 2 * np.pi, (B, 10))
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    out = ps.run_batch(ang)
+    assert out.shape == (B, 4)
+    assert np.allclose(np.sum(np.abs(out) ** 2, axis=1), 1.0, atol=1e-12)
+    perm = np.random.default_rng(2).permutation(B)
+    assert np.array_equal(ps.run_batch(ang[perm]), out[perm])
+    idx = np.arange(0, B, 97)
+    want = matrix_free.run_sv_batch(pat, ang[idx])
+    infid = 1 - np.abs(np.sum(out[idx].conj() * want, axis=1)) ** 2
+    assert np.max(np.abs(infid)) < INFID_TOL
+    # golden seed-1 vector is row 0 of this very batch
+    case = next(c for c in CASES if c["spec"][1] == [2, 6] and c["output_form"] == "sv")
+    assert np.allclose(out[0], from_cplx(case["output"]), atol=1e-9)
+
+
+def test_gradient_kernel_matches_reference_golden():
+    from mentpy_b200.gradients import psr_gradient_batched
+
+    g = load_golden("gradients.json")["c4"]
+    gs = mb.templates.grid_cluster(4, 5)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    x = np.asarray(g["x"])
+    grad, cost = psr_gradient_batched(ps, x[None, :], from_cplx(g["target"]), return_cost=True)
+    assert abs(cost[0] - g["cost"]) < 1e-12
+    assert np.allclose(grad[0], g["psr"], atol=1e-11, rtol=0)
+    grad_fd = psr_gradient_batched(ps, x[None, :], from_cplx(g["target"]), shift=1e-5)
+    assert np.allclose(grad_fd[0], g["fd"], atol=1e-6, rtol=0)

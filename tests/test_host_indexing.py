@@ -1,0 +1,112 @@
+"""CPU: host-side indexing (templates, relabelling, causal flow, layers, measurement order,
+trainable order) must be bit-exact with tables dumped from the unmodified reference
+(tests/golden/structures.json; mentpy/mbqc/mbqcircuit.py:325-422, flow.py:115-185)."""
+import pytest
+
+import mentpy_b200 as mb
+from conftest import load_golden
+
+RECORDS = load_golden("structures.json")["records"]
+
+
+def _id(r):
+    return f"{r['spec'][0]}{r['spec'][1]}{r['spec'][2] or ''}"
+
+
+@pytest.mark.parametrize("rec", RECORDS, ids=[_id(r) for r in RECORDS])
+def test_structure_tables(rec):
+    name, args, kwargs = rec["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    pat = rec["pattern"]
+    assert list(gs.graph.nodes()) == rec["nodes"]
+    assert sorted(tuple(sorted(e)) for e in gs.graph.edges()) == sorted(tuple(sorted(e)) for e in pat["edges"])
+    assert gs.input_nodes == pat["input_nodes"]
+    assert gs.output_nodes == pat["output_nodes"]
+    assert gs.trainable_nodes == pat["trainable_nodes"]
+    assert gs.measurement_order == pat["measurement_order"]
+    assert gs.quantum_output_nodes == pat["quantum_output_nodes"]
+    assert gs.outputc == rec["outputc"]
+    assert gs.inputc == rec["inputc"]
+    assert {str(k): v for k, v in gs.planes.items()} == rec["planes"]
+    assert list(gs.measurements.keys()) == [int(k) for k in pat["measurements"].keys()]
+    assert {str(v): gs.flow(v) for v in gs.outputc} == rec["flow"]
+    assert gs.gflow.layers == rec["layers"]
+    assert gs.depth == rec["depth"]
+    assert len(gs) == pat["n_nodes"]
+
+
+def test_config_table_survey_8():
+    gs = mb.templates.grid_cluster(2, 6)
+    assert gs.measurement_order == [0, 6, 1, 7, 2, 8, 3, 9, 4, 10, 5, 11]
+    assert gs.trainable_nodes == [0, 1, 2, 3, 4, 6, 7, 8, 9, 10]
+    gs = mb.templates.muta(2, 1)
+    assert gs.measurement_order == [0, 4, 5, 1, 6, 2, 7, 3, 13, 8, 9, 14, 10, 15, 11, 16, 12, 17]
+    assert (gs.input_nodes, gs.output_nodes) == ([0, 4], [12, 17])
+
+
+def test_setitem_updates_trainables():
+    gs = mb.templates.grid_cluster(2, 4)
+    gs[1] = mb.Ment("X")
+    gs[5] = mb.Ment(0.3, "XY")
+    assert gs.trainable_nodes == [0, 2, 4, 6]
+    assert gs[1].plane == "X" and gs[1].angle == 0 and gs[1].node_id == 1
+    with pytest.raises(ValueError):
+        gs[99] = mb.Ment("X")
+    with pytest.raises(ValueError):
+        gs[1] = "X"
+
+
+def test_unsorted_labels_are_ranked():
+    g = mb.GraphState()
+    g.add_edges_from([(10, 30), (30, 20), (20, 40)])
+    c = mb.MBQCircuit(g, input_nodes=[10], output_nodes=[40])
+    assert list(c.graph.nodes()) == [0, 2, 1, 3]
+    assert c.input_nodes == [0] and c.output_nodes == [3]
+    assert c.measurement_order == [0, 2, 1, 3]
+    assert c.trainable_nodes == [0, 2, 1]
+
+
+def test_no_flow_and_errors():
+    g = mb.GraphState([(0, 1), (1, 2), (2, 0)])
+    c = mb.MBQCircuit(g, input_nodes=[0], output_nodes=[2])
+    assert c.flow is None and c.measurement_order is None
+    with pytest.raises(ValueError):
+        mb.MBQCircuit(g, input_nodes=[0, 1], output_nodes=[2])
+    with pytest.raises(KeyError):  # same as the reference: unknown label fails in the relabel map
+        mb.MBQCircuit(g, input_nodes=[7], output_nodes=[2])
+    with pytest.raises(ValueError):
+        mb.MBQCircuit(g, input_nodes=[7], output_nodes=[2], relabel_indices=False)
+
+
+def test_ment_contract():
+    """mentpy tests/operators/test_ment.py:6-61 restated."""
+    import numpy as np
+
+    m = mb.Ment(0.5, "XY")
+    assert (m.angle, m.plane) == (0.5, "XY") and not m.is_trainable()
+    assert repr(m) == "Ment(0.5, XY)"
+    assert mb.Ment("XY").is_trainable() and repr(mb.Ment("xy")) == "Ment(θ, XY)"
+    assert mb.Ment("XY", 0.25).angle == 0.25
+    assert not mb.Ment("X").is_trainable() and mb.Ment("Z").angle == 0
+    assert np.allclose(mb.Ment(0.0).matrix(), np.array([[0, 1], [1, 0]]))
+    assert np.allclose(mb.Ment(np.pi / 2, "XY").matrix(), np.array([[0, -1j], [1j, 0]]))
+    with pytest.raises(ValueError):
+        mb.Ment(plane="AB")
+    with pytest.raises(ValueError):
+        mb.Ment(0.3, "X")
+    with pytest.raises(ValueError):
+        mb.Ment("XY").matrix()
+    with pytest.raises(ValueError):
+        mb.Ment(0.3).matrix(0.4)
+    with pytest.raises(TypeError):
+        mb.Ment([0.1])
+    h = load_golden("helpers.json")
+    from conftest import from_cplx
+
+    for rec in h["ment"]:
+        m = mb.Ment(rec["plane"]) if rec["angle"] is None else mb.Ment(rec["angle"], rec["plane"])
+        assert np.array_equal(np.asarray(m.matrix(), dtype=complex), from_cplx(rec["matrix"]))
+        p0, p1 = m.get_povm()
+        assert np.array_equal(np.asarray(p0, dtype=complex), from_cplx(rec["p0"]))
+        assert np.array_equal(np.asarray(p1, dtype=complex), from_cplx(rec["p1"]))
+        assert mb.Ment(rec["plane"]).is_trainable() == rec["trainable"]
