@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the MBQC pattern-evaluation hot path (BASELINE.json metric: pattern evals/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (N = 1 and per rank for N > 1, weak scaling): BASELINE.json configs[1] --
+grid_cluster(2,6) state-vector pattern, 65,536 random angle sets per step, outputs [B,4]
+complex128.  A step = one pass of the hot path over one batch = ONE kernel launch.  Batches rotate
+through a pool whose angles+outputs exceed the 126 MB L2, so no step finds its inputs cached.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over
+ranks); `e2e` = the same metric through PatternSimulator.run_batch with HOST buffers (pinned
+H2D + D2H inside the timed region); `roofline` = algorithmic bytes / step time vs measured HBM
+peak; `cpu_baseline` = the dense numpy port of the reference (oracle/dense_port.py) on host cores.
+`--impl reference` times only that CPU port (all host cores), same metric / config.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ROWS, COLS = 2, 6
+BATCH = 65536
+SEED = 1
+ALGO_BYTES_PER_EVAL = 8 * 10 + 16 * 4  # 8*T angles in + 16*2^k amplitudes out = 144 B
+L2_BYTES = 126 * 1024 * 1024
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_bytes():
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("sv_reg_kernel_c2_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the dense port of the reference, one process per host core
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    pat_json, angles = args
+    from oracle.dense_port import DensePatternSV
+    from oracle.pattern_data import PatternData
+
+    pat = PatternData.from_json(pat_json)
+    sim = DensePatternSV(pat)
+    acc = 0.0
+    for a in angles:
+        sim.reset()
+        acc += float(np.abs(sim.run(a, output_form="sv")[0]))
+    return acc
+
+
+def _pattern_json():
+    import mentpy_b200 as mb
+    from oracle.pattern_data import PatternData
+
+    return PatternData.from_circuit(mb.templates.grid_cluster(ROWS, COLS)).to_json()
+
+
+def cpu_port_rate(evals_per_core, cores, repeats=1, pool=None):
+    """evals/s of the dense reference port using `cores` processes (each single-threaded)."""
+    import multiprocessing as mp
+
+    pat_json = _pattern_json()
+    rng = np.random.default_rng(SEED)
+    chunks = [rng.uniform(0, 2 * np.pi, (evals_per_core, 10)) for _ in range(cores)]
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    best = None
+    try:
+        if pool is not None:
+            pool.map(_cpu_worker, [(pat_json, c[:2]) for c in chunks])  # warm the workers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            if pool is not None:
+                pool.map(_cpu_worker, [(pat_json, c) for c in chunks])
+            else:
+                _cpu_worker((pat_json, chunks[0]))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    finally:
+        if own and pool is not None:
+            pool.close()
+            pool.join()
+    return evals_per_core * cores / best, best
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference algorithm's CPU port on all host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    os.environ["OMP_NUM_THREADS"] = "1"
+    cores = os.cpu_count() or 1
+    per_core = 48  # ~0.3 s of work per core per step
+    pat_json = _pattern_json()
+    rng = np.random.default_rng(SEED)
+    pool = mp.get_context("spawn").Pool(cores) if cores > 1 else None
+    sample = per_core * cores
+
+    def step():
+        chunks = [(pat_json, rng.uniform(0, 2 * np.pi, (per_core, 10))) for _ in range(cores)]
+        if pool is not None:
+            pool.map(_cpu_worker, chunks)
+        else:
+            _cpu_worker(chunks[0])
+
+    steps = min(args.steps, 40)
+    for _ in range(min(args.warmup, 3)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+        pool.join()
+    value = sample * steps / dt
+    line = {
+        "impl": "reference", "metric": "pattern_evals_per_s", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "grid_cluster(2,6) statevector, random angle sets (BASELINE configs[1])",
+                   "pattern": "grid_cluster(2,6)", "backend": "numpy-sv algorithm (dense kron operators)",
+                   "evals_per_step": sample, "window": 3, "measurements": 10},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} angle sets per step x {steps} steps, one single-threaded process per core "
+                                   "(oracle/dense_port.py, restates np_simulator_sv.py incl. dense kron operators)"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample_once(self):
+        if not self.ok:
+            return
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            self.sample_once()
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import mentpy_b200 as mb
+    from mentpy_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    gs = mb.templates.grid_cluster(ROWS, COLS)
+    T = len(gs.trainable_nodes)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    sim = ps.simulator
+    k = len(gs.output_nodes)
+
+    # pool of batches: angles + outputs together exceed L2, every rank has its own angle stream
+    per_batch = BATCH * (8 * T + 16 * 2**k)
+    pool = max(4, int(np.ceil(1.5 * L2_BYTES / per_batch)))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(SEED + 1000 * rank)
+    angles = torch.rand((pool, BATCH, T), generator=gen, device=dev, dtype=torch.float64) * (2 * np.pi)
+    outs = torch.empty((pool, BATCH, 2**k), dtype=torch.complex128, device=dev)
+    status = torch.empty(BATCH, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    plan = sim._full_plan()
+    stream = torch.cuda.current_stream(dev)
+
+    def step(i):
+        j = i % pool
+        rc = lib.mbqc_run_batch_sv(plan.handle, angles[j].data_ptr(), T, None, _lib.INPUT_PLUS, BATCH,
+                                   outs[j].data_ptr(), _lib.OUT_SV, status.data_ptr(), stream.cuda_stream)
+        if rc != 0:
+            _lib.check(rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    gathered = torch.empty((world, BATCH, 2**k), dtype=torch.complex128, device=dev) if world > 1 else None
+
+    sampler = ClockSampler(local_rank)
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    if world > 1:  # the one final gather of the job: last step's outputs to every rank
+        dist.all_gather_into_tensor(gathered.view(-1), outs[(args.steps - 1) % pool].view(-1))
+    e1.record(stream)
+    sampler.sample_once()
+    barrier()
+    sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert int(status.max().item()) == 0, "kernel reported a bad norm"
+
+    # end-to-end through the public API with host buffers (pinned), every step: H2D + kernel + D2H
+    host_pool = min(pool, 4)
+    h_angles = [torch.empty((BATCH, T), dtype=torch.float64).pin_memory() for _ in range(host_pool)]
+    for j, h in enumerate(h_angles):
+        h.copy_(angles[j].cpu())
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(2):
+        ps.run_batch(h_angles[i % host_pool], copy=False)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        res = ps.run_batch(h_angles[i % host_pool], copy=False)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    assert res.shape == (BATCH, 2**k)
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        ms_per_step = ms / args.steps
+        value = world * BATCH * args.steps / (ms * 1e-3)
+        achieved = BATCH * ALGO_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9
+        cores = os.cpu_count() or 1
+        cpu_rate, cpu_s = cpu_port_rate(evals_per_core=256, cores=cores)
+        line = {
+            "metric": "pattern_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "grid_cluster(2,6) statevector, 65,536 random angle sets per step per GPU (BASELINE configs[1])",
+                       "pattern": "grid_cluster(2,6)", "backend": "cuda-sv", "batch_per_gpu": BATCH,
+                       "window": 3, "measurements": 10, "output": "sv [B,4] complex128",
+                       "l2": f"inputs rotate through a pool of {pool} batches ({pool * per_batch / 2**20:.0f} MiB > 126 MiB L2)",
+                       "parallelism": f"batch-split x{world}" + (", one final NCCL all_gather of the last step's outputs inside the timed region" if world > 1 else "")},
+            "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "evals/s",
+                    "h2d_bytes_per_step": BATCH * T * 8, "d2h_bytes_per_step": BATCH * (2**k) * 16,
+                    "steps": e2e_steps, "api": "PatternSimulator(...,backend='cuda-sv').run_batch(host angles) -> host amplitudes"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                         "peak_source": peak_src, "kernel": "sv_reg_kernel<3,false>",
+                         "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_EVAL,
+                         "note": "register-resident batched regime is FP64-pipe/launch bound, not HBM bound (SURVEY 8d); see DESIGN.md"},
+            "cpu_baseline": {"value": cpu_rate, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": f"{256 * cores} angle sets of the same workload, one single-threaded process per core, "
+                                       f"{cpu_s:.1f} s (oracle/dense_port.py: reference algorithm incl. dense kron operators)"},
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

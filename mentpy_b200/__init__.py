@@ -8,4 +8,14 @@ from .mbqc import (GraphState, MBQCircuit, Measurement, Ment, hstack, merge, tem
 from . import simulators
 from .simulators import BaseSimulator, CudaSimulatorDM, CudaSimulatorSV, PatternSimulator
 
+
+
+def pinned_empty(shape, dtype="float64"):
+    """Page-locked host array (numpy view + owning tensor) for zero-staging H2D/D2H in run_batch."""
+    import torch
+
+    t = torch.empty(shape, dtype=getattr(torch, dtype)).pin_memory()
+    return t
+
+
 __version__ = "0.1.0"

@@ -120,7 +120,7 @@ def psr_gradient_batched(simulator, angles, target, shift=1.5, input_states=None
         grad = torch.empty((batch, T), dtype=torch.float64, device=dev)
         cost = torch.empty(batch, dtype=torch.float64, device=dev) if return_cost else None
         status = torch.empty(batch, dtype=torch.int32, device=dev)
-        _lib.check(lib.mbqc_psr_grad_batch(dplan.handle, a.data_ptr(), a.stride(0),
+        _lib.check(lib.mbqc_psr_grad_batch(dplan.handle, a.data_ptr(), (a.stride(0) if batch > 1 else max(T, 1)),
                                            None if inp is None else inp.data_ptr(), mode, batch,
                                            tgt.data_ptr(), C.c_double(shift), grad.data_ptr(),
                                            None if cost is None else cost.data_ptr(),

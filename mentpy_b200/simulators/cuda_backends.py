@@ -27,8 +27,51 @@ def _require_cuda():
         raise RuntimeError("mentpy_b200 needs a CUDA device: there is no CPU fallback.")
 
 
+def _row_stride(a: torch.Tensor) -> int:
+    # a size-1 batch axis may report any stride (even 0)
+    return a.stride(0) if a.shape[0] > 1 else max(a.shape[1], 1)
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
+
+
+class _HostPipeline:
+    """Chunked host<->device pipeline for `run_batch` on host arrays: chunk c's H2D copy, kernel and
+    D2H copy are queued on stream c % n_streams, so the PCIe transfers of neighbouring chunks
+    overlap the kernel and each other (full duplex).  Owns persistent device buffers and two
+    rotating pinned output buffers (no allocation in steady state)."""
+
+    def __init__(self, dev, n_streams: int = 3, chunks: int = 6):
+        self.dev = dev
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
+        self.chunks = chunks
+        self.d_in = None
+        self.d_out = None
+        self.d_status = None
+        self.h_in = None
+        self.h_out = [None, None]
+        self.h_flag = [None, None]
+        self.turn = 0
+
+    @staticmethod
+    def _fits(t, shape, dtype):
+        return t is not None and t.dtype == dtype and t.numel() >= int(np.prod(shape))
+
+    def buffers(self, batch, T, out_elems):
+        if not self._fits(self.d_in, (batch, T), torch.float64):
+            self.d_in = torch.empty(batch * T, dtype=torch.float64, device=self.dev)
+            self.h_in = torch.empty(batch * T, dtype=torch.float64).pin_memory()
+            self.d_status = torch.empty(batch, dtype=torch.int32, device=self.dev)
+        if not self._fits(self.d_out, (batch, out_elems), torch.complex128):
+            self.d_out = torch.empty(batch * out_elems, dtype=torch.complex128, device=self.dev)
+            self.h_out = [torch.empty(batch * out_elems, dtype=torch.complex128).pin_memory() for _ in range(2)]
+            self.h_flag = [torch.zeros(self.chunks, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.turn ^= 1
+        return (self.d_in[: batch * T].view(batch, T), self.h_in[: batch * T].view(batch, T),
+                self.d_out[: batch * out_elems].view(batch, out_elems),
+                self.h_out[self.turn][: batch * out_elems].view(batch, out_elems),
+                self.d_status[:batch], self.h_flag[self.turn])
 
 
 class _CudaPatternBase(BaseSimulator):
@@ -61,6 +104,7 @@ class _CudaPatternBase(BaseSimulator):
         self._prefix = {}
         self._d_input = None
         self.last_status = None
+        self._pipe = None
 
     # -- plumbing -------------------------------------------------------------------------------
     def _parse_noise(self, kwargs):
@@ -192,8 +236,14 @@ class CudaSimulatorSV(_CudaPatternBase):
 
     mixed = False
 
-    def run_batch(self, angles, input_states=None, output_form: str = "sv", check: bool = True):
-        """Evaluate B angle vectors: angles [B,T] -> [B,2^k] ('sv') or [B,2^k,2^k] ('dm')."""
+    def run_batch(self, angles, input_states=None, output_form: str = "sv", check: bool = True,
+                  copy: bool = True):
+        """Evaluate B angle vectors: angles [B,T] -> [B,2^k] ('sv') or [B,2^k,2^k] ('dm').
+
+        Host input (numpy / CPU tensor, ideally pinned -- see `mentpy_b200.pinned_empty`) returns a
+        numpy array; with copy=False it is a view of an internal pinned buffer that stays valid
+        until the next-but-one host call.  CUDA tensor input returns a CUDA tensor, asynchronously
+        on the current stream."""
         form = output_form.lower()
         if form in ("dm", "densitymatrix"):
             code = _lib.OUT_DM
@@ -201,11 +251,14 @@ class CudaSimulatorSV(_CudaPatternBase):
             code = _lib.OUT_SV
         else:
             raise ValueError(f"Output form {output_form} is not supported.")
-        return self._run_plan(self._full_plan(), angles, input_states, code, check)
+        return self._run_plan(self._full_plan(), angles, input_states, code, check, copy)
 
-    def _run_plan(self, dplan: DevicePlan, angles, input_states, code, check):
+    def _run_plan(self, dplan: DevicePlan, angles, input_states, code, check, copy=True):
         dev = self._dev()
         lib = _lib.load()
+        on_host = not (isinstance(angles, torch.Tensor) and angles.is_cuda)
+        if on_host and (input_states is None or np.ndim(input_states) == 1):
+            return self._run_plan_host(dplan, angles, input_states, code, check, copy)
         with torch.cuda.device(dev):
             a, on_host = self._stage_angles(angles, dev)
             batch = a.shape[0]
@@ -214,7 +267,7 @@ class CudaSimulatorSV(_CudaPatternBase):
             shape = (batch, dim) if code == _lib.OUT_SV else (batch, dim, dim)
             out = torch.empty(shape, dtype=torch.complex128, device=dev)
             status = torch.empty(batch, dtype=torch.int32, device=dev)
-            _lib.check(lib.mbqc_run_batch_sv(dplan.handle, _ptr(a), a.stride(0), _ptr(inp), mode,
+            _lib.check(lib.mbqc_run_batch_sv(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
                                              batch, _ptr(out), code, _ptr(status),
                                              torch.cuda.current_stream(dev).cuda_stream))
             if on_host:
@@ -224,6 +277,66 @@ class CudaSimulatorSV(_CudaPatternBase):
                 return res
             self.last_status = status
             return out
+
+    def _run_plan_host(self, dplan, angles, input_states, code, check, copy):
+        """Host arrays in, host arrays out: pinned, chunked, multi-stream pipeline."""
+        dev = self._dev()
+        lib = _lib.load()
+        if isinstance(angles, torch.Tensor):
+            src = angles if angles.dtype == torch.float64 else angles.to(torch.float64)
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(np.asarray(angles, dtype=np.float64)))
+        if src.dim() == 1:
+            src = src[None, :]
+        if src.dim() != 2 or src.shape[1] != self.plan.n_angles:
+            raise ValueError(
+                f"Number of angles ({src.shape[-1]}) does not match number of trainable nodes ({self.plan.n_angles})."
+            )
+        src = src.contiguous()
+        batch, T = src.shape
+        dim = 2 ** dplan.n_out
+        out_elems = dim if code == _lib.OUT_SV else dim * dim
+        with torch.cuda.device(dev):
+            if self._pipe is None or self._pipe.dev != dev:
+                self._pipe = _HostPipeline(dev)
+            pipe = self._pipe
+            d_in, h_in, d_out, h_out, d_status, h_flag = pipe.buffers(batch, max(T, 1), out_elems)
+            inp, mode = self._stage_inputs(input_states, batch, dev)
+            pinned = src.is_pinned()
+            n_chunks = max(1, min(pipe.chunks, batch // 2048))
+            bounds = np.linspace(0, batch, n_chunks + 1).astype(np.int64)
+            cur = torch.cuda.current_stream(dev)
+            start = torch.cuda.Event()
+            start.record(cur)
+            h_flag.zero_()
+            for c in range(n_chunks):
+                lo, hi = int(bounds[c]), int(bounds[c + 1])
+                if hi == lo:
+                    continue
+                st = pipe.streams[c % len(pipe.streams)]
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    if T > 0:
+                        if pinned:
+                            d_in[lo:hi].copy_(src[lo:hi], non_blocking=True)
+                        else:
+                            h_in[lo:hi].copy_(src[lo:hi])
+                            d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
+                    _lib.check(lib.mbqc_run_batch_sv(dplan.handle, d_in[lo:hi].data_ptr(), max(T, 1), _ptr(inp), mode,
+                                                     hi - lo, d_out[lo:hi].data_ptr(), code,
+                                                     d_status[lo:hi].data_ptr(), st.cuda_stream))
+                    h_out[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
+                    if check:
+                        h_flag[c : c + 1].copy_(d_status[lo:hi].max().reshape(1), non_blocking=True)
+            for st in pipe.streams[: min(n_chunks, len(pipe.streams))]:
+                st.synchronize()
+            if check and int(h_flag.max()) & _lib.STATUS_BAD_NORM:
+                raise ValueError("qstate has nan, you might want to increase the window size")
+            self.last_status = None
+            res = h_out.numpy()
+            if code == _lib.OUT_DM:
+                res = res.reshape(batch, dim, dim)
+            return res.copy() if copy else res
 
     def measure(self, angle: float) -> Tuple[np.ndarray, int]:
         st = self._record_angle(angle)
@@ -298,7 +411,7 @@ class CudaSimulatorDM(_CudaPatternBase):
             out = torch.empty((batch, dim, dim), dtype=torch.complex128, device=dev)
             status = torch.empty(batch, dtype=torch.int32, device=dev)
             outc = torch.zeros((batch, max(dplan.n_steps, 1)), dtype=torch.int8, device=dev)
-            _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), a.stride(0), _ptr(inp), mode,
+            _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
                                              batch, _ptr(out), _ptr(outc), _ptr(status),
                                              torch.cuda.current_stream(dev).cuda_stream))
             if on_host:
