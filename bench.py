@@ -250,11 +250,14 @@ def run_gpu_arm(args):
     lib = _lib.load()
     plan = sim._full_plan()
     stream = torch.cuda.current_stream(dev)
+    a_ptr = [angles[j].data_ptr() for j in range(pool)]
+    o_ptr = [outs[j].data_ptr() for j in range(pool)]
+    s_ptr = status.data_ptr()
+    run_sv = lib.mbqc_run_batch_sv
 
-    def step(i):
+    def step(i, cuda_stream):
         j = i % pool
-        rc = lib.mbqc_run_batch_sv(plan.handle, angles[j].data_ptr(), T, None, _lib.INPUT_PLUS, BATCH,
-                                   outs[j].data_ptr(), _lib.OUT_SV, status.data_ptr(), stream.cuda_stream)
+        rc = run_sv(plan.handle, a_ptr[j], T, None, _lib.INPUT_PLUS, BATCH, o_ptr[j], _lib.OUT_SV, s_ptr, cuda_stream)
         if rc != 0:
             _lib.check(rc)
 
@@ -264,18 +267,38 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
 
     for i in range(max(args.warmup, 3)):
-        step(i)
+        step(i, stream.cuda_stream)
     barrier()
     gathered = torch.empty((world, BATCH, 2**k), dtype=torch.complex128, device=dev) if world > 1 else None
 
+    # the step loop is launch-bound (one ~few-us kernel per step): capture one pass over the pool
+    # in a CUDA graph and replay it; leftover steps are launched directly
+    graph = None
+    if not args.no_graph:
+        graph = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.graph(graph, stream=cap_stream):
+            cs = torch.cuda.current_stream(dev).cuda_stream
+            for j in range(pool):
+                step(j, cs)
+        graph.replay()
+        barrier()
+
+    def run_steps(n):
+        done = 0
+        if graph is not None:
+            while n - done >= pool:
+                graph.replay()
+                done += pool
+        for i in range(done, n):
+            step(i, stream.cuda_stream)
+
     sampler = ClockSampler(local_rank)
-    launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.start()
     e0.record(stream)
-    for i in range(args.steps):
-        step(i)
+    run_steps(args.steps)
     if world > 1:  # the one final gather of the job: last step's outputs to every rank
         dist.all_gather_into_tensor(gathered.view(-1), outs[(args.steps - 1) % pool].view(-1))
     e1.record(stream)
@@ -283,32 +306,44 @@ def run_gpu_arm(args):
     barrier()
     sampler.stop()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    launches = args.steps  # one kernel per step (graph replays execute `pool` kernel nodes each)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     assert int(status.max().item()) == 0, "kernel reported a bad norm"
 
-    # end-to-end through the public API with host buffers (pinned), every step: H2D + kernel + D2H
-    host_pool = min(pool, 4)
-    h_angles = [torch.empty((BATCH, T), dtype=torch.float64).pin_memory() for _ in range(host_pool)]
-    for j, h in enumerate(h_angles):
-        h.copy_(angles[j].cpu())
-    e2e_steps = max(3, min(args.steps, 50))
-    for i in range(2):
-        ps.run_batch(h_angles[i % host_pool], copy=False)
+    # same K steps with plain stream launches (no graph), for the record
     barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        res = ps.run_batch(h_angles[i % host_pool], copy=False)
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    assert res.shape == (BATCH, 2**k)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for i in range(args.steps):
+        step(i, stream.cuda_stream)
+    e3.record(stream)
+    barrier()
+    ms_nograph = e2.elapsed_time(e3)
+
+    # end-to-end through the public API with host buffers (pinned), every step: H2D + kernel + D2H
+    e2e = None
+    host_pool = min(pool, 4)
+    if not args.skip_e2e:
+        h_angles = [torch.empty((BATCH, T), dtype=torch.float64).pin_memory() for _ in range(host_pool)]
+        for j, h in enumerate(h_angles):
+            h.copy_(angles[j].cpu())
+        e2e_steps = max(3, min(args.steps, 50))
+        for i in range(2):
+            ps.run_batch(h_angles[i % host_pool], copy=False)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            res = ps.run_batch(h_angles[i % host_pool], copy=False)
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert res.shape == (BATCH, 2**k)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -316,7 +351,7 @@ def run_gpu_arm(args):
         value = world * BATCH * args.steps / (ms * 1e-3)
         achieved = BATCH * ALGO_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        cpu_rate, cpu_s = cpu_port_rate(evals_per_core=256, cores=cores)
+        cpu_rate, cpu_s = (None, 0.0) if args.skip_cpu else cpu_port_rate(evals_per_core=256, cores=cores)
         line = {
             "metric": "pattern_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -325,11 +360,16 @@ def run_gpu_arm(args):
             "config": {"workload": "grid_cluster(2,6) statevector, 65,536 random angle sets per step per GPU (BASELINE configs[1])",
                        "pattern": "grid_cluster(2,6)", "backend": "cuda-sv", "batch_per_gpu": BATCH,
                        "window": 3, "measurements": 10, "output": "sv [B,4] complex128",
+                       "launch_mode": "direct stream launches" if graph is None else f"CUDA graph of {pool} steps replayed",
                        "l2": f"inputs rotate through a pool of {pool} batches ({pool * per_batch / 2**20:.0f} MiB > 126 MiB L2)",
                        "parallelism": f"batch-split x{world}" + (", one final NCCL all_gather of the last step's outputs inside the timed region" if world > 1 else "")},
-            "e2e": {"value": world * BATCH * e2e_steps / e2e_s, "unit": "evals/s",
-                    "h2d_bytes_per_step": BATCH * T * 8, "d2h_bytes_per_step": BATCH * (2**k) * 16,
-                    "steps": e2e_steps, "api": "PatternSimulator(...,backend='cuda-sv').run_batch(host angles) -> host amplitudes"},
+            "e2e": None if args.skip_e2e else {
+                "value": world * BATCH * e2e_steps / e2e_s, "unit": "evals/s",
+                "h2d_bytes_per_step": BATCH * T * 8, "d2h_bytes_per_step": BATCH * (2**k) * 16,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "api": "PatternSimulator(gs, backend='cuda-sv').run_batch(pinned host angles, copy=False) -> host amplitudes "
+                       "(C ABI mbqc_run_batch_sv_host: chunked H2D / kernel / D2H on 4 streams)"},
+            "value_stream_launch": world * BATCH * args.steps / (ms_nograph * 1e-3),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
@@ -352,6 +392,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch every step directly instead of replaying a CUDA graph")
+    ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline leg")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: no host end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

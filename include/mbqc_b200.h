@@ -104,6 +104,18 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
                       int32_t out_form, int32_t* d_status, void* stream);
 
+/* Host-buffer form of mbqc_run_batch_sv -- the end-to-end plugin call: h_angles [B][T] and h_out
+ * live in host memory (page-locked for full PCIe speed).  The batch is cut into n_chunks pieces
+ * (<= 0: library default) whose H2D copy, kernel and D2H copy are queued on internal streams so
+ * that transfers in both directions overlap each other and the kernels.  d_work is caller-owned
+ * device scratch of at least mbqc_host_workspace_bytes() bytes.  Synchronous: h_out is complete
+ * on return.  h_status_any (may be NULL) receives the OR of all per-sample status bits. */
+int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batch, int32_t out_form);
+int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                           const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                           int32_t out_form, void* d_work, int64_t work_bytes,
+                           int32_t* h_status_any, int32_t n_chunks);
+
 /* NumpySimulatorDM.run over a batch (np_simulator_dm.py:218-283), optional noise from the plan:
  * out [B][2^k][2^k]; d_outcomes (may be NULL) [B][n_steps] int8 receives the outcome record
  * (simulator.outcomes). */

@@ -187,14 +187,28 @@ static void fill_sv_params(SvBatchParams& p, const mbqc_plan* plan, const double
     p.status = d_status;
 }
 
+// dynamic shared memory of the register kernels: step records + the CTA's (cos, sin) tile
+// (rows of `tp` double2, tp odd); tp = 0 selects the unstaged fallback for very long angle vectors
+static int staged_row_pitch(int n_angles, int rows, size_t steps_bytes, size_t budget) {
+    if (n_angles <= 0) return 0;
+    const int tp = n_angles | 1;
+    return (steps_bytes + (size_t)rows * tp * sizeof(double2) <= budget) ? tp : 0;
+}
+
 template <bool DM>
 static int launch_sv_reg(const SvBatchParams& p, cudaStream_t st) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
-    const size_t smem = DM ? ((size_t)threads << p.tab.n_out) * sizeof(double2) : 0;
+    const size_t steps_bytes = (size_t)p.tab.n_steps * sizeof(StepDev);
+    const int tp = staged_row_pitch(p.tab.n_angles, threads, steps_bytes, 96 * 1024);
+    size_t smem = steps_bytes + (size_t)threads * tp * sizeof(double2);
+    if (DM) {
+        const size_t stage = ((size_t)threads << p.tab.n_out) * sizeof(double2);
+        if (stage > smem) smem = stage;
+    }
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(p);
+        kern<<<blocks, threads, smem, st>>>(p, tp);
         return after_launch("sv_reg_kernel");
     };
     switch (p.tab.window) {
@@ -240,6 +254,100 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
     SvBatchParams p;
     fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
     return launch_sv(p, out_form, (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipeline --------------------------------------------------------------------
+namespace {
+constexpr int kPipeStreams = 4;
+struct PipeStreams {
+    cudaStream_t s[kPipeStreams];
+    bool ready = false;
+};
+PipeStreams g_pipe[64];  // per device
+
+int pipe_streams(int device, cudaStream_t** out) {
+    if (device < 0 || device >= 64) return fail(MBQC_E_ARG, "device index %d out of range", device);
+    PipeStreams& ps = g_pipe[device];
+    if (!ps.ready) {
+        for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking));
+        ps.ready = true;
+    }
+    *out = ps.s;
+    return MBQC_OK;
+}
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batch, int32_t out_form) {
+    if (!plan || batch < 0) return -1;
+    const int k = plan->tab.n_out;
+    const size_t out_elems = (out_form == MBQC_OUT_DM) ? ((size_t)1 << (2 * k)) : ((size_t)1 << k);
+    const int T = plan->tab.n_angles > 0 ? plan->tab.n_angles : 1;
+    return (int64_t)(align256((size_t)batch * T * sizeof(double)) + align256((size_t)batch * out_elems * sizeof(double2)) + 256);
+}
+
+int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                           const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                           int32_t out_form, void* d_work, int64_t work_bytes,
+                           int32_t* h_status_any, int32_t n_chunks) {
+    int rc = check_batch_args(plan, h_angles, angle_stride, d_inputs, input_mode, batch, h_out);
+    if (rc) return rc;
+    if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
+    if (!d_work || work_bytes < mbqc_host_workspace_bytes(plan, batch, out_form))
+        return fail(MBQC_E_ARG, "d_work too small: need %lld bytes", (long long)mbqc_host_workspace_bytes(plan, batch, out_form));
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
+    if (h_status_any) *h_status_any = 0;
+    if (batch == 0) return MBQC_OK;
+    cudaStream_t* streams = nullptr;
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    rc = pipe_streams(device, &streams);
+    if (rc) return rc;
+    const int T = plan->tab.n_angles;
+    const int Tw = T > 0 ? T : 1;
+    const int k = plan->tab.n_out;
+    const size_t out_elems = (out_form == MBQC_OUT_DM) ? ((size_t)1 << (2 * k)) : ((size_t)1 << k);
+    char* base = (char*)d_work;
+    double* d_angles = (double*)base;
+    double2* d_out = (double2*)(base + align256((size_t)batch * Tw * sizeof(double)));
+    int32_t* d_any = (int32_t*)((char*)d_out + align256((size_t)batch * out_elems * sizeof(double2)));
+    if (n_chunks < 1) n_chunks = 8;
+    if ((int64_t)n_chunks > (batch + 1023) / 1024) n_chunks = (int)((batch + 1023) / 1024);
+    if (n_chunks < 1) n_chunks = 1;
+    CUDA_TRY(cudaMemsetAsync(d_any, 0, sizeof(int32_t), streams[0]));
+    CUDA_TRY(cudaStreamSynchronize(streams[0]));
+    const int64_t per = (batch + n_chunks - 1) / n_chunks;
+    int used = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t lo = (int64_t)c * per;
+        const int64_t hi = (lo + per < batch) ? lo + per : batch;
+        if (hi <= lo) break;
+        cudaStream_t st = streams[c % kPipeStreams];
+        if (c < kPipeStreams) used = c + 1;
+        if (T > 0) {
+            if (angle_stride == T) {
+                CUDA_TRY(cudaMemcpyAsync(d_angles + lo * T, h_angles + lo * T, (size_t)(hi - lo) * T * sizeof(double), cudaMemcpyHostToDevice, st));
+            } else {
+                CUDA_TRY(cudaMemcpy2DAsync(d_angles + lo * T, (size_t)T * sizeof(double), h_angles + lo * angle_stride,
+                                           (size_t)angle_stride * sizeof(double), (size_t)T * sizeof(double), (size_t)(hi - lo),
+                                           cudaMemcpyHostToDevice, st));
+            }
+        }
+        SvBatchParams p;
+        const void* din = d_inputs;
+        if (input_mode == MBQC_INPUT_BATCH) din = (const char*)d_inputs + ((size_t)lo << plan->tab.n_in) * sizeof(double2);
+        fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, d_out + lo * out_elems, nullptr);
+        p.status_any = d_any;
+        rc = launch_sv(p, out_form, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(streams[i]));
+    if (h_status_any) CUDA_TRY(cudaMemcpy(h_status_any, d_any, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return MBQC_OK;
 }
 
 int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
@@ -299,17 +407,28 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     p.shift = shift;
     p.grad = d_grad;
     p.cost = d_cost;
-    const int threads = 128;
-    const int64_t total = batch * plan->tab.n_angles;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const int T = plan->tab.n_angles;
+    if (T > 128) return fail(MBQC_E_UNSUPPORTED, "fused gradient covers at most 128 angles (got %d)", T);
+    const int spb = 128 / T;  // whole angle vectors per CTA
+    const int threads = spb * T;
+    const size_t steps_bytes = (size_t)plan->tab.n_steps * sizeof(StepDev);
+    const int tp = staged_row_pitch(T, spb, steps_bytes, 96 * 1024);
+    const size_t smem = steps_bytes + (size_t)spb * tp * sizeof(double2);
+    const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
     cudaStream_t st = (cudaStream_t)stream;
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, threads, smem, st>>>(p, tp, spb);
+        return MBQC_OK;
+    };
     switch (w) {
-        case 1: sv_reg_grad_kernel<1><<<blocks, threads, 0, st>>>(p); break;
-        case 2: sv_reg_grad_kernel<2><<<blocks, threads, 0, st>>>(p); break;
-        case 3: sv_reg_grad_kernel<3><<<blocks, threads, 0, st>>>(p); break;
-        case 4: sv_reg_grad_kernel<4><<<blocks, threads, 0, st>>>(p); break;
-        default: sv_reg_grad_kernel<5><<<blocks, threads, 0, st>>>(p); break;
+        case 1: rc = go(sv_reg_grad_kernel<1>); break;
+        case 2: rc = go(sv_reg_grad_kernel<2>); break;
+        case 3: rc = go(sv_reg_grad_kernel<3>); break;
+        case 4: rc = go(sv_reg_grad_kernel<4>); break;
+        default: rc = go(sv_reg_grad_kernel<5>); break;
     }
+    if (rc) return rc;
     return after_launch("sv_reg_grad_kernel");
 }
 

@@ -21,6 +21,7 @@ struct SvBatchParams {
     int64_t batch;
     double2* __restrict__ out;  // [B][2^k]
     int32_t* __restrict__ status;
+    int32_t* __restrict__ status_any;  // optional: OR of all status bits (host pipeline)
     // parameter-shift support (grad kernels): unused by the plain run
     const double2* __restrict__ target;
     double shift;
@@ -60,11 +61,40 @@ __device__ __forceinline__ void reg_step(double (&re)[1 << W], double (&im)[1 <<
     }
 }
 
+// Angle sources for the evolve loop.  Global: one dependent DRAM load + sincos per step (fallback
+// for very long angle vectors).  Staged: the CTA has already turned its [threads x T] angle tile
+// into (cos, sin) pairs in shared memory with coalesced loads and independent sincos evaluations,
+// so a step costs one LDS; a parameter shift is a rotation by (cos s, sin s), no second sincos.
+struct AngleGlobal {
+    const double* row;
+    int shift_col;
+    double shift;
+    __device__ __forceinline__ void get(int idx, double& c, double& s) const {
+        double th = __ldg(row + idx);
+        if (idx == shift_col) th += shift;
+        sincos(th, &s, &c);
+    }
+};
+struct AngleStaged {
+    const double2* row;  // shared memory, (cos, sin) per angle column
+    int shift_col;
+    double cs, ss;  // cos / sin of the shift
+    __device__ __forceinline__ void get(int idx, double& c, double& s) const {
+        const double2 v = row[idx];
+        c = v.x;
+        s = v.y;
+        if (idx == shift_col) {
+            c = v.x * cs - v.y * ss;
+            s = v.y * cs + v.x * ss;
+        }
+    }
+};
+
 // Evolve one sample through the whole pattern.  Returns the squared norm over the output entries;
 // (zr, zi) accumulates the unnormalised reference phase prod (1 + e^{i theta}).
-template <int W>
-__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, int64_t b, int shift_col,
-                                                double shift, double (&re)[1 << W],
+template <int W, class AngleSrc>
+__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const StepDev* __restrict__ steps,
+                                                int64_t b, const AngleSrc& ang, double (&re)[1 << W],
                                                 double (&im)[1 << W], double& zr, double& zi) {
     constexpr int N = 1 << W;
     const PlanTables& t = p.tab;
@@ -87,16 +117,11 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, int64_t 
     }
     zr = 1.0;
     zi = 0.0;
-    const double* row = p.angles + b * p.stride;
     const int M = t.n_steps;
     for (int m = 0; m < M; ++m) {
-        const StepDev st = p.steps[m];
+        const StepDev st = steps[m];
         double c = st.fc, s = st.fs;
-        if (st.angle_idx >= 0) {
-            double th = __ldg(row + st.angle_idx);
-            if (st.angle_idx == shift_col) th += shift;
-            sincos(th, &s, &c);
-        }
+        if (st.angle_idx >= 0) ang.get(st.angle_idx, c, s);
         // reference global phase factor (1 + e^{i theta}), normalised at the end
         const double pr = 1.0 + c, pi = s;
         const double nzr = zr * pr - zi * pi;
@@ -125,25 +150,69 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, int64_t 
     return n2;
 }
 
+// Shared-memory staging done by every CTA of the register kernels before the evolve loop:
+//   s_steps [n_steps]            the plan's step records (one coalesced copy instead of a
+//                                dependent global load per step)
+//   s_cs    [samples][tp]        (cos, sin) of every angle of the CTA's samples; tp is odd so the
+//                                per-thread row reads are bank-conflict free
+// `samples` = number of angle vectors the CTA covers starting at sample b0.
+__device__ __forceinline__ void stage_plan_and_angles(const SvBatchParams& p, StepDev* s_steps,
+                                                      double2* s_cs, int tp, int64_t b0, int samples,
+                                                      bool stage_angles) {
+    const int M = p.tab.n_steps;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.steps);
+        uint4* dst = reinterpret_cast<uint4*>(s_steps);
+        for (int i = threadIdx.x; i < M * 3; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (stage_angles) {
+        const int T = p.tab.n_angles;
+        const int total = samples * T;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            const int bl = idx / T, j = idx - bl * T;
+            double sn, cs;
+            sincos(__ldg(p.angles + (b0 + bl) * p.stride + j), &sn, &cs);
+            s_cs[bl * tp + j] = make_double2(cs, sn);
+        }
+    }
+    __syncthreads();
+}
+
 // DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
 // (np_simulator_sv.py:292-293, the reference's default output form); the CTA stages its
 // normalised amplitudes in shared memory and writes the outer products fully coalesced.
+// Dynamic shared memory: [steps | (cos,sin) tile] during the evolve, re-used as the DM stage.
 template <int W, bool DM>
-__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvBatchParams p) {
+__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvBatchParams p, int tp) {
     constexpr int N = 1 << W;
-    extern __shared__ double2 stage[];  // DM only: [blockDim][2^k]
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double2 dyn[];
+    StepDev* s_steps = reinterpret_cast<StepDev*>(dyn);
+    double2* s_cs = dyn + 3 * p.tab.n_steps;
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t b = b0 + threadIdx.x;
     const bool live = b < p.batch;
     const int k = p.tab.n_out;
+    const int samples = (int)min((int64_t)blockDim.x, p.batch - b0);
+    stage_plan_and_angles(p, s_steps, s_cs, tp, b0, samples, tp > 0);
+    double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
     if (live) {
-        double re[N], im[N], zr, zi;
-        const double n2 = sv_reg_evolve<W>(p, b, -1, 0.0, re, im, zr, zi);
+        if (tp > 0) {
+            const AngleStaged ang{s_cs + threadIdx.x * tp, -1, 1.0, 0.0};
+            n2 = sv_reg_evolve<W>(p, s_steps, b, ang, re, im, zr, zi);
+        } else {
+            const AngleGlobal ang{p.angles + b * p.stride, -1, 0.0};
+            n2 = sv_reg_evolve<W>(p, s_steps, b, ang, re, im, zr, zi);
+        }
+    }
+    if constexpr (DM) __syncthreads();  // everyone is done with s_steps / s_cs: re-use as stage
+    if (live) {
         const double zn = zr * zr + zi * zi;
         const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
         if (p.status) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+        if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
         const double r = rsqrt(n2) * rsqrt(zn);
         const double ur = zr * r, ui = zi * r;  // unit phase / norm
-        double2* o = DM ? (stage + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
+        double2* o = DM ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int d = p.tab.out_dst[i];
@@ -152,13 +221,11 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvB
     }
     if constexpr (DM) {
         __syncthreads();
-        const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
-        const int64_t nlive = min((int64_t)blockDim.x, p.batch - b0);
-        const int64_t total = nlive << (2 * k);
+        const int64_t total = (int64_t)samples << (2 * k);
         double2* o = p.out + (b0 << (2 * k));
         const uint32_t km = (1u << k) - 1u;
         for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
-            const double2* sv = stage + ((e >> (2 * k)) << k);
+            const double2* sv = dyn + ((e >> (2 * k)) << k);
             const double2 x = sv[(e >> k) & km], y = sv[e & km];
             o[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
         }
@@ -277,6 +344,7 @@ __global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_
     const double zn = zr * zr + zi * zi;
     const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
     if (p.status && tid == 0) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+    if (!ok && p.status_any && tid == 0) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
     const double r = rsqrt(n2) * rsqrt(zn);
     const double ur = zr * r, ui = zi * r;
     if (!dm_out) {

@@ -36,42 +36,26 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-class _HostPipeline:
-    """Chunked host<->device pipeline for `run_batch` on host arrays: chunk c's H2D copy, kernel and
-    D2H copy are queued on stream c % n_streams, so the PCIe transfers of neighbouring chunks
-    overlap the kernel and each other (full duplex).  Owns persistent device buffers and two
-    rotating pinned output buffers (no allocation in steady state)."""
+class _HostBuffers:
+    """Persistent device workspace + two rotating page-locked output buffers for the host-array
+    path of `run_batch` (mbqc_run_batch_sv_host): no allocation in steady state."""
 
-    def __init__(self, dev, n_streams: int = 3, chunks: int = 6):
+    def __init__(self, dev):
         self.dev = dev
-        self.streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-        self.chunks = chunks
-        self.d_in = None
-        self.d_out = None
-        self.d_status = None
+        self.d_work = None
         self.h_in = None
         self.h_out = [None, None]
-        self.h_flag = [None, None]
         self.turn = 0
 
-    @staticmethod
-    def _fits(t, shape, dtype):
-        return t is not None and t.dtype == dtype and t.numel() >= int(np.prod(shape))
-
-    def buffers(self, batch, T, out_elems):
-        if not self._fits(self.d_in, (batch, T), torch.float64):
-            self.d_in = torch.empty(batch * T, dtype=torch.float64, device=self.dev)
-            self.h_in = torch.empty(batch * T, dtype=torch.float64).pin_memory()
-            self.d_status = torch.empty(batch, dtype=torch.int32, device=self.dev)
-        if not self._fits(self.d_out, (batch, out_elems), torch.complex128):
-            self.d_out = torch.empty(batch * out_elems, dtype=torch.complex128, device=self.dev)
-            self.h_out = [torch.empty(batch * out_elems, dtype=torch.complex128).pin_memory() for _ in range(2)]
-            self.h_flag = [torch.zeros(self.chunks, dtype=torch.int32).pin_memory() for _ in range(2)]
+    def get(self, work_bytes, in_elems, out_elems):
+        if self.d_work is None or self.d_work.numel() < work_bytes:
+            self.d_work = torch.empty(int(work_bytes), dtype=torch.uint8, device=self.dev)
+        if self.h_in is None or self.h_in.numel() < in_elems:
+            self.h_in = torch.empty(max(in_elems, 1), dtype=torch.float64).pin_memory()
+        if self.h_out[0] is None or self.h_out[0].numel() < out_elems:
+            self.h_out = [torch.empty(out_elems, dtype=torch.complex128).pin_memory() for _ in range(2)]
         self.turn ^= 1
-        return (self.d_in[: batch * T].view(batch, T), self.h_in[: batch * T].view(batch, T),
-                self.d_out[: batch * out_elems].view(batch, out_elems),
-                self.h_out[self.turn][: batch * out_elems].view(batch, out_elems),
-                self.d_status[:batch], self.h_flag[self.turn])
+        return self.d_work, self.h_in, self.h_out[self.turn]
 
 
 class _CudaPatternBase(BaseSimulator):
@@ -196,6 +180,7 @@ class _CudaPatternBase(BaseSimulator):
         if input_state is not None:
             self.input_state = np.asarray(input_state)
             self._d_input = None
+            self._input_synced = False
         self._angles_seen[:] = 0.0
         self.outcomes = {}
 
@@ -279,7 +264,9 @@ class CudaSimulatorSV(_CudaPatternBase):
             return out
 
     def _run_plan_host(self, dplan, angles, input_states, code, check, copy):
-        """Host arrays in, host arrays out: pinned, chunked, multi-stream pipeline."""
+        """Host arrays in, host arrays out through the C-level chunked H2D/kernel/D2H pipeline."""
+        import ctypes as C
+
         dev = self._dev()
         lib = _lib.load()
         if isinstance(angles, torch.Tensor):
@@ -298,44 +285,25 @@ class CudaSimulatorSV(_CudaPatternBase):
         out_elems = dim if code == _lib.OUT_SV else dim * dim
         with torch.cuda.device(dev):
             if self._pipe is None or self._pipe.dev != dev:
-                self._pipe = _HostPipeline(dev)
-            pipe = self._pipe
-            d_in, h_in, d_out, h_out, d_status, h_flag = pipe.buffers(batch, max(T, 1), out_elems)
+                self._pipe = _HostBuffers(dev)
+            need = lib.mbqc_host_workspace_bytes(dplan.handle, batch, code)
+            d_work, h_in, h_out = self._pipe.get(need, batch * T, batch * out_elems)
             inp, mode = self._stage_inputs(input_states, batch, dev)
-            pinned = src.is_pinned()
-            n_chunks = max(1, min(pipe.chunks, batch // 2048))
-            bounds = np.linspace(0, batch, n_chunks + 1).astype(np.int64)
-            cur = torch.cuda.current_stream(dev)
-            start = torch.cuda.Event()
-            start.record(cur)
-            h_flag.zero_()
-            for c in range(n_chunks):
-                lo, hi = int(bounds[c]), int(bounds[c + 1])
-                if hi == lo:
-                    continue
-                st = pipe.streams[c % len(pipe.streams)]
-                st.wait_event(start)
-                with torch.cuda.stream(st):
-                    if T > 0:
-                        if pinned:
-                            d_in[lo:hi].copy_(src[lo:hi], non_blocking=True)
-                        else:
-                            h_in[lo:hi].copy_(src[lo:hi])
-                            d_in[lo:hi].copy_(h_in[lo:hi], non_blocking=True)
-                    _lib.check(lib.mbqc_run_batch_sv(dplan.handle, d_in[lo:hi].data_ptr(), max(T, 1), _ptr(inp), mode,
-                                                     hi - lo, d_out[lo:hi].data_ptr(), code,
-                                                     d_status[lo:hi].data_ptr(), st.cuda_stream))
-                    h_out[lo:hi].copy_(d_out[lo:hi], non_blocking=True)
-                    if check:
-                        h_flag[c : c + 1].copy_(d_status[lo:hi].max().reshape(1), non_blocking=True)
-            for st in pipe.streams[: min(n_chunks, len(pipe.streams))]:
-                st.synchronize()
-            if check and int(h_flag.max()) & _lib.STATUS_BAD_NORM:
+            if inp is not None and not getattr(self, "_input_synced", False):
+                torch.cuda.current_stream(dev).synchronize()  # the pipeline runs on its own streams
+                self._input_synced = True
+            if not src.is_pinned() and batch * T >= (1 << 16):
+                h_in[: batch * T].view(batch, T).copy_(src)  # stage large pageable input once
+                src = h_in[: batch * T].view(batch, T)
+            flag = C.c_int32(0)
+            _lib.check(lib.mbqc_run_batch_sv_host(dplan.handle, src.data_ptr(), max(T, 1), _ptr(inp), mode,
+                                                  batch, h_out.data_ptr(), code, d_work.data_ptr(),
+                                                  d_work.numel(), C.byref(flag), 0))
+            if check and (flag.value & _lib.STATUS_BAD_NORM):
                 raise ValueError("qstate has nan, you might want to increase the window size")
             self.last_status = None
-            res = h_out.numpy()
-            if code == _lib.OUT_DM:
-                res = res.reshape(batch, dim, dim)
+            res = h_out[: batch * out_elems].numpy()
+            res = res.reshape(batch, dim) if code == _lib.OUT_SV else res.reshape(batch, dim, dim)
             return res.copy() if copy else res
 
     def measure(self, angle: float) -> Tuple[np.ndarray, int]:

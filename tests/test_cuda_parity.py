@@ -264,3 +264,67 @@ def test_gradient_kernel_matches_reference_golden():
     assert np.allclose(grad[0], g["psr"], atol=1e-11, rtol=0)
     grad_fd = psr_gradient_batched(ps, x[None, :], from_cplx(g["target"]), shift=1e-5)
     assert np.allclose(grad_fd[0], g["fd"], atol=1e-6, rtol=0)
+
+
+def test_host_pipeline_pinned_and_pageable_agree():
+    """run_batch on host arrays goes through mbqc_run_batch_sv_host (chunked, multi-stream)."""
+    gs = mb.templates.grid_cluster(2, 6)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    B = 20000  # several chunks, ragged last chunk
+    ang = np.random.default_rng(8).uniform(0, 2 * np.pi, (B, 10))
+    dev_out = ps.run_batch(torch.from_numpy(ang).cuda()).cpu().numpy()
+    pinned = mb.pinned_empty((B, 10))
+    pinned.copy_(torch.from_numpy(ang))
+    a = ps.run_batch(ang)
+    b = ps.run_batch(pinned, copy=False)
+    assert np.array_equal(a, dev_out) and np.array_equal(b, dev_out)
+    c = ps.run_batch(pinned, output_form="dm")
+    assert c.shape == (B, 4, 4)
+    assert np.allclose(c, dev_out[:, :, None] * dev_out.conj()[:, None, :], atol=1e-14)
+    # tiny and empty batches
+    assert ps.run_batch(ang[:1]).shape == (1, 4)
+    assert ps.run_batch(np.zeros((0, 10))).shape == (0, 4)
+
+
+def test_long_pattern_unstaged_angles_and_renormalisation():
+    """T large enough that the (cos,sin) tile does not fit shared memory -> global-angle fallback;
+    also exercises the periodic renormalisation (> 16 steps)."""
+    gs = mb.templates.linear_cluster(60)
+    pat = PatternData.from_circuit(gs)
+    ang = np.random.default_rng(12).uniform(0, 2 * np.pi, (64, 59))
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    got = ps.run_batch(ang)
+    want = matrix_free.linear_cluster_analytic(ang)
+    infid = 1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2
+    assert np.max(np.abs(infid)) < INFID_TOL
+    gs2 = mb.templates.grid_cluster(2, 40)
+    ang2 = np.random.default_rng(13).uniform(0, 2 * np.pi, (16, 78))
+    got2 = mb.PatternSimulator(gs2, backend="cuda-sv").run_batch(ang2)
+    want2 = matrix_free.run_sv_batch(PatternData.from_circuit(gs2), ang2)
+    infid = 1 - np.abs(np.sum(got2.conj() * want2, axis=1)) ** 2
+    assert np.max(np.abs(infid)) < INFID_TOL
+
+
+def test_batched_gradient_random_patterns():
+    from mentpy_b200.gradients import psr_gradient_batched
+    from scipy.stats import unitary_group
+
+    for name, args in (("grid_cluster", [2, 4]), ("linear_cluster", [6]), ("grid_cluster", [3, 4])):
+        gs = getattr(mb.templates, name)(*args)
+        pat = PatternData.from_circuit(gs)
+        T, k = len(gs.trainable_nodes), len(gs.output_nodes)
+        X = np.random.default_rng(3).uniform(0, 2 * np.pi, (9, T))
+        tgt = unitary_group.rvs(2**k, random_state=4)[:, 0]
+        ps = mb.PatternSimulator(gs, backend="cuda-sv")
+        grad, cost = psr_gradient_batched(ps, X, tgt, return_cost=True)
+
+        def cost_fn(x):
+            psi = matrix_free.run_sv_batch(pat, x)[0]
+            return 1 - abs(np.vdot(tgt, psi)) ** 2
+
+        for b in range(3):
+            assert abs(cost[b] - cost_fn(X[b])) < 1e-12
+            for i in range(T):
+                e = np.zeros(T); e[i] = 1.5
+                want = (cost_fn(X[b] + e) - cost_fn(X[b] - e)) / 3.0
+                assert abs(grad[b, i] - want) < 1e-11
