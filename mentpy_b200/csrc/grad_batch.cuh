@@ -31,27 +31,37 @@ __device__ __forceinline__ double sv_reg_cost(const SvBatchParams& p, const Step
 
 // One thread per (angle vector b, parameter i), parameter index fastest, so the T threads of one
 // angle vector sit next to each other and share its staged (cos, sin) row: one sincos per angle
-// instead of one per angle per shifted evaluation.  The CTA covers `spb` whole angle vectors.
+// instead of one per angle per shifted evaluation, and a shift is a rotation of that pair.
+// The CTA covers `spb` whole angle vectors (spb * T <= 128 threads).
 template <int W>
-__global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant__ SvBatchParams p, int tp, int spb) {
+__global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant__ SvBatchParams p, int staged, int spb) {
     extern __shared__ double2 dyn[];
-    StepDev* s_steps = reinterpret_cast<StepDev*>(dyn);
-    double2* s_cs = dyn + 3 * p.tab.n_steps;
     const int T = p.tab.n_angles;
+    StepDev* s_steps = reinterpret_cast<StepDev*>(dyn);
+    double2* s_cs = dyn + 3 * p.tab.n_steps;  // [spb][T] : element e = bl * T + i, pitch 1 per column
     const int64_t b0 = (int64_t)blockIdx.x * spb;
     const int samples = (int)min((int64_t)spb, p.batch - b0);
-    stage_plan_and_angles(p, s_steps, s_cs, tp, b0, samples, tp > 0);
+    stage_steps(p, s_steps);
     const int bl = threadIdx.x / T;
     const int i = threadIdx.x - bl * T;
-    if (bl >= samples) return;
+    const bool live = bl < samples;
+    if (staged && live) {  // one angle per thread: a single round of loads for the whole CTA
+        double sn, cs;
+        sincos(__ldg(p.angles + (b0 + bl) * p.stride + i), &sn, &cs);
+        s_cs[threadIdx.x] = make_double2(cs, sn);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) return;
     const int64_t b = b0 + bl;
     double cp, cm, c0 = 0.0;
-    if (tp > 0) {
+    if (staged) {
         double ss, cs;
         sincos(p.shift, &ss, &cs);
-        cp = sv_reg_cost<W>(p, s_steps, b, AngleStaged{s_cs + bl * tp, i, cs, ss});
-        cm = sv_reg_cost<W>(p, s_steps, b, AngleStaged{s_cs + bl * tp, i, cs, -ss});
-        if (p.cost && i == 0) c0 = sv_reg_cost<W>(p, s_steps, b, AngleStaged{s_cs + bl * tp, -1, 1.0, 0.0});
+        const double2* row = s_cs + bl * T;
+        cp = sv_reg_cost<W>(p, s_steps, b, AngleStaged{row, 1, i, cs, ss});
+        cm = sv_reg_cost<W>(p, s_steps, b, AngleStaged{row, 1, i, cs, -ss});
+        if (p.cost && i == 0) c0 = sv_reg_cost<W>(p, s_steps, b, AngleStaged{row, 1, -1, 1.0, 0.0});
     } else {
         const double* row = p.angles + b * p.stride;
         cp = sv_reg_cost<W>(p, s_steps, b, AngleGlobal{row, i, p.shift});

@@ -187,12 +187,12 @@ static void fill_sv_params(SvBatchParams& p, const mbqc_plan* plan, const double
     p.status = d_status;
 }
 
-// dynamic shared memory of the register kernels: step records + the CTA's (cos, sin) tile
-// (rows of `tp` double2, tp odd); tp = 0 selects the unstaged fallback for very long angle vectors
-static int staged_row_pitch(int n_angles, int rows, size_t steps_bytes, size_t budget) {
+// dynamic shared memory of the register kernels: step records, the CTA's (cos, sin) tile and
+// its raw angle tile; returns 0 when the tile does not fit the budget (unstaged fallback)
+static size_t staged_bytes(int n_angles, int rows, size_t steps_bytes, size_t budget) {
     if (n_angles <= 0) return 0;
-    const int tp = n_angles | 1;
-    return (steps_bytes + (size_t)rows * tp * sizeof(double2) <= budget) ? tp : 0;
+    const size_t need = steps_bytes + (size_t)rows * n_angles * (sizeof(double2) + sizeof(double));
+    return need <= budget ? need : 0;
 }
 
 template <bool DM>
@@ -200,15 +200,15 @@ static int launch_sv_reg(const SvBatchParams& p, cudaStream_t st) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
     const size_t steps_bytes = (size_t)p.tab.n_steps * sizeof(StepDev);
-    const int tp = staged_row_pitch(p.tab.n_angles, threads, steps_bytes, 96 * 1024);
-    size_t smem = steps_bytes + (size_t)threads * tp * sizeof(double2);
+    const size_t staged = staged_bytes(p.tab.n_angles, threads, steps_bytes, 100 * 1024);
+    size_t smem = staged ? staged : steps_bytes;
     if (DM) {
         const size_t stage = ((size_t)threads << p.tab.n_out) * sizeof(double2);
         if (stage > smem) smem = stage;
     }
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(p, tp);
+        kern<<<blocks, threads, smem, st>>>(p, staged ? 1 : 0);
         return after_launch("sv_reg_kernel");
     };
     switch (p.tab.window) {
@@ -412,13 +412,13 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     const int spb = 128 / T;  // whole angle vectors per CTA
     const int threads = spb * T;
     const size_t steps_bytes = (size_t)plan->tab.n_steps * sizeof(StepDev);
-    const int tp = staged_row_pitch(T, spb, steps_bytes, 96 * 1024);
-    const size_t smem = steps_bytes + (size_t)spb * tp * sizeof(double2);
+    const int staged = 1;  // spb * T <= 128 pairs always fit
+    const size_t smem = steps_bytes + (size_t)spb * T * sizeof(double2);
     const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
     cudaStream_t st = (cudaStream_t)stream;
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(p, tp, spb);
+        kern<<<blocks, threads, smem, st>>>(p, staged, spb);
         return MBQC_OK;
     };
     switch (w) {

@@ -76,11 +76,12 @@ struct AngleGlobal {
     }
 };
 struct AngleStaged {
-    const double2* row;  // shared memory, (cos, sin) per angle column
+    const double2* col0;  // shared memory: (cos, sin) of angle column j at col0[j * pitch]
+    int pitch;
     int shift_col;
     double cs, ss;  // cos / sin of the shift
     __device__ __forceinline__ void get(int idx, double& c, double& s) const {
-        const double2 v = row[idx];
+        const double2 v = col0[idx * pitch];
         c = v.x;
         s = v.y;
         if (idx == shift_col) {
@@ -150,32 +151,52 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const St
     return n2;
 }
 
-// Shared-memory staging done by every CTA of the register kernels before the evolve loop:
-//   s_steps [n_steps]            the plan's step records (one coalesced copy instead of a
-//                                dependent global load per step)
-//   s_cs    [samples][tp]        (cos, sin) of every angle of the CTA's samples; tp is odd so the
-//                                per-thread row reads are bank-conflict free
-// `samples` = number of angle vectors the CTA covers starting at sample b0.
-__device__ __forceinline__ void stage_plan_and_angles(const SvBatchParams& p, StepDev* s_steps,
-                                                      double2* s_cs, int tp, int64_t b0, int samples,
-                                                      bool stage_angles) {
-    const int M = p.tab.n_steps;
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(p.steps);
-        uint4* dst = reinterpret_cast<uint4*>(s_steps);
-        for (int i = threadIdx.x; i < M * 3; i += blockDim.x) dst[i] = __ldg(src + i);
-    }
-    if (stage_angles) {
-        const int T = p.tab.n_angles;
+// Shared-memory staging done by every CTA of the register kernels before the evolve loop.
+//   s_steps [n_steps]        the plan's step records (one coalesced copy instead of a dependent
+//                            global load per step)
+//   s_raw   [samples][T]     the CTA's angle tile, fetched with cp.async so that ALL of its loads
+//                            are in flight together (one DRAM latency for the whole pattern)
+//   s_cs    [T][pitch]       (cos, sin) per angle, column-major: thread `row` converts its own row
+//                            (independent sincos evaluations -> ILP) and later reads
+//                            s_cs[col * pitch + row], conflict-free across the warp
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__device__ __forceinline__ void stage_steps(const SvBatchParams& p, StepDev* s_steps) {
+    const char* src = reinterpret_cast<const char*>(p.steps);
+    char* dst = reinterpret_cast<char*>(s_steps);
+    for (int i = threadIdx.x; i < p.tab.n_steps * 3; i += blockDim.x) cp_async16(dst + 16 * i, src + 16 * i);
+}
+
+// rows [b0, b0+samples) of the angle matrix -> s_raw[samples][T]
+__device__ __forceinline__ void stage_raw_angles(const SvBatchParams& p, double* s_raw, int64_t b0, int samples) {
+    const int T = p.tab.n_angles;
+    if (p.stride == T) {
+        const double* src = p.angles + b0 * T;
         const int total = samples * T;
-        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-            const int bl = idx / T, j = idx - bl * T;
-            double sn, cs;
-            sincos(__ldg(p.angles + (b0 + bl) * p.stride + j), &sn, &cs);
-            s_cs[bl * tp + j] = make_double2(cs, sn);
-        }
+        for (int i = threadIdx.x; i < total; i += blockDim.x) cp_async8(s_raw + i, src + i);
+    } else {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = wid; r < samples; r += nw)
+            for (int j = lane; j < T; j += 32) cp_async8(s_raw + r * T + j, p.angles + (b0 + r) * p.stride + j);
     }
-    __syncthreads();
+}
+
+// thread `row` turns its own angle row into (cos, sin) pairs, column-major with pitch `pitch`
+__device__ __forceinline__ void convert_own_row(const double* s_raw, double2* s_cs, int T, int row, int pitch) {
+#pragma unroll 2
+    for (int j = 0; j < T; ++j) {
+        double sn, cs;
+        sincos(s_raw[row * T + j], &sn, &cs);
+        s_cs[j * pitch + row] = make_double2(cs, sn);
+    }
 }
 
 // DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
@@ -183,21 +204,27 @@ __device__ __forceinline__ void stage_plan_and_angles(const SvBatchParams& p, St
 // normalised amplitudes in shared memory and writes the outer products fully coalesced.
 // Dynamic shared memory: [steps | (cos,sin) tile] during the evolve, re-used as the DM stage.
 template <int W, bool DM>
-__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvBatchParams p, int tp) {
+__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvBatchParams p, int staged) {
     constexpr int N = 1 << W;
     extern __shared__ double2 dyn[];
+    const int T = p.tab.n_angles;
     StepDev* s_steps = reinterpret_cast<StepDev*>(dyn);
-    double2* s_cs = dyn + 3 * p.tab.n_steps;
+    double2* s_cs = dyn + 3 * p.tab.n_steps;                                   // [T][blockDim]
+    double* s_raw = reinterpret_cast<double*>(s_cs + (size_t)T * blockDim.x);  // [blockDim][T]
     const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
     const int64_t b = b0 + threadIdx.x;
     const bool live = b < p.batch;
     const int k = p.tab.n_out;
     const int samples = (int)min((int64_t)blockDim.x, p.batch - b0);
-    stage_plan_and_angles(p, s_steps, s_cs, tp, b0, samples, tp > 0);
+    stage_steps(p, s_steps);
+    if (staged) stage_raw_angles(p, s_raw, b0, samples);
+    cp_async_wait_all();
+    __syncthreads();
     double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
     if (live) {
-        if (tp > 0) {
-            const AngleStaged ang{s_cs + threadIdx.x * tp, -1, 1.0, 0.0};
+        if (staged) {
+            convert_own_row(s_raw, s_cs, T, threadIdx.x, blockDim.x);  // own row only: no barrier needed
+            const AngleStaged ang{s_cs + threadIdx.x, (int)blockDim.x, -1, 1.0, 0.0};
             n2 = sv_reg_evolve<W>(p, s_steps, b, ang, re, im, zr, zi);
         } else {
             const AngleGlobal ang{p.angles + b * p.stride, -1, 0.0};

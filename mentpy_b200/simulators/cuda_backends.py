@@ -283,6 +283,8 @@ class CudaSimulatorSV(_CudaPatternBase):
         batch, T = src.shape
         dim = 2 ** dplan.n_out
         out_elems = dim if code == _lib.OUT_SV else dim * dim
+        if batch == 0:
+            return np.zeros((0, dim) if code == _lib.OUT_SV else (0, dim, dim), dtype=np.complex128)
         with torch.cuda.device(dev):
             if self._pipe is None or self._pipe.dev != dev:
                 self._pipe = _HostBuffers(dev)
