@@ -10,6 +10,8 @@
 #include "dm_batch.cuh"
 #include "grad_batch.cuh"
 #include "sv_batch.cuh"
+#include "sv_reg.cuh"
+#include <vector>
 
 using namespace mbqc;
 
@@ -137,8 +139,56 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
     if (e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(StepDev) * (n_steps > 0 ? n_steps : 1));
     if (e == cudaSuccess && n_steps > 0)
         e = cudaMemcpy(pl->d_steps, pl->h_steps, sizeof(StepDev) * n_steps, cudaMemcpyHostToDevice);
+    pl->d_reg_blob = nullptr;
+    pl->d_reg_cols = pl->d_reg_signs = nullptr;
+    pl->d_reg_fixed = nullptr;
+    pl->reg_n_fixed = pl->reg_sign_pitch = pl->reg_periodic = 0;
+    if (e == cudaSuccess && window <= MBQC_MAX_WINDOW_REG) {
+        // register-kernel tables: packed (slot<<16 | column), sign words per pair, fixed (cos,sin)
+        const int np = 1 << (window - 1);
+        const int sp = np < 4 ? 4 : np;
+        const int mpad = (n_steps + 3) & ~3;
+        std::vector<uint32_t> signs((size_t)(n_steps > 0 ? n_steps : 1) * sp, 0u), cols(mpad > 0 ? mpad : 4, 0u);
+        std::vector<double2> fixed;
+        int periodic = 1;
+        for (int m = 0; m < n_steps; ++m) {
+            const StepDev& d = pl->h_steps[m];
+            if (d.slot != window - 1 - (m % window)) periodic = 0;
+            uint32_t col;
+            if (d.angle_idx >= 0) {
+                col = (uint32_t)d.angle_idx;
+            } else {
+                col = (uint32_t)(n_angles + (int)fixed.size());
+                fixed.push_back(make_double2(d.fc, d.fs));
+            }
+            cols[m] = ((uint32_t)d.slot << 16) | (col & 0xffffu);
+            int pidx = 0;
+            for (uint32_t i = 0; i < (1u << window); ++i) {
+                if ((i >> d.slot) & 1u) continue;
+                const uint32_t j = i | (1u << d.slot);
+                signs[(size_t)m * sp + pidx] = ((d.flipmask >> j) & 1u) ? 0x80000000u : 0u;
+                ++pidx;
+            }
+        }
+        if (n_angles + (int)fixed.size() > 0xffff) periodic = 0;  // (never for w <= 5 patterns in practice)
+        const size_t b_signs = signs.size() * 4, b_cols = cols.size() * 4, b_fixed = (fixed.size() ? fixed.size() : 1) * 16;
+        e = cudaMalloc(&pl->d_reg_blob, b_signs + b_cols + b_fixed);
+        if (e == cudaSuccess) {
+            char* base = (char*)pl->d_reg_blob;
+            e = cudaMemcpy(base, signs.data(), b_signs, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(base + b_signs, cols.data(), b_cols, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess && !fixed.empty()) e = cudaMemcpy(base + b_signs + b_cols, fixed.data(), fixed.size() * 16, cudaMemcpyHostToDevice);
+            pl->d_reg_signs = (const uint32_t*)base;
+            pl->d_reg_cols = (const uint32_t*)(base + b_signs);
+            pl->d_reg_fixed = (const double2*)(base + b_signs + b_cols);
+            pl->reg_n_fixed = (int)fixed.size();
+            pl->reg_sign_pitch = sp;
+            pl->reg_periodic = periodic;
+        }
+    }
     if (e != cudaSuccess) {
         if (pl->d_steps) cudaFree(pl->d_steps);
+        if (pl->d_reg_blob) cudaFree(pl->d_reg_blob);
         delete[] pl->h_steps;
         delete pl;
         return cuda_fail(e, "plan upload");
@@ -150,6 +200,7 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
 void mbqc_plan_destroy(mbqc_plan* plan) {
     if (!plan) return;
     if (plan->d_steps) cudaFree(plan->d_steps);
+    if (plan->d_reg_blob) cudaFree(plan->d_reg_blob);
     delete[] plan->h_steps;
     delete plan;
 }
@@ -187,28 +238,35 @@ static void fill_sv_params(SvBatchParams& p, const mbqc_plan* plan, const double
     p.status = d_status;
 }
 
-// dynamic shared memory of the register kernels: step records, the CTA's (cos, sin) tile and
-// its raw angle tile; returns 0 when the tile does not fit the budget (unstaged fallback)
-static size_t staged_bytes(int n_angles, int rows, size_t steps_bytes, size_t budget) {
-    if (n_angles <= 0) return 0;
-    const size_t need = steps_bytes + (size_t)rows * n_angles * (sizeof(double2) + sizeof(double));
-    return need <= budget ? need : 0;
+static void fill_reg_params(SvRegParams& rp, const SvBatchParams& p, const mbqc_plan* plan) {
+    rp.base = p;
+    rp.reg.cols = plan->d_reg_cols;
+    rp.reg.signs = plan->d_reg_signs;
+    rp.reg.fixed = plan->d_reg_fixed;
+    rp.reg.n_fixed = plan->reg_n_fixed;
+    rp.reg.sign_pitch = plan->reg_sign_pitch;
+    rp.reg.periodic = plan->reg_periodic;
 }
 
+// dynamic shared memory of the register kernels: plan tables + (staged) the CTA's (cos, sin)
+// tile and raw angle tile; staging is skipped when the tile does not fit the budget
 template <bool DM>
-static int launch_sv_reg(const SvBatchParams& p, cudaStream_t st) {
+static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
-    const size_t steps_bytes = (size_t)p.tab.n_steps * sizeof(StepDev);
-    const size_t staged = staged_bytes(p.tab.n_angles, threads, steps_bytes, 100 * 1024);
-    size_t smem = staged ? staged : steps_bytes;
+    SvRegParams rp;
+    fill_reg_params(rp, p, plan);
+    const size_t tables = reg_smem_tables_bytes(p.tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
+    const size_t tile = (size_t)threads * p.tab.n_angles * (sizeof(double2) + sizeof(double));
+    const int staged = (p.tab.n_angles > 0 && tables + tile <= 100 * 1024) ? 1 : 0;
+    size_t smem = tables + (staged ? tile : 0);
     if (DM) {
         const size_t stage = ((size_t)threads << p.tab.n_out) * sizeof(double2);
         if (stage > smem) smem = stage;
     }
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(p, staged ? 1 : 0);
+        kern<<<blocks, threads, smem, st>>>(rp, staged);
         return after_launch("sv_reg_kernel");
     };
     switch (p.tab.window) {
@@ -220,10 +278,10 @@ static int launch_sv_reg(const SvBatchParams& p, cudaStream_t st) {
     }
 }
 
-static int launch_sv(const SvBatchParams& p, int out_form, cudaStream_t st) {
+static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st) {
     const int w = p.tab.window;
     if (w <= MBQC_MAX_WINDOW_REG)
-        return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, st) : launch_sv_reg<false>(p, st);
+        return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, plan, st) : launch_sv_reg<false>(p, plan, st);
     if (w > MBQC_MAX_WINDOW_SMEM_SV)
         return fail(MBQC_E_UNSUPPORTED, "batched SV covers window <= %d (got %d); use the streaming calls", MBQC_MAX_WINDOW_SMEM_SV, w);
     // threads per sample: one per pair up to 256
@@ -253,7 +311,7 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
     if (batch == 0) return MBQC_OK;
     SvBatchParams p;
     fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
-    return launch_sv(p, out_form, (cudaStream_t)stream);
+    return launch_sv(p, plan, out_form, (cudaStream_t)stream);
 }
 
 // ---- host-buffer pipeline --------------------------------------------------------------------
@@ -340,7 +398,7 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
         if (input_mode == MBQC_INPUT_BATCH) din = (const char*)d_inputs + ((size_t)lo << plan->tab.n_in) * sizeof(double2);
         fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, d_out + lo * out_elems, nullptr);
         p.status_any = d_any;
-        rc = launch_sv(p, out_form, st);
+        rc = launch_sv(p, plan, out_form, st);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
                                  cudaMemcpyDeviceToHost, st));
@@ -411,14 +469,14 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     if (T > 128) return fail(MBQC_E_UNSUPPORTED, "fused gradient covers at most 128 angles (got %d)", T);
     const int spb = 128 / T;  // whole angle vectors per CTA
     const int threads = spb * T;
-    const size_t steps_bytes = (size_t)plan->tab.n_steps * sizeof(StepDev);
-    const int staged = 1;  // spb * T <= 128 pairs always fit
-    const size_t smem = steps_bytes + (size_t)spb * T * sizeof(double2);
+    SvRegParams rp;
+    fill_reg_params(rp, p, plan);
+    const size_t smem = reg_smem_tables_bytes(plan->tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed) + (size_t)threads * sizeof(double2);
     const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
     cudaStream_t st = (cudaStream_t)stream;
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(p, staged, spb);
+        kern<<<blocks, threads, smem, st>>>(rp, spb);
         return MBQC_OK;
     };
     switch (w) {

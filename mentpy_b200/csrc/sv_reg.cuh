@@ -1,0 +1,411 @@
+// Register-resident batched state-vector kernel (window w <= 5): the whole pattern in ONE launch,
+// one thread per angle set, the 2^w amplitudes never leave the register file.
+//
+// Replaces NumpySimulatorSV.run / measure / measure_ment / reset and the helpers they call
+// (mentpy/simulators/np_simulator_sv.py:164-358, calculator/state_ops.py:42-74,
+// operators/gates.py:62-72,127-143) -- see common.cuh for the per-measurement identity.
+//
+// What bounds it (ncu, profiles/): HBM traffic is only angles in / amplitudes out (144 B per
+// evaluation on grid_cluster(2,6)), the work is ~45 FP64 instructions per measurement, so the
+// kernel is FP64-pipe / issue bound.  Design points that follow from that:
+//   * all angle loads of a CTA are issued together with cp.async (one DRAM latency per pattern,
+//     not one per measurement) and converted to (cos, sin) by independent evaluations;
+//   * sincos is a branch-light Cody-Waite + fdlibm-kernel implementation with its constants in
+//     the constant bank (FMA operands), ~1/2 the instructions of the library call;
+//   * measured slots follow m -> w-1-(m mod w) for every reference schedule (window position 0
+//     is always measured and its slot recycled), so the step loop is unrolled by w with
+//     compile-time slots: no switch, no register shuffling between cases;
+//   * CZ signs come as ready-made sign words (0 / 0x80000000) from shared memory and are applied
+//     with one LOP3 per word on the integer pipe, keeping the FP64 pipe for the FMAs.
+#pragma once
+#include <utility>
+
+#include "sv_batch.cuh"
+
+namespace mbqc {
+
+// device tables for the register kernel, built once per plan
+struct RegPlanDev {
+    const uint32_t* __restrict__ cols;   // [M] (slot << 16) | column; column >= T: fixed[column-T]
+    const uint32_t* __restrict__ signs;  // [M][SP] sign words of the pair partners
+    const double2* __restrict__ fixed;   // [n_fixed] (cos, sin) of fixed-angle steps
+    int32_t n_fixed;
+    int32_t sign_pitch;  // SP = max(2^(w-1), 4)
+    int32_t periodic;    // slots follow w-1-(m mod w)
+};
+
+struct SvRegParams {
+    SvBatchParams base;
+    RegPlanDev reg;
+};
+
+// ---- sincos ------------------------------------------------------------------------------------
+// fdlibm __kernel_sin / __kernel_cos minimax coefficients on [-pi/4, pi/4] and the three-part
+// pi/2 used by the CUDA math library's Cody-Waite reduction.
+__constant__ double kTrig[16] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03,  -1.98412698298579493134e-04,
+    2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11,
+    1.5707963267948966e+00,      6.123233995736766e-17,       1.4973849048591698e-33,
+    6.36619772367581382433e-01};
+
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+    if (!(fabs(x) < 1.0e5)) {  // rare: large / non-finite arguments take the library path
+        sincos(x, &sn, &cs);
+        return;
+    }
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
+    const double t = fma(x, kTrig[15], magic);
+    const int q = __double2loint(t);
+    const double qd = t - magic;
+    double r = fma(qd, -kTrig[12], x);
+    r = fma(qd, -kTrig[13], r);
+    r = fma(qd, -kTrig[14], r);
+    const double z = r * r;
+    double ps = fma(kTrig[5], z, kTrig[4]);
+    double pc = fma(kTrig[11], z, kTrig[10]);
+    ps = fma(ps, z, kTrig[3]);
+    pc = fma(pc, z, kTrig[9]);
+    ps = fma(ps, z, kTrig[2]);
+    pc = fma(pc, z, kTrig[8]);
+    ps = fma(ps, z, kTrig[1]);
+    pc = fma(pc, z, kTrig[7]);
+    ps = fma(ps, z, kTrig[0]);
+    pc = fma(pc, z, kTrig[6]);
+    const double s0 = fma(r * z, ps, r);
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant: q&1 swaps, sin sign = bit1 of q, cos sign = bit1 of (q+1)
+    const double sa = (q & 1) ? c0 : s0;
+    const double ca = (q & 1) ? s0 : c0;
+    sn = flip_sign(sa, ((uint32_t)q << 30) & 0x80000000u);
+    cs = flip_sign(ca, ((uint32_t)(q + 1) << 30) & 0x80000000u);
+}
+
+// ---- angle sources -----------------------------------------------------------------------------
+// Staged: the CTA turned its angle tile into (cos, sin) pairs in shared memory (column j of row
+// `row` at col0[j * pitch]); a parameter shift is a rotation by (cos s, sin s).  Global: fallback
+// for angle vectors too long to stage (one dependent load + sincos per measurement).
+struct AngleStaged {
+    const double2* col0;
+    int pitch;
+    int n_angles;
+    const double2* fixed;
+    int shift_col;
+    double cs, ss;
+    __device__ __forceinline__ void get(uint32_t col, double& c, double& s) const {
+        if ((int)col >= n_angles) {
+            const double2 f = fixed[col - n_angles];
+            c = f.x;
+            s = f.y;
+            return;
+        }
+        const double2 v = col0[col * pitch];
+        c = v.x;
+        s = v.y;
+        if ((int)col == shift_col) {
+            c = v.x * cs - v.y * ss;
+            s = v.y * cs + v.x * ss;
+        }
+    }
+};
+struct AngleGlobal {
+    const double* row;
+    int n_angles;
+    const double2* fixed;
+    int shift_col;
+    double shift;
+    __device__ __forceinline__ void get(uint32_t col, double& c, double& s) const {
+        if ((int)col >= n_angles) {
+            const double2 f = fixed[col - n_angles];
+            c = f.x;
+            s = f.y;
+            return;
+        }
+        double th = __ldg(row + col);
+        if ((int)col == shift_col) th += shift;
+        sincos_cw(th, s, c);
+    }
+};
+
+template <class F, int... U>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, U...>) {
+    (f(std::integral_constant<int, U>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// ---- one measurement ---------------------------------------------------------------------------
+template <int W, int S>
+__device__ __forceinline__ void reg_stage(double (&re)[1 << W], double (&im)[1 << W], double c,
+                                          double s, const uint32_t* __restrict__ sg) {
+    constexpr int NP = 1 << (W - 1);
+    uint32_t w[NP < 4 ? 4 : NP];
+#pragma unroll
+    for (int q = 0; q < (NP < 4 ? 1 : NP / 4); ++q) {
+        const uint4 v = reinterpret_cast<const uint4*>(sg)[q];
+        w[4 * q + 0] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+    }
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) {
+        if (i & (1 << S)) continue;
+        const int j = i | (1 << S);
+        // t = a_i + (c - i s) a_j
+        const double tr = fma(c, re[j], fma(s, im[j], re[i]));
+        const double ti = fma(c, im[j], fma(-s, re[j], im[i]));
+        re[i] = tr;
+        im[i] = ti;
+        re[j] = flip_sign(tr, w[p]);
+        im[j] = flip_sign(ti, w[p]);
+        ++p;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void reg_step_any(double (&re)[1 << W], double (&im)[1 << W], int slot,
+                                             double c, double s, const uint32_t* sg) {
+    switch (slot) {
+        case 0: reg_stage<W, 0>(re, im, c, s, sg); break;
+        case 1: if constexpr (W > 1) reg_stage<W, 1>(re, im, c, s, sg); break;
+        case 2: if constexpr (W > 2) reg_stage<W, 2>(re, im, c, s, sg); break;
+        case 3: if constexpr (W > 3) reg_stage<W, 3>(re, im, c, s, sg); break;
+        case 4: if constexpr (W > 4) reg_stage<W, 4>(re, im, c, s, sg); break;
+        default: break;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void reg_renorm(double (&re)[1 << W], double (&im)[1 << W], double& zr, double& zi) {
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+    const double r = rsqrt(n2);
+    const double rz = rsqrt(zr * zr + zi * zi);
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) {
+        re[i] *= r;
+        im[i] *= r;
+    }
+    zr *= rz;
+    zi *= rz;
+}
+
+// shared-memory views of the plan tables staged by the CTA
+struct RegSmem {
+    const uint32_t* cols;
+    const uint32_t* signs;
+    int sign_pitch;
+};
+
+// Evolve one sample through the whole pattern.  Returns the squared norm over the output entries;
+// (zr, zi) accumulates the unnormalised reference phase prod_j (1 + e^{i theta_j}).
+template <int W, class AngleSrc>
+__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const RegSmem& sm, bool periodic,
+                                                int64_t b, const AngleSrc& ang, double (&re)[1 << W],
+                                                double (&im)[1 << W], double& zr, double& zi) {
+    constexpr int N = 1 << W;
+    const PlanTables& t = p.tab;
+    if (p.input_mode == MBQC_INPUT_PLUS) {
+        const double a = t.init_scale * exp2(-0.5 * t.n_in);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            re[i] = flip_sign(a, (t.init_sign << (31 - i)) & 0x80000000u);
+            im[i] = 0.0;
+        }
+    } else {
+        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double2 v = __ldg(in + t.init_src[i]);
+            const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
+            re[i] = flip_sign(v.x * t.init_scale, sb);
+            im[i] = flip_sign(v.y * t.init_scale, sb);
+        }
+    }
+    zr = 1.0;
+    zi = 0.0;
+    const int M = t.n_steps;
+    auto phase = [&](double c, double s) {  // (zr, zi) *= (1 + c, s)
+        const double pr = 1.0 + c;
+        const double nzr = fma(zr, pr, -zi * s);
+        zi = fma(zr, s, zi * pr);
+        zr = nzr;
+    };
+    if (periodic) {
+        for (int m0 = 0; m0 < M; m0 += W) {
+            static_for<W>([&](auto uc) {
+                constexpr int u = decltype(uc)::value;
+                const int m = m0 + u;
+                if (m < M) {
+                    double c, s;
+                    ang.get(sm.cols[m] & 0xffffu, c, s);
+                    phase(c, s);
+                    reg_stage<W, W - 1 - u>(re, im, c, s, sm.signs + m * sm.sign_pitch);
+                }
+            });
+            if (((m0 + W) >> 4) != (m0 >> 4)) reg_renorm<W>(re, im, zr, zi);  // long patterns
+        }
+    } else {
+        for (int m = 0; m < M; ++m) {
+            const uint32_t cw = sm.cols[m];
+            double c, s;
+            ang.get(cw & 0xffffu, c, s);
+            phase(c, s);
+            reg_step_any<W>(re, im, (int)(cw >> 16), c, s, sm.signs + m * sm.sign_pitch);
+            if ((m & 15) == 15) reg_renorm<W>(re, im, zr, zi);
+        }
+    }
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (t.out_dst[i] >= 0) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+    return n2;
+}
+
+// ---- shared-memory staging ---------------------------------------------------------------------
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// dynamic shared memory layout of the register kernels (all offsets 16-byte aligned)
+struct RegSmemLayout {
+    uint32_t* signs;   // [M][SP]
+    uint32_t* cols;    // [M] padded to 4
+    double2* fixed;    // [n_fixed]
+    double2* cs;       // [T][pitch]        (staged only)
+    double* raw;       // [rows][T]         (staged only)
+};
+__host__ __device__ __forceinline__ size_t reg_smem_tables_bytes(int M, int sp, int n_fixed) {
+    return (size_t)M * sp * 4 + (size_t)((M + 3) & ~3) * 4 + (size_t)n_fixed * 16;
+}
+__device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int sp, int n_fixed, int T, int pitch) {
+    RegSmemLayout l;
+    char* p = reinterpret_cast<char*>(base);
+    l.signs = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)M * sp * 4;
+    l.cols = reinterpret_cast<uint32_t*>(p);
+    p += (size_t)((M + 3) & ~3) * 4;
+    l.fixed = reinterpret_cast<double2*>(p);
+    p += (size_t)n_fixed * 16;
+    l.cs = reinterpret_cast<double2*>(p);
+    p += (size_t)T * pitch * 16;
+    l.raw = reinterpret_cast<double*>(p);
+    return l;
+}
+
+__device__ __forceinline__ void stage_reg_tables(const SvRegParams& p, const RegSmemLayout& l) {
+    const int M = p.base.tab.n_steps;
+    const int nsig = M * p.reg.sign_pitch / 4;
+    for (int i = threadIdx.x; i < nsig; i += blockDim.x)
+        cp_async16(reinterpret_cast<uint4*>(l.signs) + i, reinterpret_cast<const uint4*>(p.reg.signs) + i);
+    for (int i = threadIdx.x; i < M; i += blockDim.x) cp_async4(l.cols + i, p.reg.cols + i);
+    for (int i = threadIdx.x; i < p.reg.n_fixed; i += blockDim.x) cp_async16(l.fixed + i, p.reg.fixed + i);
+}
+
+// rows [b0, b0+samples) of the angle matrix -> raw[samples][T], every load in flight at once
+__device__ __forceinline__ void stage_raw_angles(const SvBatchParams& p, double* raw, int64_t b0, int samples) {
+    const int T = p.tab.n_angles;
+    if (p.stride == T) {
+        const double* src = p.angles + b0 * T;
+        const int total = samples * T;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = threadIdx.x; i < (total >> 1); i += blockDim.x) cp_async16(raw + 2 * i, src + 2 * i);
+            if ((total & 1) && threadIdx.x == 0) cp_async8(raw + total - 1, src + total - 1);
+        } else {
+            for (int i = threadIdx.x; i < total; i += blockDim.x) cp_async8(raw + i, src + i);
+        }
+    } else {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        for (int r = wid; r < samples; r += nw)
+            for (int j = lane; j < T; j += 32) cp_async8(raw + r * T + j, p.angles + (b0 + r) * p.stride + j);
+    }
+}
+
+// thread `row` turns its own angle row into (cos, sin) pairs, column-major with pitch `pitch`:
+// independent evaluations (ILP), conflict-free column reads later, no barrier needed
+__device__ __forceinline__ void convert_own_row(const double* raw, double2* cs, int T, int row, int pitch) {
+#pragma unroll 2
+    for (int j = 0; j < T; ++j) {
+        double sn, c;
+        sincos_cw(raw[row * T + j], sn, c);
+        cs[j * pitch + row] = make_double2(c, sn);
+    }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+// DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
+// (np_simulator_sv.py:292-293, the reference's default output form); the CTA stages its
+// normalised amplitudes in shared memory and writes the outer products fully coalesced.
+template <int W, bool DM>
+__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvRegParams pp, int staged) {
+    constexpr int N = 1 << W;
+    extern __shared__ double2 dyn[];
+    const SvBatchParams& p = pp.base;
+    const int T = p.tab.n_angles, M = p.tab.n_steps;
+    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed, T, blockDim.x);
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t b = b0 + threadIdx.x;
+    const bool live = b < p.batch;
+    const int k = p.tab.n_out;
+    const int samples = (int)min((int64_t)blockDim.x, p.batch - b0);
+    stage_reg_tables(pp, l);
+    if (staged) stage_raw_angles(p, l.raw, b0, samples);
+    cp_async_wait_all();
+    __syncthreads();
+    const RegSmem sm{l.cols, l.signs, pp.reg.sign_pitch};
+    double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
+    if (live) {
+        if (staged) {
+            convert_own_row(l.raw, l.cs, T, threadIdx.x, blockDim.x);
+            const AngleStaged ang{l.cs + threadIdx.x, (int)blockDim.x, T, l.fixed, -1, 1.0, 0.0};
+            n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+        } else {
+            const AngleGlobal ang{p.angles + b * p.stride, T, l.fixed, -1, 0.0};
+            n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+        }
+    }
+    if constexpr (DM) __syncthreads();  // everyone is done with the staged tables: re-use as stage
+    if (live) {
+        const double zn = zr * zr + zi * zi;
+        const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
+        if (p.status) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+        if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
+        const double r = rsqrt(n2) * rsqrt(zn);
+        const double ur = zr * r, ui = zi * r;  // unit phase / norm
+        double2* o = DM ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int d = p.tab.out_dst[i];
+            if (d >= 0) o[d] = make_double2(re[i] * ur - im[i] * ui, re[i] * ui + im[i] * ur);
+        }
+    }
+    if constexpr (DM) {
+        __syncthreads();
+        const int64_t total = (int64_t)samples << (2 * k);
+        double2* o = p.out + (b0 << (2 * k));
+        const uint32_t km = (1u << k) - 1u;
+        for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+            const double2* sv = dyn + ((e >> (2 * k)) << k);
+            const double2 x = sv[(e >> k) & km], y = sv[e & km];
+            o[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
+        }
+    }
+}
+
+}  // namespace mbqc

@@ -54,13 +54,14 @@ class LoweredPlan:
     n_angles: int
     mixed: bool
     first_window: List[int]
+    first_slots: Dict[int, int] = field(default_factory=dict)
 
     def window_nodes_after(self, n_done: int) -> List[int]:
         """Reference window content (position 0 first) after n_done measurements."""
         return self.schedule[n_done: n_done + self.window]
 
     def slot_of_after(self, n_done: int) -> Dict[int, int]:
-        slot = {v: self.window - 1 - p for p, v in enumerate(self.first_window)}
+        slot = {v: s for v, s in self.first_slots.items()}
         for st in self.steps[:n_done]:
             del slot[st.node]
             if st.append:
@@ -79,7 +80,10 @@ def _fixed_cos_sin(plane: str, angle):
 
 
 def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = None,
-          mixed: bool = False) -> LoweredPlan:
+          mixed: bool = False, slot_order: str = "msb") -> LoweredPlan:
+    """slot_order: "msb" puts window position p at slot w-1-p (reference layout; the measured slots
+    then cycle w-1, w-2, ..., 0 and the register kernel takes its unrolled path); "lsb" puts it at
+    slot p (exercises the kernels' generic slot path; results are identical)."""
     nodes = list(circuit.graph.nodes())
     n_nodes = len(nodes)
     outputs_excluded = circuit.quantum_output_nodes if mixed else circuit.output_nodes
@@ -136,13 +140,16 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
 
     w = window_size
     first_window = schedule[:w]
-    slot_of: Dict[int, int] = {v: w - 1 - p for p, v in enumerate(first_window)}
+    if slot_order not in ("msb", "lsb"):
+        raise ValueError("slot_order must be 'msb' or 'lsb'")
+    slot_of: Dict[int, int] = {v: (w - 1 - p if slot_order == "msb" else p) for p, v in enumerate(first_window)}
     init_cz = [0] * w
     for a, b in circuit.graph.edges():
         if a in slot_of and b in slot_of and a != b:
             lo, hi = sorted((slot_of[a], slot_of[b]))
             init_cz[lo] ^= 1 << hi
     input_slot = [slot_of[v] for v in circuit.input_nodes]
+    first_slots = dict(slot_of)
 
     trainable = list(circuit.trainable_nodes)
     steps: List[StepRecord] = []
@@ -185,7 +192,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
         raise NotImplementedError(f"more than {_lib.MAX_IO} input/output qubits")
     return LoweredPlan(w, n_nodes, schedule, schedule_measure, steps, list(circuit.input_nodes),
                        input_slot, init_cz, out_order, output_slot, len(trainable), mixed,
-                       first_window)
+                       first_window, first_slots)
 
 
 def window_is_valid(plan: LoweredPlan) -> bool:

@@ -69,12 +69,14 @@ class _CudaPatternBase(BaseSimulator):
         self.dev_mode = kwargs.pop("dev_mode", False)
         self.wires = kwargs.pop("wires", None)
         self.device = kwargs.pop("device", None)
+        self._slot_order = kwargs.pop("slot_order", "msb")
         if not self.force0:
             raise NotImplementedError("Numpy simulator does not support force0=False.")
         if self.dev_mode:
             raise NotImplementedError("dev_mode scheduling is not supported by the CUDA backends.")
         self._noise = self._parse_noise(kwargs)
-        self.plan: LoweredPlan = lower(mbqcircuit, self.window_size, self.schedule, mixed=self.mixed)
+        self.plan: LoweredPlan = lower(mbqcircuit, self.window_size, self.schedule, mixed=self.mixed,
+                                       slot_order=self._slot_order)
         self.window_size = self.plan.window
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure

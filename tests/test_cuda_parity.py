@@ -328,3 +328,35 @@ def test_batched_gradient_random_patterns():
                 e = np.zeros(T); e[i] = 1.5
                 want = (cost_fn(X[b] + e) - cost_fn(X[b] - e)) / 3.0
                 assert abs(grad[b, i] - want) < 1e-11
+
+
+@pytest.mark.parametrize("backend", ["cuda-sv", "cuda-dm"])
+def test_slot_layout_independence(backend):
+    """Results must not depend on which bit slot a qubit lives in: 'lsb' slot order drives the
+    register kernel through its generic (non-unrolled) slot path."""
+    rng = np.random.default_rng(21)
+    for name, args, w in (("grid_cluster", [2, 6], None), ("grid_cluster", [3, 5], 5), ("linear_cluster", [7], 3)):
+        gs = getattr(mb.templates, name)(*args)
+        gs[1] = mb.Ment("X")
+        gs[2] = mb.Ment(0.77, "XY")
+        ang = rng.uniform(0, 2 * np.pi, (33, len(gs.trainable_nodes)))
+        kw = {} if w is None else {"window_size": w}
+        a = mb.PatternSimulator(gs, backend=backend, **kw).run_batch(ang)
+        b = mb.PatternSimulator(gs, backend=backend, slot_order="lsb", **kw).run_batch(ang)
+        assert np.allclose(a, b, atol=1e-13, rtol=0)
+        pat = PatternData.from_circuit(gs)
+        want = (matrix_free.run_sv_batch if backend == "cuda-sv" else matrix_free.run_dm_batch)(pat, ang, window_size=(w or 1))
+        assert np.allclose(a, want, atol=1e-10, rtol=0)
+
+
+def test_sincos_accuracy_over_wide_angle_range():
+    """The kernel's own sincos (Cody-Waite + fdlibm kernels) against numpy over many periods,
+    through linear_cluster(2): output ~ J(-theta)|+> = (1 + e^{-i theta}, 1 - e^{-i theta})/2."""
+    gs = mb.templates.linear_cluster(3)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    th = np.concatenate([np.linspace(-50, 50, 4001), np.array([1e4 + 0.3, -9.9e4, 2e5, 1e7 + 0.1, 0.0, np.pi, -np.pi / 2])])
+    ang = np.stack([th, np.zeros_like(th)], axis=1)
+    got = ps.run_batch(ang)
+    want = matrix_free.linear_cluster_analytic(ang)
+    infid = 1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2
+    assert np.max(np.abs(infid)) < 1e-13
