@@ -277,10 +277,16 @@ def run_gpu_arm(args):
     if not args.no_graph:
         graph = torch.cuda.CUDAGraph()
         cap_stream = torch.cuda.Stream(device=dev)
+        side = [torch.cuda.Stream(device=dev) for _ in range(args.graph_branches - 1)]
         with torch.cuda.graph(graph, stream=cap_stream):
-            cs = torch.cuda.current_stream(dev).cuda_stream
-            for j in range(pool):
-                step(j, cs)
+            cur = torch.cuda.current_stream(dev)
+            for sd in side:
+                sd.wait_stream(cur)
+            for j in range(pool):  # independent batches: fork into parallel branches, join at the end
+                br = j % args.graph_branches
+                step(j, (cur if br == 0 else side[br - 1]).cuda_stream)
+            for sd in side:
+                cur.wait_stream(sd)
         graph.replay()
         barrier()
 
@@ -360,7 +366,7 @@ def run_gpu_arm(args):
             "config": {"workload": "grid_cluster(2,6) statevector, 65,536 random angle sets per step per GPU (BASELINE configs[1])",
                        "pattern": "grid_cluster(2,6)", "backend": "cuda-sv", "batch_per_gpu": BATCH,
                        "window": 3, "measurements": 10, "output": "sv [B,4] complex128",
-                       "launch_mode": "direct stream launches" if graph is None else f"CUDA graph of {pool} steps replayed",
+                       "launch_mode": "direct stream launches" if graph is None else f"CUDA graph of {pool} steps in {args.graph_branches} parallel branches, replayed",
                        "l2": f"inputs rotate through a pool of {pool} batches ({pool * per_batch / 2**20:.0f} MiB > 126 MiB L2)",
                        "parallelism": f"batch-split x{world}" + (", one final NCCL all_gather of the last step's outputs inside the timed region" if world > 1 else "")},
             "e2e": None if args.skip_e2e else {
@@ -392,6 +398,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--graph-branches", type=int, default=4, help="parallel branches of the CUDA graph (independent batches overlap)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step directly instead of replaying a CUDA graph")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline leg")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: no host end-to-end leg")

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
     const SvBatchParams& p = pp.base;
     const int T = p.tab.n_angles, M = p.tab.n_steps;
     // cs tile: [spb][T] row-major (pitch 1 per column inside a row)
-    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed, 0, 0);
+    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed);
     const int64_t b0 = (int64_t)blockIdx.x * spb;
     const int samples = (int)min((int64_t)spb, p.batch - b0);
     stage_reg_tables(pp, l);

@@ -257,7 +257,7 @@ static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStre
     SvRegParams rp;
     fill_reg_params(rp, p, plan);
     const size_t tables = reg_smem_tables_bytes(p.tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
-    const size_t tile = (size_t)threads * p.tab.n_angles * (sizeof(double2) + sizeof(double));
+    const size_t tile = (size_t)threads * p.tab.n_angles * sizeof(double2);
     const int staged = (p.tab.n_angles > 0 && tables + tile <= 100 * 1024) ? 1 : 0;
     size_t smem = tables + (staged ? tile : 0);
     if (DM) {

@@ -50,11 +50,9 @@ __constant__ double kTrig[16] = {
     1.5707963267948966e+00,      6.123233995736766e-17,       1.4973849048591698e-33,
     6.36619772367581382433e-01};
 
-__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
-    if (!(fabs(x) < 1.0e5)) {  // rare: large / non-finite arguments take the library path
-        sincos(x, &sn, &cs);
-        return;
-    }
+// branch-free core, valid for |x| < 1e5 (the quadrant count must fit the 2^52 rounding trick and
+// the three-term reduction keeps ~1 ulp there)
+__device__ __forceinline__ void sincos_core(double x, double& sn, double& cs) {
     const double magic = 6755399441055744.0;  // 1.5 * 2^52: rounds to nearest integer
     const double t = fma(x, kTrig[15], magic);
     const int q = __double2loint(t);
@@ -80,6 +78,13 @@ __device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
     const double ca = (q & 1) ? s0 : c0;
     sn = flip_sign(sa, ((uint32_t)q << 30) & 0x80000000u);
     cs = flip_sign(ca, ((uint32_t)(q + 1) << 30) & 0x80000000u);
+}
+__device__ __forceinline__ void sincos_cw(double x, double& sn, double& cs) {
+    if (!(fabs(x) < 1.0e5)) {  // rare: large / non-finite arguments take the library path
+        sincos(x, &sn, &cs);
+        return;
+    }
+    sincos_core(x, sn, cs);
 }
 
 // ---- angle sources -----------------------------------------------------------------------------
@@ -283,18 +288,19 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+constexpr int kRegThreads = 128;  // CTA size of the register kernels
+
 // dynamic shared memory layout of the register kernels (all offsets 16-byte aligned)
 struct RegSmemLayout {
     uint32_t* signs;   // [M][SP]
     uint32_t* cols;    // [M] padded to 4
     double2* fixed;    // [n_fixed]
-    double2* cs;       // [T][pitch]        (staged only)
-    double* raw;       // [rows][T]         (staged only)
+    double2* cs;       // [T][pitch] (cos, sin), column-major   (staged only)
 };
 __host__ __device__ __forceinline__ size_t reg_smem_tables_bytes(int M, int sp, int n_fixed) {
     return (size_t)M * sp * 4 + (size_t)((M + 3) & ~3) * 4 + (size_t)n_fixed * 16;
 }
-__device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int sp, int n_fixed, int T, int pitch) {
+__device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int sp, int n_fixed) {
     RegSmemLayout l;
     char* p = reinterpret_cast<char*>(base);
     l.signs = reinterpret_cast<uint32_t*>(p);
@@ -304,47 +310,37 @@ __device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int s
     l.fixed = reinterpret_cast<double2*>(p);
     p += (size_t)n_fixed * 16;
     l.cs = reinterpret_cast<double2*>(p);
-    p += (size_t)T * pitch * 16;
-    l.raw = reinterpret_cast<double*>(p);
     return l;
 }
 
+// plan tables -> shared memory (a few hundred bytes; one 16-byte cp.async per thread or less)
 __device__ __forceinline__ void stage_reg_tables(const SvRegParams& p, const RegSmemLayout& l) {
     const int M = p.base.tab.n_steps;
-    const int nsig = M * p.reg.sign_pitch / 4;
-    for (int i = threadIdx.x; i < nsig; i += blockDim.x)
+    const int nsig = (M * p.reg.sign_pitch) >> 2;
+    const int ncol = (M + 3) >> 2;
+    for (int i = threadIdx.x; i < nsig; i += kRegThreads)
         cp_async16(reinterpret_cast<uint4*>(l.signs) + i, reinterpret_cast<const uint4*>(p.reg.signs) + i);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) cp_async4(l.cols + i, p.reg.cols + i);
-    for (int i = threadIdx.x; i < p.reg.n_fixed; i += blockDim.x) cp_async16(l.fixed + i, p.reg.fixed + i);
+    for (int i = threadIdx.x; i < ncol; i += kRegThreads)
+        cp_async16(reinterpret_cast<uint4*>(l.cols) + i, reinterpret_cast<const uint4*>(p.reg.cols) + i);
+    for (int i = threadIdx.x; i < p.reg.n_fixed; i += kRegThreads) cp_async16(l.fixed + i, p.reg.fixed + i);
 }
 
-// rows [b0, b0+samples) of the angle matrix -> raw[samples][T], every load in flight at once
-__device__ __forceinline__ void stage_raw_angles(const SvBatchParams& p, double* raw, int64_t b0, int samples) {
-    const int T = p.tab.n_angles;
-    if (p.stride == T) {
-        const double* src = p.angles + b0 * T;
-        const int total = samples * T;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            for (int i = threadIdx.x; i < (total >> 1); i += blockDim.x) cp_async16(raw + 2 * i, src + 2 * i);
-            if ((total & 1) && threadIdx.x == 0) cp_async8(raw + total - 1, src + total - 1);
-        } else {
-            for (int i = threadIdx.x; i < total; i += blockDim.x) cp_async8(raw + i, src + i);
-        }
-    } else {
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        for (int r = wid; r < samples; r += nw)
-            for (int j = lane; j < T; j += 32) cp_async8(raw + r * T + j, p.angles + (b0 + r) * p.stride + j);
-    }
+// Thread `row` fetches its own angle row straight into the low halves of its (cos, sin) slots:
+// T independent 8-byte cp.async per thread, all in flight together (one DRAM latency for the
+// whole pattern); a warp covers 32 consecutive rows = one contiguous span of the angle matrix,
+// so every fetched sector is fully used.
+__device__ __forceinline__ void fetch_own_row(const double* __restrict__ grow, double2* cs_col0, int T, int pitch) {
+    for (int j = 0; j < T; ++j) cp_async8(&cs_col0[j * pitch].x, grow + j);
 }
 
-// thread `row` turns its own angle row into (cos, sin) pairs, column-major with pitch `pitch`:
-// independent evaluations (ILP), conflict-free column reads later, no barrier needed
-__device__ __forceinline__ void convert_own_row(const double* raw, double2* cs, int T, int row, int pitch) {
+// ... and converts them in place to (cos, sin): independent evaluations, no barrier needed since
+// every slot is written and read by the same thread.
+__device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pitch) {
 #pragma unroll 2
     for (int j = 0; j < T; ++j) {
         double sn, c;
-        sincos_cw(raw[row * T + j], sn, c);
-        cs[j * pitch + row] = make_double2(c, sn);
+        sincos_cw(cs_col0[j * pitch].x, sn, c);
+        cs_col0[j * pitch] = make_double2(c, sn);
     }
 }
 
@@ -358,22 +354,22 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
     extern __shared__ double2 dyn[];
     const SvBatchParams& p = pp.base;
     const int T = p.tab.n_angles, M = p.tab.n_steps;
-    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed, T, blockDim.x);
-    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x;
+    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed);
+    const int64_t b0 = (int64_t)blockIdx.x * kRegThreads;
     const int64_t b = b0 + threadIdx.x;
     const bool live = b < p.batch;
     const int k = p.tab.n_out;
-    const int samples = (int)min((int64_t)blockDim.x, p.batch - b0);
+    const int samples = (int)min((int64_t)kRegThreads, p.batch - b0);
     stage_reg_tables(pp, l);
-    if (staged) stage_raw_angles(p, l.raw, b0, samples);
+    if (staged && live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
     cp_async_wait_all();
     __syncthreads();
     const RegSmem sm{l.cols, l.signs, pp.reg.sign_pitch};
     double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
     if (live) {
         if (staged) {
-            convert_own_row(l.raw, l.cs, T, threadIdx.x, blockDim.x);
-            const AngleStaged ang{l.cs + threadIdx.x, (int)blockDim.x, T, l.fixed, -1, 1.0, 0.0};
+            convert_own_row(l.cs + threadIdx.x, T, kRegThreads);
+            const AngleStaged ang{l.cs + threadIdx.x, kRegThreads, T, l.fixed, -1, 1.0, 0.0};
             n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
         } else {
             const AngleGlobal ang{p.angles + b * p.stride, T, l.fixed, -1, 0.0};
@@ -400,7 +396,7 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
         const int64_t total = (int64_t)samples << (2 * k);
         double2* o = p.out + (b0 << (2 * k));
         const uint32_t km = (1u << k) - 1u;
-        for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
+        for (int64_t e = threadIdx.x; e < total; e += kRegThreads) {
             const double2* sv = dyn + ((e >> (2 * k)) << k);
             const double2 x = sv[(e >> k) & km], y = sv[e & km];
             o[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);

@@ -26,9 +26,15 @@ def time_kernel(spec, B, reps=200, form=_lib.OUT_SV):
     for j in range(nbuf): go(j, stream.cuda_stream)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
+    S = int(os.environ.get("PERF_STREAMS", "1"))
+    side = [torch.cuda.Stream() for _ in range(S - 1)]
     with torch.cuda.graph(g):
-        cs = torch.cuda.current_stream().cuda_stream
-        for j in range(nbuf): go(j, cs)
+        cur = torch.cuda.current_stream()
+        for st_ in side: st_.wait_stream(cur)
+        for j in range(nbuf):
+            s_ = cur if j % S == 0 else side[j % S - 1]
+            go(j, s_.cuda_stream)
+        for st_ in side: cur.wait_stream(st_)
     g.replay(); torch.cuda.synchronize()
     n = max(1, reps // nbuf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,6 +45,11 @@ def time_kernel(spec, B, reps=200, form=_lib.OUT_SV):
     return us
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:  # e.g. perf_sv.py grid_cluster 2,6 1048576  (single config, for ncu)
+        spec = (sys.argv[1], [int(x) for x in sys.argv[2].split(",")])
+        B = int(sys.argv[3])
+        print(spec, B, time_kernel(spec, B, reps=20))
+        sys.exit(0)
     for spec in (("grid_cluster", [2, 6]), ("grid_cluster", [4, 5]), ("linear_cluster", [5])):
         for B in (1024, 8192, 32768, 65536, 262144, 1048576):
             us = time_kernel(spec, B)
