@@ -314,29 +314,37 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
     return launch_sv(p, plan, out_form, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
 constexpr int kPipeStreams = 4;
-struct PipeStreams {
+struct PipeState {  // created lazily, once per device
     cudaStream_t s[kPipeStreams];
+    cudaEvent_t done[kPipeStreams];
+    int32_t* h_flags = nullptr;  // page-locked, kPipeStreams words
     bool ready = false;
 };
-PipeStreams g_pipe[64];  // per device
+PipeState g_pipe[64];
 
-int pipe_streams(int device, cudaStream_t** out) {
+int pipe_state(int device, PipeState** out) {
     if (device < 0 || device >= 64) return fail(MBQC_E_ARG, "device index %d out of range", device);
-    PipeStreams& ps = g_pipe[device];
+    PipeState& ps = g_pipe[device];
     if (!ps.ready) {
-        for (int i = 0; i < kPipeStreams; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking));
+        for (int i = 0; i < kPipeStreams; ++i) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&ps.done[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaHostAlloc((void**)&ps.h_flags, kPipeStreams * sizeof(int32_t), cudaHostAllocDefault));
         ps.ready = true;
     }
-    *out = ps.s;
+    *out = &ps;
     return MBQC_OK;
 }
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
 
-int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batch, int32_t out_form) {
+extern "C" int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batch, int32_t out_form) {
     if (!plan || batch < 0) return -1;
     const int k = plan->tab.n_out;
     const size_t out_elems = (out_form == MBQC_OUT_DM) ? ((size_t)1 << (2 * k)) : ((size_t)1 << k);
@@ -344,10 +352,10 @@ int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batch, int32_t 
     return (int64_t)(align256((size_t)batch * T * sizeof(double)) + align256((size_t)batch * out_elems * sizeof(double2)) + 256);
 }
 
-int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
-                           const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
-                           int32_t out_form, void* d_work, int64_t work_bytes,
-                           int32_t* h_status_any, int32_t n_chunks) {
+extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                                      const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                                      int32_t out_form, void* d_work, int64_t work_bytes,
+                                      int32_t* h_status_any, int32_t n_chunks) {
     int rc = check_batch_args(plan, h_angles, angle_stride, d_inputs, input_mode, batch, h_out);
     if (rc) return rc;
     if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
@@ -358,10 +366,10 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
     if (h_status_any) *h_status_any = 0;
     if (batch == 0) return MBQC_OK;
-    cudaStream_t* streams = nullptr;
+    PipeState* ps = nullptr;
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
-    rc = pipe_streams(device, &streams);
+    rc = pipe_state(device, &ps);
     if (rc) return rc;
     const int T = plan->tab.n_angles;
     const int Tw = T > 0 ? T : 1;
@@ -371,19 +379,17 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
     double* d_angles = (double*)base;
     double2* d_out = (double2*)(base + align256((size_t)batch * Tw * sizeof(double)));
     int32_t* d_any = (int32_t*)((char*)d_out + align256((size_t)batch * out_elems * sizeof(double2)));
-    if (n_chunks < 1) n_chunks = 8;
+    if (n_chunks < 1) n_chunks = 4;
     if ((int64_t)n_chunks > (batch + 1023) / 1024) n_chunks = (int)((batch + 1023) / 1024);
     if (n_chunks < 1) n_chunks = 1;
-    CUDA_TRY(cudaMemsetAsync(d_any, 0, sizeof(int32_t), streams[0]));
-    CUDA_TRY(cudaStreamSynchronize(streams[0]));
+    const int used = n_chunks < kPipeStreams ? n_chunks : kPipeStreams;
+    for (int i = 0; i < used; ++i) CUDA_TRY(cudaMemsetAsync(d_any + i, 0, sizeof(int32_t), ps->s[i]));
     const int64_t per = (batch + n_chunks - 1) / n_chunks;
-    int used = 0;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t lo = (int64_t)c * per;
         const int64_t hi = (lo + per < batch) ? lo + per : batch;
         if (hi <= lo) break;
-        cudaStream_t st = streams[c % kPipeStreams];
-        if (c < kPipeStreams) used = c + 1;
+        cudaStream_t st = ps->s[c % kPipeStreams];
         if (T > 0) {
             if (angle_stride == T) {
                 CUDA_TRY(cudaMemcpyAsync(d_angles + lo * T, h_angles + lo * T, (size_t)(hi - lo) * T * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -397,16 +403,28 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
         const void* din = d_inputs;
         if (input_mode == MBQC_INPUT_BATCH) din = (const char*)d_inputs + ((size_t)lo << plan->tab.n_in) * sizeof(double2);
         fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, d_out + lo * out_elems, nullptr);
-        p.status_any = d_any;
+        p.status_any = d_any + (c % kPipeStreams);
         rc = launch_sv(p, plan, out_form, st);
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
                                  cudaMemcpyDeviceToHost, st));
     }
-    for (int i = 0; i < used; ++i) CUDA_TRY(cudaStreamSynchronize(streams[i]));
-    if (h_status_any) CUDA_TRY(cudaMemcpy(h_status_any, d_any, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // join: every stream's tail feeds stream 0, which fetches the status words; one host wait
+    for (int i = 1; i < used; ++i) {
+        CUDA_TRY(cudaEventRecord(ps->done[i], ps->s[i]));
+        CUDA_TRY(cudaStreamWaitEvent(ps->s[0], ps->done[i], 0));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ps->h_flags, d_any, used * sizeof(int32_t), cudaMemcpyDeviceToHost, ps->s[0]));
+    CUDA_TRY(cudaStreamSynchronize(ps->s[0]));
+    if (h_status_any) {
+        int32_t any = 0;
+        for (int i = 0; i < used; ++i) any |= ps->h_flags[i];
+        *h_status_any = any;
+    }
     return MBQC_OK;
 }
+
+extern "C" {
 
 int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,

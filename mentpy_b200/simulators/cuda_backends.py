@@ -36,26 +36,33 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-class _HostBuffers:
-    """Persistent device workspace + two rotating page-locked output buffers for the host-array
-    path of `run_batch` (mbqc_run_batch_sv_host): no allocation in steady state."""
+class _HostCall:
+    """Everything a steady-state host-array `run_batch` call needs, resolved once per
+    (plan, batch, output form): device workspace, two rotating page-locked output buffers with
+    their numpy views, raw pointers.  The hot call is then: pointer of the input, one ctypes call,
+    return a view."""
 
-    def __init__(self, dev):
-        self.dev = dev
-        self.d_work = None
+    def __init__(self, lib, dplan, dev, batch, T, code):
+        import ctypes as C
+
+        dim = 2 ** dplan.n_out
+        self.shape = (batch, dim) if code == _lib.OUT_SV else (batch, dim, dim)
+        out_elems = int(np.prod(self.shape[1:])) * batch
+        self.need = int(lib.mbqc_host_workspace_bytes(dplan.handle, batch, code))
+        self.d_work = torch.empty(self.need, dtype=torch.uint8, device=dev)
+        self.work_ptr = self.d_work.data_ptr()
+        self.h_out = [torch.empty(max(out_elems, 1), dtype=torch.complex128).pin_memory() for _ in range(2)]
+        self.out_ptr = [t.data_ptr() for t in self.h_out]
+        self.views = [t[:out_elems].numpy().reshape(self.shape) for t in self.h_out]
         self.h_in = None
-        self.h_out = [None, None]
+        self.flag = C.c_int32(0)
+        self.flag_ref = C.byref(self.flag)
         self.turn = 0
 
-    def get(self, work_bytes, in_elems, out_elems):
-        if self.d_work is None or self.d_work.numel() < work_bytes:
-            self.d_work = torch.empty(int(work_bytes), dtype=torch.uint8, device=self.dev)
-        if self.h_in is None or self.h_in.numel() < in_elems:
-            self.h_in = torch.empty(max(in_elems, 1), dtype=torch.float64).pin_memory()
-        if self.h_out[0] is None or self.h_out[0].numel() < out_elems:
-            self.h_out = [torch.empty(out_elems, dtype=torch.complex128).pin_memory() for _ in range(2)]
-        self.turn ^= 1
-        return self.d_work, self.h_in, self.h_out[self.turn]
+    def staging(self, batch, T):
+        if self.h_in is None:
+            self.h_in = torch.empty((batch, max(T, 1)), dtype=torch.float64).pin_memory()
+        return self.h_in
 
 
 class _CudaPatternBase(BaseSimulator):
@@ -90,7 +97,8 @@ class _CudaPatternBase(BaseSimulator):
         self._prefix = {}
         self._d_input = None
         self.last_status = None
-        self._pipe = None
+        self._host_calls = {}
+        self._input_synced = False
 
     # -- plumbing -------------------------------------------------------------------------------
     def _parse_noise(self, kwargs):
@@ -266,9 +274,8 @@ class CudaSimulatorSV(_CudaPatternBase):
             return out
 
     def _run_plan_host(self, dplan, angles, input_states, code, check, copy):
-        """Host arrays in, host arrays out through the C-level chunked H2D/kernel/D2H pipeline."""
-        import ctypes as C
-
+        """Host arrays in, host arrays out through the C-level chunked H2D/kernel/D2H pipeline
+        (mbqc_run_batch_sv_host)."""
         dev = self._dev()
         lib = _lib.load()
         if isinstance(angles, torch.Tensor):
@@ -281,34 +288,39 @@ class CudaSimulatorSV(_CudaPatternBase):
             raise ValueError(
                 f"Number of angles ({src.shape[-1]}) does not match number of trainable nodes ({self.plan.n_angles})."
             )
-        src = src.contiguous()
+        if not src.is_contiguous():
+            src = src.contiguous()
         batch, T = src.shape
-        dim = 2 ** dplan.n_out
-        out_elems = dim if code == _lib.OUT_SV else dim * dim
         if batch == 0:
+            dim = 2 ** dplan.n_out
             return np.zeros((0, dim) if code == _lib.OUT_SV else (0, dim, dim), dtype=np.complex128)
-        with torch.cuda.device(dev):
-            if self._pipe is None or self._pipe.dev != dev:
-                self._pipe = _HostBuffers(dev)
-            need = lib.mbqc_host_workspace_bytes(dplan.handle, batch, code)
-            d_work, h_in, h_out = self._pipe.get(need, batch * T, batch * out_elems)
-            inp, mode = self._stage_inputs(input_states, batch, dev)
-            if inp is not None and not getattr(self, "_input_synced", False):
-                torch.cuda.current_stream(dev).synchronize()  # the pipeline runs on its own streams
-                self._input_synced = True
-            if not src.is_pinned() and batch * T >= (1 << 16):
-                h_in[: batch * T].view(batch, T).copy_(src)  # stage large pageable input once
-                src = h_in[: batch * T].view(batch, T)
-            flag = C.c_int32(0)
-            _lib.check(lib.mbqc_run_batch_sv_host(dplan.handle, src.data_ptr(), max(T, 1), _ptr(inp), mode,
-                                                  batch, h_out.data_ptr(), code, d_work.data_ptr(),
-                                                  d_work.numel(), C.byref(flag), 0))
-            if check and (flag.value & _lib.STATUS_BAD_NORM):
-                raise ValueError("qstate has nan, you might want to increase the window size")
-            self.last_status = None
-            res = h_out[: batch * out_elems].numpy()
-            res = res.reshape(batch, dim) if code == _lib.OUT_SV else res.reshape(batch, dim, dim)
-            return res.copy() if copy else res
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        key = (id(dplan), batch, code)
+        call = self._host_calls.get(key)
+        if call is None:
+            if len(self._host_calls) > 8:
+                self._host_calls.clear()
+            call = self._host_calls[key] = _HostCall(lib, dplan, dev, batch, T, code)
+        inp, mode = self._stage_inputs(input_states, batch, dev)
+        if not self._input_synced:
+            torch.cuda.current_stream(dev).synchronize()  # the pipeline runs on its own streams
+            self._input_synced = True
+        if batch * T >= (1 << 16) and not src.is_pinned():
+            stage = call.staging(batch, T)  # large pageable input: one copy into page-locked memory
+            stage.copy_(src)
+            src = stage
+        call.turn ^= 1
+        rc = lib.mbqc_run_batch_sv_host(dplan.handle, src.data_ptr(), max(T, 1), _ptr(inp), mode, batch,
+                                        call.out_ptr[call.turn], code, call.work_ptr, call.need,
+                                        call.flag_ref, 0)
+        if rc:
+            _lib.check(rc)
+        if check and (call.flag.value & _lib.STATUS_BAD_NORM):
+            raise ValueError("qstate has nan, you might want to increase the window size")
+        self.last_status = None
+        res = call.views[call.turn]
+        return res.copy() if copy else res
 
     def measure(self, angle: float) -> Tuple[np.ndarray, int]:
         st = self._record_angle(angle)
