@@ -379,7 +379,7 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
     double* d_angles = (double*)base;
     double2* d_out = (double2*)(base + align256((size_t)batch * Tw * sizeof(double)));
     int32_t* d_any = (int32_t*)((char*)d_out + align256((size_t)batch * out_elems * sizeof(double2)));
-    if (n_chunks < 1) n_chunks = 4;
+    if (n_chunks < 1) n_chunks = 2;  // measured on B200/PCIe5: 2-4 pieces are best, more only add engine hand-offs
     if ((int64_t)n_chunks > (batch + 1023) / 1024) n_chunks = (int)((batch + 1023) / 1024);
     if (n_chunks < 1) n_chunks = 1;
     const int used = n_chunks < kPipeStreams ? n_chunks : kPipeStreams;

@@ -1,0 +1,6 @@
+"""Optimisers with the mentpy.optimizers API, running on batched CUDA cost evaluations."""
+from .descent import (AdamOptimizer, BaseOptimizer, BatchedFidelityCost, RCDOptimizer, SGDOptimizer,
+                      compute_gradient_variance)
+
+__all__ = ["AdamOptimizer", "SGDOptimizer", "RCDOptimizer", "BaseOptimizer", "BatchedFidelityCost",
+           "compute_gradient_variance"]
