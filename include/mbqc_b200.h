@@ -132,6 +132,55 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
                         const void* d_target, double shift, double* d_grad, double* d_cost,
                         int32_t* d_status, void* stream);
 
+/* ---- streaming regime: one large window resident in HBM, one angle set -------------------------
+ * Replaces NumpySimulatorSV.reset / measure / run for windows the reference cannot hold (it
+ * materialises 2^w x 2^w operators: np_simulator_sv.py:103-128, :164-225, :286-297).  The state is
+ * 2^local_bits complex numbers per GPU; with G = 2^g GPUs the top g index bits are the rank
+ * ("shard slots").  The host mirror (mentpy_b200/streaming.py) turns the plan's steps into pass
+ * descriptors; slots in these calls are PHYSICAL bit positions of the global index. */
+#define MBQC_STREAM_MAX_FUSE 5
+#define MBQC_STREAM_MAX_RANGES 16
+
+typedef struct mbqc_stream_desc {
+    int32_t n_fused;         /* K consecutive measurements applied in this pass (1..5) */
+    int32_t n_ranges;        /* zero fields squeezed out of the thread index (fused + dead slots) */
+    uint32_t range_pos[MBQC_STREAM_MAX_RANGES];   /* ascending, in index coordinates after the */
+    uint32_t range_width[MBQC_STREAM_MAX_RANGES]; /*   previous inserts                         */
+    uint64_t elem_offset[MBQC_STREAM_MAX_FUSE];   /* 1 << slot of fused measurement j */
+    double cos_t[MBQC_STREAM_MAX_FUSE];
+    double sin_t[MBQC_STREAM_MAX_FUSE];
+    uint64_t nbr_mask[MBQC_STREAM_MAX_FUSE];      /* slots of the appended qubit's neighbours */
+    uint32_t local_mask[MBQC_STREAM_MAX_FUSE];    /* ... restricted to the fused slots (bit i = measurement i) */
+    uint32_t append_mask;    /* bit j: measurement j appends a |+> qubit (else its slot dies) */
+    uint64_t n_groups;       /* 2^(live local bits - K) */
+    uint64_t index_or;       /* rank << local_bits: completes the index for sign parities */
+    double scale;            /* exact power-of-two rescale applied on load */
+} mbqc_stream_desc;
+
+/* Seed the local share of the window: input (x) |+>^(w-|I|), initial CZ signs (np_simulator_sv.py:103-128). */
+int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32_t window,
+                     int32_t n_inputs, const int32_t* input_slot, const uint64_t* init_cz_mask,
+                     const void* d_input, double scale, void* stream);
+/* One in-place pass over the local share applying desc->n_fused measurements (np_simulator_sv.py:164-225). */
+int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream);
+/* Measurement of a shard slot fused with the NVLink transfer: d_peer is the partner GPU's half
+ * (peer-mapped memory), read directly by the kernel.  role 0/1: this rank's shard bit; role 2:
+ * tail step without append (whole shard, survivor side).  See csrc/stream.cuh. */
+int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t role, double cos_t,
+                         double sin_t, double scale, uint64_t nbr_mask, int32_t const_parity,
+                         uint64_t n, void* stream);
+/* Collect the output amplitudes this rank owns into d_out [2^k] (others untouched; np_simulator_sv.py:286-297). */
+int mbqc_stream_gather(const void* d_state, int32_t local_bits, uint64_t index_or,
+                       int32_t n_outputs, const int32_t* output_slot, void* d_out, void* stream);
+
+/* Plain cudaMalloc'ed buffers (IPC-exportable, unlike sub-allocations of a caching allocator) and
+ * CUDA IPC handles (64 bytes) so that one process per GPU can map its neighbours' shards. */
+int mbqc_device_alloc(int64_t bytes, void** d_ptr);
+int mbqc_device_free(void* d_ptr);
+int mbqc_ipc_export(const void* d_ptr, void* handle64);
+int mbqc_ipc_import(const void* handle64, void** d_ptr);
+int mbqc_ipc_close(void* d_ptr);
+
 /* plan introspection (used by the host mirror and the tests) */
 int32_t mbqc_plan_window(const mbqc_plan* plan);
 int32_t mbqc_plan_num_steps(const mbqc_plan* plan);

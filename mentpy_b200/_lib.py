@@ -25,6 +25,18 @@ class Step(C.Structure):
                 ("nbr_mask", C.c_uint64)]
 
 
+STREAM_MAX_FUSE, STREAM_MAX_RANGES = 5, 16
+
+
+class StreamDesc(C.Structure):
+    _fields_ = [("n_fused", C.c_int32), ("n_ranges", C.c_int32),
+                ("range_pos", C.c_uint32 * STREAM_MAX_RANGES), ("range_width", C.c_uint32 * STREAM_MAX_RANGES),
+                ("elem_offset", C.c_uint64 * STREAM_MAX_FUSE), ("cos_t", C.c_double * STREAM_MAX_FUSE),
+                ("sin_t", C.c_double * STREAM_MAX_FUSE), ("nbr_mask", C.c_uint64 * STREAM_MAX_FUSE),
+                ("local_mask", C.c_uint32 * STREAM_MAX_FUSE), ("append_mask", C.c_uint32),
+                ("n_groups", C.c_uint64), ("index_or", C.c_uint64), ("scale", C.c_double)]
+
+
 class Noise(C.Structure):
     _fields_ = [("pop", C.c_double * 4), ("coh_g", C.c_double), ("coh_d", C.c_double)]
 
@@ -45,6 +57,18 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mbqc_stream_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p, C.c_double, C.c_void_p]),
+    "mbqc_stream_steps": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_void_p]),
+    "mbqc_stream_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
+                                       C.c_double, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
+    "mbqc_stream_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_int32),
+                                     C.c_void_p, C.c_void_p]),
+    "mbqc_device_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "mbqc_device_free": (C.c_int, [C.c_void_p]),
+    "mbqc_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mbqc_ipc_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mbqc_ipc_close": (C.c_int, [C.c_void_p]),
     "mbqc_plan_window": (C.c_int32, [C.c_void_p]),
     "mbqc_plan_num_steps": (C.c_int32, [C.c_void_p]),
     "mbqc_plan_num_outputs": (C.c_int32, [C.c_void_p]),

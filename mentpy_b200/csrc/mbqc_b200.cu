@@ -11,6 +11,7 @@
 #include "grad_batch.cuh"
 #include "sv_batch.cuh"
 #include "sv_reg.cuh"
+#include "stream.cuh"
 #include <vector>
 
 using namespace mbqc;
@@ -506,6 +507,127 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     }
     if (rc) return rc;
     return after_launch("sv_reg_grad_kernel");
+}
+
+}  // extern "C"
+
+
+// ---- streaming regime --------------------------------------------------------------------------
+namespace {
+int stream_grid(uint64_t work_items, int threads) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t need = (work_items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)sms * 8;  // persistent grid-stride CTAs, a multiple of the SM count
+    return (int)(need < cap ? (need ? need : 1) : cap);
+}
+}  // namespace
+
+extern "C" {
+
+int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32_t window,
+                     int32_t n_inputs, const int32_t* input_slot, const uint64_t* init_cz_mask,
+                     const void* d_input, double scale, void* stream) {
+    if (!d_state) return fail(MBQC_E_ARG, "d_state is NULL");
+    if (window < 1 || window > MBQC_MAX_WINDOW || local_bits < 0 || local_bits > window) return fail(MBQC_E_ARG, "bad window/local_bits");
+    if (n_inputs < 0 || n_inputs > kMaxIO || (n_inputs && !input_slot) || !init_cz_mask) return fail(MBQC_E_ARG, "bad input tables");
+    StreamInitParams p;
+    memset(&p, 0, sizeof(p));
+    p.state = (double2*)d_state;
+    p.input = (const double2*)d_input;
+    p.n_local = 1ull << local_bits;
+    p.index_or = index_or;
+    p.window = window;
+    p.n_in = n_inputs;
+    p.scale = scale;
+    for (int q = 0; q < n_inputs; ++q) p.in_slot[q] = input_slot[q];
+    for (int a = 0; a < window; ++a) p.cz[a] = init_cz_mask[a];
+    stream_init_kernel<<<stream_grid(p.n_local, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("stream_init_kernel");
+}
+
+int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream) {
+    if (!d_state || !desc) return fail(MBQC_E_ARG, "NULL argument");
+    if (desc->n_fused < 1 || desc->n_fused > MBQC_STREAM_MAX_FUSE) return fail(MBQC_E_ARG, "n_fused %d outside [1,%d]", desc->n_fused, MBQC_STREAM_MAX_FUSE);
+    if (desc->n_ranges < 0 || desc->n_ranges > MBQC_STREAM_MAX_RANGES) return fail(MBQC_E_ARG, "n_ranges %d outside [0,%d]", desc->n_ranges, MBQC_STREAM_MAX_RANGES);
+    if (desc->n_groups == 0) return MBQC_OK;
+    const int grid = stream_grid(desc->n_groups, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* s = (double2*)d_state;
+    switch (desc->n_fused) {
+        case 1: stream_steps_kernel<1><<<grid, 256, 0, st>>>(s, *desc); break;
+        case 2: stream_steps_kernel<2><<<grid, 256, 0, st>>>(s, *desc); break;
+        case 3: stream_steps_kernel<3><<<grid, 256, 0, st>>>(s, *desc); break;
+        case 4: stream_steps_kernel<4><<<grid, 256, 0, st>>>(s, *desc); break;
+        default: stream_steps_kernel<5><<<grid, 256, 0, st>>>(s, *desc); break;
+    }
+    return after_launch("stream_steps_kernel");
+}
+
+int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t role, double cos_t,
+                         double sin_t, double scale, uint64_t nbr_mask, int32_t const_parity,
+                         uint64_t n, void* stream) {
+    if (!d_own || !d_peer || (role != 2 && !d_spare)) return fail(MBQC_E_ARG, "NULL buffer");
+    if (role < 0 || role > 2) return fail(MBQC_E_ARG, "role %d unknown", role);
+    if (n == 0) return MBQC_OK;
+    ExchangeParams p;
+    p.own = (double2*)d_own;
+    p.peer = (const double2*)d_peer;
+    p.spare = (double2*)d_spare;
+    p.role = role;
+    p.c = cos_t;
+    p.s = sin_t;
+    p.scale = scale;
+    p.nbr_mask = nbr_mask;
+    p.const_parity = (uint32_t)(const_parity & 1);
+    p.n = n;
+    stream_exchange_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("stream_exchange_kernel");
+}
+
+int mbqc_stream_gather(const void* d_state, int32_t local_bits, uint64_t index_or,
+                       int32_t n_outputs, const int32_t* output_slot, void* d_out, void* stream) {
+    if (!d_state || !d_out) return fail(MBQC_E_ARG, "NULL buffer");
+    if (n_outputs < 0 || n_outputs > kMaxIO || (n_outputs && !output_slot)) return fail(MBQC_E_ARG, "bad output table");
+    StreamGatherParams p;
+    memset(&p, 0, sizeof(p));
+    p.state = (const double2*)d_state;
+    p.out = (double2*)d_out;
+    p.index_or = index_or;
+    p.local_mask = (local_bits >= 64) ? ~0ull : ((1ull << local_bits) - 1ull);
+    p.n_out = n_outputs;
+    for (int q = 0; q < n_outputs; ++q) p.out_slot[q] = output_slot[q];
+    stream_gather_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
+    return after_launch("stream_gather_kernel");
+}
+
+int mbqc_device_alloc(int64_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes < 0) return fail(MBQC_E_ARG, "bad arguments");
+    *d_ptr = nullptr;
+    CUDA_TRY(cudaMalloc(d_ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return MBQC_OK;
+}
+int mbqc_device_free(void* d_ptr) {
+    if (d_ptr) CUDA_TRY(cudaFree(d_ptr));
+    return MBQC_OK;
+}
+int mbqc_ipc_export(const void* d_ptr, void* handle64) {
+    if (!d_ptr || !handle64) return fail(MBQC_E_ARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CUDA_TRY(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, (void*)d_ptr));
+    return MBQC_OK;
+}
+int mbqc_ipc_import(const void* handle64, void** d_ptr) {
+    if (!d_ptr || !handle64) return fail(MBQC_E_ARG, "NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MBQC_OK;
+}
+int mbqc_ipc_close(void* d_ptr) {
+    if (d_ptr) CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return MBQC_OK;
 }
 
 }  // extern "C"

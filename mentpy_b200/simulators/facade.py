@@ -9,9 +9,11 @@ from typing import List
 
 import numpy as np
 
+from ..streaming import CudaSimulatorSVStream
 from .cuda_backends import CudaSimulatorDM, CudaSimulatorSV
 
-SUPPORTED_BACKENDS = {"cuda-sv": CudaSimulatorSV, "cuda-dm": CudaSimulatorDM}
+SUPPORTED_BACKENDS = {"cuda-sv": CudaSimulatorSV, "cuda-dm": CudaSimulatorDM,
+                      "cuda-sv-stream": CudaSimulatorSVStream}
 
 
 class PatternSimulator:
