@@ -1,0 +1,67 @@
+"""All BASELINE.json configs on one GPU (GPU box): device-resident throughput with CUDA events.
+C1 linear_cluster(5) SV, C2 grid 2x6 SV, C3 grid 3x8 DM (+depolarizing), C4 grid 4x5 psr gradient,
+C5 streaming linear_cluster(w+16, window w).  One JSON line per config -> profiles/."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import mentpy_b200 as mb
+from mentpy_b200 import _lib
+from mentpy_b200.gradients import psr_gradient_batched
+
+PEAK = 6459.0
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+def timeit(fn, reps):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+dev = torch.device("cuda")
+# C1 / C2: batched SV
+for tag, spec, B in (("C1", ("linear_cluster", [5]), 1 << 20), ("C2", ("grid_cluster", [2, 6]), 65536), ("C2-large-batch", ("grid_cluster", [2, 6]), 1 << 22)):
+    gs = getattr(mb.templates, spec[0])(*spec[1]); T, k = len(gs.trainable_nodes), len(gs.output_nodes)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    ang = torch.rand((B, T), device=dev, dtype=torch.float64) * 6.283
+    t = timeit(lambda: ps.run_batch(ang), 50)
+    by = B * (8 * T + 16 * 2**k)
+    emit(config=tag, pattern=f"{spec[0]}{spec[1]}", batch=B, evals_per_s=B / t, ms=t * 1e3, algorithmic_GBps=by / t / 1e9, hbm_frac=by / t / 1e9 / PEAK, note="single stream, torch out alloc inside")
+# C3: DM with noise
+gs = mb.templates.grid_cluster(3, 8); T = len(gs.trainable_nodes)
+for p in (0.0, 0.01, 0.1):
+    ps = mb.PatternSimulator(gs, backend="cuda-dm", **({} if p == 0 else {"circuit_noise": "depolarizing", "p": p}))
+    ang = torch.rand((4096, T), device=dev, dtype=torch.float64) * 6.283
+    t = timeit(lambda: ps.run_batch(ang), 20)
+    by = 4096 * (8 * T + 16 * 64)
+    emit(config="C3", pattern="grid_cluster(3,8) DM", depolarizing_p=p, batch=4096, evals_per_s=4096 / t, ms=t * 1e3, algorithmic_GBps=by / t / 1e9, hbm_frac=by / t / 1e9 / PEAK)
+# C4: gradient
+gs = mb.templates.grid_cluster(4, 5); T = len(gs.trainable_nodes)
+ps = mb.PatternSimulator(gs, backend="cuda-sv")
+tgt = np.full(16, 0.25)
+for B in (1 << 16, 1 << 20):
+    ang = torch.rand((B, T), device=dev, dtype=torch.float64) * 6.283
+    t = timeit(lambda: psr_gradient_batched(ps, ang, tgt), 5)
+    emit(config="C4", pattern="grid_cluster(4,5) psr gradient", base_vectors=B, gradients_per_s=B / t, pattern_evals_per_s=B * 2 * T / t, ms=t * 1e3, algorithmic_GBps=B * 256 / t / 1e9, hbm_frac=B * 256 / t / 1e9 / PEAK)
+# C5: streaming
+for w in (28, 30, 32):
+    try:
+        gs = mb.templates.linear_cluster(w + 16)
+        ps = mb.PatternSimulator(gs, backend="cuda-sv-stream", window_size=w, fuse=4)
+        ang = np.random.default_rng(4).uniform(0, 2 * np.pi, w + 15)
+        ps.run(ang)
+        torch.cuda.synchronize(); t0 = time.perf_counter(); ps.run(ang); torch.cuda.synchronize(); t = time.perf_counter() - t0
+        s = ps.simulator.last_schedule
+        emit(config="C5", pattern=f"linear_cluster({w+16}) window {w}", state_GiB=16 * 2**w / 2**30, fuse=4, s_per_pattern=t, passes=len(s.passes),
+             algorithmic_GBps=s.algorithmic_bytes / t / 1e9, hbm_frac_algorithmic=s.algorithmic_bytes / t / 1e9 / PEAK, streamed_GBps=s.streamed_bytes / t / 1e9)
+        del ps
+    except Exception as e:
+        emit(config="C5", window=w, error=repr(e)[:200])
