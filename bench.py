@@ -357,7 +357,7 @@ def run_gpu_arm(args):
         value = world * BATCH * args.steps / (ms * 1e-3)
         achieved = BATCH * ALGO_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9
         cores = os.cpu_count() or 1
-        cpu_rate, cpu_s = (None, 0.0) if args.skip_cpu else cpu_port_rate(evals_per_core=256, cores=cores)
+        cpu_rate, cpu_s = (None, 0.0) if args.skip_cpu else cpu_port_rate(evals_per_core=4096, cores=cores)
         line = {
             "metric": "pattern_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -383,7 +383,7 @@ def run_gpu_arm(args):
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_EVAL,
                          "note": "register-resident batched regime is FP64-pipe/launch bound, not HBM bound (SURVEY 8d); see DESIGN.md"},
             "cpu_baseline": {"value": cpu_rate, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": f"{256 * cores} angle sets of the same workload, one single-threaded process per core, "
+                             "sample": f"{4096 * cores} angle sets of the same workload, one single-threaded process per core, "
                                        f"{cpu_s:.1f} s (oracle/dense_port.py: reference algorithm incl. dense kron operators)"},
             "clocks": sampler.summary(),
         }

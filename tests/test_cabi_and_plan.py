@@ -129,3 +129,28 @@ def test_facade_contract_without_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             ps.run([0.0, 0.0])
+
+
+def test_lowering_accepts_reference_circuit_objects():
+    """the CUDA backends read only public attributes, so a mentpy.MBQCircuit can be
+    handed over unchanged (build container only: needs the reference tree)."""
+    from oracle.ref_shim import import_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    mp = import_reference()
+    for name, args, w in (("grid_cluster", (2, 6), 1), ("grid_cluster", (3, 5), 6), ("muta", (2, 1), 5)):
+        ref = getattr(mp.templates, name)(*args)
+        mine = getattr(mb.templates, name)(*args)
+        if name == "grid_cluster":
+            ref[1] = mp.Ment("X")
+            mine[1] = mb.Ment("X")
+        a, b = lower(ref, window_size=w), lower(mine, window_size=w)
+        assert a.schedule == b.schedule and a.input_slot == b.input_slot and a.output_slot == b.output_slot
+        assert a.init_cz_mask == b.init_cz_mask and a.n_angles == b.n_angles
+        for sa, sb in zip(a.steps, b.steps):
+            assert (sa.node, sa.slot, sa.angle_idx, sa.plane, sa.append, sa.new_node, sa.nbr_mask,
+                    sa.fixed_cos, sa.fixed_sin) == (sb.node, sb.slot, sb.angle_idx, sb.plane, sb.append,
+                                                    sb.new_node, sb.nbr_mask, sb.fixed_cos, sb.fixed_sin)
+        sim = mb.simulators.CudaSimulatorSV(ref, None, window_size=w)   # constructs without a GPU
+        assert sim.window_size == a.window
