@@ -87,6 +87,12 @@ __device__ __forceinline__ double dm_group_sum(double v, int tps_log2, int ls, d
     return tot;
 }
 
+// barrier over the threads of one sample: a warp-level sync is enough when the group fits a warp
+__device__ __forceinline__ void dm_group_barrier(int tps_log2) {
+    if (tps_log2 <= 5) __syncwarp();
+    else __syncthreads();
+}
+
 // TPS = 2^tps_log2 threads per sample (>= 4^(w-1)/kDmMaxGroupsPerThread), SPB samples per CTA.
 __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_log2, int spb) {
     extern __shared__ double2 smem[];
@@ -123,22 +129,40 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
             psi[i] = v;
         }
     }
-    __syncthreads();
+    dm_group_barrier(tps_log2);
     if (live)
         for (uint32_t e = tid; e < nelem; e += tps) {
             const double2 x = psi[e >> w], y = psi[e & (dim - 1)];
             rho[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
         }
-    __syncthreads();
+    dm_group_barrier(tps_log2);
 
     const double* row = p.angles + (live ? b : 0) * p.stride;
     const uint32_t ngroups = nelem >> 2;
     const uint32_t gmask = (dim >> 1) - 1;  // w-1 bits
     int bad = 0, took1 = 0;
+    // (cos, sin) of the next `chunk` measurements are evaluated by different lanes of the sample's
+    // group (one sincos per measurement per warp instead of one per lane) and broadcast by shuffle
+    const int chunk = tps < 32 ? tps : 32;
+    const int lane = threadIdx.x & 31;
+    const int lane_base = tps < 32 ? (lane & ~(tps - 1)) : 0;
+    double c_mine = 1.0, s_mine = 0.0;
     for (int m = 0; m < t.n_steps; ++m) {
+        const int within = m % chunk;
+        if (within == 0) {
+            const int mm = m + (tps < 32 ? tid : lane);
+            c_mine = 1.0;
+            s_mine = 0.0;
+            if (mm < t.n_steps) {
+                const StepDev sx = p.steps[mm];
+                c_mine = sx.fc;
+                s_mine = sx.fs;
+                if (sx.angle_idx >= 0) sincos_cw(__ldg(row + sx.angle_idx), s_mine, c_mine);
+            }
+        }
+        const double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
+        const double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
         const StepDev st = p.steps[m];
-        double c = st.fc, s = st.fs;
-        if (st.angle_idx >= 0) sincos(__ldg(row + st.angle_idx), &s, &c);
         const int sl = st.slot;
         const uint32_t cbit = 1u << sl, rbit = cbit << w;
         const MeasCoef q = meas_coef(st.plane, c, s, t);
@@ -194,7 +218,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
                 }
             }
         }
-        __syncthreads();
+        dm_group_barrier(tps_log2);
     }
 
     // channel on the output qubits (pennylane_simulator.py:123-136 touches every wire)
@@ -214,7 +238,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
                     rho[i00 | cbit] = make_double2(nz.coh_g * bq.x + nz.coh_d * cq.x, nz.coh_g * bq.y + nz.coh_d * cq.y);
                     rho[i00 | rbit] = make_double2(nz.coh_g * cq.x + nz.coh_d * bq.x, nz.coh_g * cq.y + nz.coh_d * bq.y);
                 }
-            __syncthreads();
+            dm_group_barrier(tps_log2);
         }
     }
 
