@@ -1,0 +1,88 @@
+"""Multi-GPU batch parallelism: one process per GPU (torch.distributed, NCCL over NVLink).
+
+Angle sets -- and the +-shift evaluations of a gradient -- are independent pattern runs
+(mentpy/gradients/_parameter_shift.py:20-24 has no cross term), so the batch is cut into contiguous
+slices, every rank runs the single-GPU kernels on its slice with a replicated plan, and the only
+communication is ONE all_gather of the results at the end (or none when the caller keeps results
+sharded).  The reference's only parallelism is a process pool over input states in a docs snippet
+(docs/tutorials/intro-to-mbqml-parallel.rst:23-51); this is its multi-GPU counterpart.
+"""
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def slice_bounds(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split: the first `total % world` ranks get one extra item."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, extra = divmod(int(total), world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _rank_world(group):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def gather_slices(local, total: int, group=None):
+    """all_gather of per-rank slices (torch tensors, leading axis = batch) into the full batch on
+    every rank.  Ragged slices are padded to the largest one for the collective."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = _rank_world(group)
+    if world == 1:
+        return local
+    sizes = [slice_bounds(total, r, world) for r in range(world)]
+    biggest = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world, biggest) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    flat_in = torch.view_as_real(pad).reshape(-1) if pad.is_complex() else pad.reshape(-1)
+    flat_out = torch.view_as_real(out).reshape(-1) if out.is_complex() else out.reshape(-1)
+    dist.all_gather_into_tensor(flat_out, flat_in.contiguous(), group=group)
+    return torch.cat([out[r, : hi - lo] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+def run_batch_distributed(simulator, angles, group=None, gather: bool = True, **kwargs):
+    """Evaluate the rows of `angles` ([B,T], identical on every rank) split across the ranks of
+    `group`.  Returns the full [B, ...] result on every rank (gather=True, one NCCL all_gather) or
+    this rank's slice and its bounds (gather=False)."""
+    import torch
+
+    rank, world = _rank_world(group)
+    sim = getattr(simulator, "simulator", simulator)
+    B = len(angles)
+    lo, hi = slice_bounds(B, rank, world)
+    dev = sim._dev()
+    part = angles[lo:hi]
+    if not isinstance(part, torch.Tensor):
+        part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+    local = sim.run_batch(part.to(dev), **kwargs)
+    if not gather:
+        return local, (lo, hi)
+    return gather_slices(local, B, group)
+
+
+def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, group=None, gather: bool = True):
+    """BASELINE config 4: parameter-shift gradients of B angle vectors split across the GPUs."""
+    import torch
+
+    from .gradients import psr_gradient_batched
+
+    rank, world = _rank_world(group)
+    sim = getattr(simulator, "simulator", simulator)
+    B = len(angles)
+    lo, hi = slice_bounds(B, rank, world)
+    part = angles[lo:hi]
+    if not isinstance(part, torch.Tensor):
+        part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+    local = psr_gradient_batched(sim, part.to(sim._dev()), target, shift=shift)
+    if not gather:
+        return local, (lo, hi)
+    return gather_slices(local, B, group)

@@ -360,3 +360,45 @@ def test_sincos_accuracy_over_wide_angle_range():
     want = matrix_free.linear_cluster_analytic(ang)
     infid = 1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2
     assert np.max(np.abs(infid)) < 1e-13
+
+
+def test_full_size_properties_c3_c4():
+    """BASELINE configs 3 and 4 at full per-GPU size through size-independent properties."""
+    from mentpy_b200.gradients import psr_gradient_batched
+
+    # C3: 4,096 angle sets, grid_cluster(3,8) DM with depolarizing noise
+    gs = mb.templates.grid_cluster(3, 8)
+    ang = np.random.default_rng(2).uniform(0, 2 * np.pi, (4096, 21))
+    clean = mb.PatternSimulator(gs, backend="cuda-dm").run_batch(ang)
+    noisy = mb.PatternSimulator(gs, backend="cuda-dm", circuit_noise="depolarizing", p=0.01).run_batch(ang)
+    for rho in (clean, noisy):
+        assert rho.shape == (4096, 8, 8)
+        assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1.0, atol=1e-12)
+        assert np.allclose(rho, np.conj(np.swapaxes(rho, 1, 2)), atol=1e-12)
+    purity = np.real(np.einsum("bij,bji->b", clean, clean))
+    assert np.allclose(purity, 1.0, atol=1e-10)                      # noiseless run stays pure
+    assert np.all(np.real(np.einsum("bij,bji->b", noisy, noisy)) < 1.0 - 1e-3)
+    case = next(c for c in CASES if c["spec"][1] == [3, 8])          # golden seed-2 row (SURVEY 8c)
+    assert dm_distance(clean[0], from_cplx(case["output"])) < 1e-10
+    # SV and DM backends agree on the whole batch (reference: tests/test_simulators.py:33-64)
+    sv = mb.PatternSimulator(gs, backend="cuda-sv").run_batch(ang[:512], output_form="dm")
+    assert dm_distance(sv, clean[:512]) < 1e-10
+
+    # C4: 65,536 base vectors x 32 shifted evaluations, grid_cluster(4,5)
+    gs = mb.templates.grid_cluster(4, 5)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    X = np.random.default_rng(4).uniform(0, 2 * np.pi, (65536, 16))
+    tgt = np.full(16, 0.25)
+    g, c = psr_gradient_batched(ps, X, tgt, return_cost=True)
+    assert g.shape == (65536, 16) and np.all(np.isfinite(g)) and np.all((c > -1e-12) & (c < 1 + 1e-12))
+    g2 = psr_gradient_batched(ps, X + 2 * np.pi, tgt)                # 2 pi periodicity in every angle
+    assert np.allclose(g, g2, atol=1e-9)
+    gold = load_golden("gradients.json")["c4"]                       # row 0 is the golden vector
+    assert np.allclose(g[0], gold["psr"], atol=1e-11) and abs(c[0] - gold["cost"]) < 1e-12
+    # explicit shifted evaluations on a subsample
+    idx = np.arange(0, 65536, 4099)
+    for i in (0, 7, 15):
+        e = np.zeros(16); e[i] = 1.5
+        fp = 1 - np.abs(ps.run_batch(X[idx] + e) @ tgt) ** 2
+        fm = 1 - np.abs(ps.run_batch(X[idx] - e) @ tgt) ** 2
+        assert np.allclose(g[idx, i], (fp - fm) / 3.0, atol=1e-11)
