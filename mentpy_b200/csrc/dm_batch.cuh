@@ -114,7 +114,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
         const double2* in = (p.input_mode == MBQC_INPUT_PLUS)
                                 ? nullptr
                                 : p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
-        const double a0 = t.init_scale * exp2(-0.5 * t.n_in);
+        const double a0 = t.plus_amp;
         for (uint32_t i = tid; i < dim; i += tps) {
             double2 v = make_double2(a0, 0.0);
             if (in) {

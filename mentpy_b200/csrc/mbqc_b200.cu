@@ -99,6 +99,7 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
     t.has_noise = noise ? 1 : 0;
     if (noise) t.noise = *noise;
     t.init_scale = std::exp2(-0.5 * (window - n_inputs));
+    t.plus_amp = std::exp2(-0.5 * window);
     for (int q = 0; q < n_inputs; ++q) t.in_slot[q] = input_slot[q];
     for (int q = 0; q < n_outputs; ++q) t.out_slot[q] = output_slot[q];
     if (window <= kMaxSlotsSmall)

@@ -169,7 +169,7 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const Re
     constexpr int N = 1 << W;
     const PlanTables& t = p.tab;
     if (p.input_mode == MBQC_INPUT_PLUS) {
-        const double a = t.init_scale * exp2(-0.5 * t.n_in);
+        const double a = t.plus_amp;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             re[i] = flip_sign(a, (t.init_sign << (31 - i)) & 0x80000000u);
@@ -282,6 +282,7 @@ __device__ __forceinline__ void stage_reg_tables(const SvRegParams& p, const Reg
 // whole pattern); a warp covers 32 consecutive rows = one contiguous span of the angle matrix,
 // so every fetched sector is fully used.
 __device__ __forceinline__ void fetch_own_row(const double* __restrict__ grow, double2* cs_col0, int T, int pitch) {
+#pragma unroll 1
     for (int j = 0; j < T; ++j) cp_async8(&cs_col0[j * pitch].x, grow + j);
 }
 
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
         const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
         if (p.status) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
         if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
-        const double r = rsqrt(n2) * rsqrt(zn);
+        const double r = rsqrt(n2 * zn);
         const double ur = zr * r, ui = zi * r;  // unit phase / norm
         double2* o = DM ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
 #pragma unroll
