@@ -374,7 +374,7 @@ def run_gpu_arm(args):
                 "h2d_bytes_per_step": BATCH * T * 8, "d2h_bytes_per_step": BATCH * (2**k) * 16,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": "PatternSimulator(gs, backend='cuda-sv').run_batch(pinned host angles, copy=False) -> host amplitudes "
-                       "(C ABI mbqc_run_batch_sv_host: chunked H2D / kernel / D2H on 4 streams)"},
+                       "(C ABI mbqc_run_batch_sv_host: chunked H2D DMA + kernels storing CTA-coalesced results straight into the mapped page-locked output buffer, 4 streams)"},
             "value_stream_launch": world * BATCH * args.steps / (ms_nograph * 1e-3),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
             n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
         }
     }
-    if constexpr (DM) __syncthreads();  // everyone is done with the staged tables: re-use as stage
+    __syncthreads();  // everyone is done with the staged tables: the buffer becomes the output stage
     if (live) {
         const double zn = zr * zr + zi * zi;
         const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
@@ -337,15 +337,18 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
         if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
         const double r = rsqrt(n2 * zn);
         const double ur = zr * r, ui = zi * r;  // unit phase / norm
-        double2* o = DM ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
+        double2* o = dyn + ((size_t)threadIdx.x << k);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int d = p.tab.out_dst[i];
             if (d >= 0) o[d] = make_double2(re[i] * ur - im[i] * ui, re[i] * ui + im[i] * ur);
         }
     }
+    __syncthreads();
+    // The CTA writes its [samples][2^k] (or [samples][4^k]) block as one contiguous, fully
+    // coalesced span: 512 B per warp instruction -- also what makes direct stores into
+    // page-locked HOST memory efficient (mbqc_run_batch_sv_host with a mapped output buffer).
     if constexpr (DM) {
-        __syncthreads();
         const int64_t total = (int64_t)samples << (2 * k);
         double2* o = p.out + (b0 << (2 * k));
         const uint32_t km = (1u << k) - 1u;
@@ -354,6 +357,10 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
             const double2 x = sv[(e >> k) & km], y = sv[e & km];
             o[e] = make_double2(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y);
         }
+    } else {
+        const int total = samples << k;
+        double2* o = p.out + (b0 << k);
+        for (int e = threadIdx.x; e < total; e += kRegThreads) o[e] = dyn[e];
     }
 }
 
