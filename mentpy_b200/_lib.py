@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_mbqc_b200.so")
+LIB_PATH = os.environ.get("MBQC_LIB_PATH", os.path.join(_HERE, "_mbqc_b200.so"))  # override: kernel experiments
 
 MBQC_OK, MBQC_E_ARG, MBQC_E_CUDA, MBQC_E_UNSUPPORTED = 0, -1, -2, -3
 PLANE_XY, PLANE_XZ, PLANE_YZ = 0, 1, 2

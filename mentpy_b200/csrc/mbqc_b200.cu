@@ -253,7 +253,7 @@ static void fill_reg_params(SvRegParams& rp, const SvBatchParams& p, const mbqc_
 // dynamic shared memory of the register kernels: plan tables + (staged) the CTA's (cos, sin)
 // tile and raw angle tile; staging is skipped when the tile does not fit the budget
 template <bool DM>
-static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st) {
+static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st, bool coalesced_out) {
     const int threads = 128;
     const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
     SvRegParams rp;
@@ -266,7 +266,7 @@ static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStre
     if (stage > smem) smem = stage;
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(rp, staged);
+        kern<<<blocks, threads, smem, st>>>(rp, staged | (coalesced_out ? 2 : 0));
         return after_launch("sv_reg_kernel");
     };
     switch (p.tab.window) {
@@ -278,10 +278,10 @@ static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStre
     }
 }
 
-static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st) {
+static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st, bool coalesced_out = false) {
     const int w = p.tab.window;
     if (w <= MBQC_MAX_WINDOW_REG)
-        return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, plan, st) : launch_sv_reg<false>(p, plan, st);
+        return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, plan, st, true) : launch_sv_reg<false>(p, plan, st, coalesced_out);
     if (w > MBQC_MAX_WINDOW_SMEM_SV)
         return fail(MBQC_E_UNSUPPORTED, "batched SV covers window <= %d (got %d); use the streaming calls", MBQC_MAX_WINDOW_SMEM_SV, w);
     // threads per sample: one per pair up to 256
@@ -416,7 +416,7 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
         double2* dst = dev_view_of_host_out ? dev_view_of_host_out + lo * out_elems : d_out + lo * out_elems;
         fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, dst, nullptr);
         p.status_any = d_any + (c % kPipeStreams);
-        rc = launch_sv(p, plan, out_form, st);
+        rc = launch_sv(p, plan, out_form, st, dev_view_of_host_out != nullptr);
         if (rc) return rc;
         if (!dev_view_of_host_out)
             CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
@@ -554,7 +554,18 @@ int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32
     p.n_in = n_inputs;
     p.scale = scale;
     for (int q = 0; q < n_inputs; ++q) p.in_slot[q] = input_slot[q];
-    for (int a = 0; a < window; ++a) p.cz[a] = init_cz_mask[a];
+    // cz[a] holds the slots b > a coupled to a: regroup by distance d = b - a
+    p.n_dist = 0;
+    for (int d = 1; d < window; ++d) {
+        uint64_t m = 0;
+        for (int a = 0; a + d < window; ++a)
+            if ((init_cz_mask[a] >> (a + d)) & 1ull) m |= 1ull << a;
+        if (m) {
+            p.dist[p.n_dist] = d;
+            p.pair_mask[p.n_dist] = m;
+            ++p.n_dist;
+        }
+    }
     stream_init_kernel<<<stream_grid(p.n_local, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return after_launch("stream_init_kernel");
 }

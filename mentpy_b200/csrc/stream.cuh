@@ -132,7 +132,12 @@ struct StreamInitParams {
     int32_t window, n_in;
     double scale;
     int32_t in_slot[kMaxIO];
-    uint64_t cz[MBQC_MAX_WINDOW];
+    // initial CZ signs grouped by slot distance d: parity(g & (g >> d) & pair_mask[d]) summed over
+    // the distances present (1 for a linear cluster, {1, rows} for a grid) instead of a loop
+    // over all window bits per amplitude
+    int32_t n_dist;
+    int32_t dist[MBQC_MAX_WINDOW];
+    uint64_t pair_mask[MBQC_MAX_WINDOW];
 };
 
 __global__ void __launch_bounds__(256) stream_init_kernel(const __grid_constant__ StreamInitParams p) {
@@ -147,9 +152,9 @@ __global__ void __launch_bounds__(256) stream_init_kernel(const __grid_constant_
             v.x *= p.scale;
             v.y *= p.scale;
         }
-        uint32_t sg = 0;
-        for (int a = 0; a < p.window; ++a)
-            if ((g >> a) & 1ull) sg ^= (uint32_t)__popcll(g & p.cz[a]) & 1u;
+        uint64_t acc = 0;
+        for (int q = 0; q < p.n_dist; ++q) acc ^= g & (g >> p.dist[q]) & p.pair_mask[q];
+        const uint32_t sg = (uint32_t)__popcll(acc) & 1u;
         if (sg) {
             v.x = -v.x;
             v.y = -v.y;

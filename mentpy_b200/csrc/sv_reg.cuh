@@ -240,6 +240,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+#ifndef MBQC_REG_MINBLOCKS_W3
+#define MBQC_REG_MINBLOCKS_W3 8
+#endif
 constexpr int kRegThreads = 128;  // CTA size of the register kernels
 
 // dynamic shared memory layout of the register kernels (all offsets 16-byte aligned)
@@ -301,8 +304,9 @@ __device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pit
 // DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
 // (np_simulator_sv.py:292-293, the reference's default output form); the CTA stages its
 // normalised amplitudes in shared memory and writes the outer products fully coalesced.
+// `staged`: bit 0 = angle tile staged in shared memory, bit 1 = CTA-coalesced output stage.
 template <int W, bool DM>
-__global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvRegParams pp, int staged) {
+__global__ void __launch_bounds__(128, (W <= 3 ? MBQC_REG_MINBLOCKS_W3 : (W == 4 ? 5 : 3))) sv_reg_kernel(const __grid_constant__ SvRegParams pp, int staged) {
     constexpr int N = 1 << W;
     extern __shared__ double2 dyn[];
     const SvBatchParams& p = pp.base;
@@ -314,13 +318,13 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
     const int k = p.tab.n_out;
     const int samples = (int)min((int64_t)kRegThreads, p.batch - b0);
     stage_reg_tables(pp, l);
-    if (staged && live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
+    if ((staged & 1) && live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
     cp_async_wait_all();
     __syncthreads();
     const RegSmem sm{l.cols, l.signs, pp.reg.sign_pitch};
     double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
     if (live) {
-        if (staged) {
+        if (staged & 1) {
             convert_own_row(l.cs + threadIdx.x, T, kRegThreads);
             const AngleStaged ang{l.cs + threadIdx.x, kRegThreads, T, l.fixed, -1, 1.0, 0.0};
             n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
@@ -329,7 +333,13 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
             n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
         }
     }
-    __syncthreads();  // everyone is done with the staged tables: the buffer becomes the output stage
+    // Output.  Device-resident callers get direct 16-byte stores from registers.  With
+    // `stage_out` (DM form, or an output buffer in page-locked HOST memory) the CTA first
+    // collects its normalised amplitudes in shared memory and then writes its whole block as one
+    // contiguous span, 512 B per warp instruction: that is what makes stores over PCIe efficient
+    // (156 vs 261 us per 65,536-sample step in scripts/zerocopy_probe2.cu).
+    const bool stage_out = DM || (staged & 2);
+    if (stage_out) __syncthreads();  // everyone is done with the staged tables: re-use the buffer
     if (live) {
         const double zn = zr * zr + zi * zi;
         const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
@@ -337,17 +347,15 @@ __global__ void __launch_bounds__(128) sv_reg_kernel(const __grid_constant__ SvR
         if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
         const double r = rsqrt(n2 * zn);
         const double ur = zr * r, ui = zi * r;  // unit phase / norm
-        double2* o = dyn + ((size_t)threadIdx.x << k);
+        double2* o = stage_out ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int d = p.tab.out_dst[i];
             if (d >= 0) o[d] = make_double2(re[i] * ur - im[i] * ui, re[i] * ui + im[i] * ur);
         }
     }
+    if (!stage_out) return;
     __syncthreads();
-    // The CTA writes its [samples][2^k] (or [samples][4^k]) block as one contiguous, fully
-    // coalesced span: 512 B per warp instruction -- also what makes direct stores into
-    // page-locked HOST memory efficient (mbqc_run_batch_sv_host with a mapped output buffer).
     if constexpr (DM) {
         const int64_t total = (int64_t)samples << (2 * k);
         double2* o = p.out + (b0 << (2 * k));

@@ -44,3 +44,21 @@ t0 = time.perf_counter()
 for _ in range(50): ps.run_batch(h, copy=False)
 dt = (time.perf_counter() - t0) / 50
 print(f"python run_batch(copy=False): {dt*1e6:8.1f} us/step  {B/dt/1e6:8.1f} M evals/s")
+
+# same C call as run_batch makes (shared input state instead of the built-in |+> seed)
+inp, mode = sim._stage_inputs(None, B, dev)
+torch.cuda.synchronize()
+for label, iptr, imode in (("INPUT_PLUS", None, 0), ("INPUT_SHARED", inp.data_ptr(), mode)):
+    def run2():
+        rc = lib.mbqc_run_batch_sv_host(plan.handle, h.data_ptr(), T, iptr, imode, B, ho.data_ptr(), 0, work.data_ptr(), need, C.byref(flag), 0)
+        assert rc == 0
+    for _ in range(5): run2()
+    t0 = time.perf_counter()
+    for _ in range(50): run2()
+    dt = (time.perf_counter() - t0) / 50
+    print(f"C pipeline default chunks, {label}: {dt*1e6:8.1f} us/step")
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for _ in range(50): ps.run_batch(h, copy=False)
+pr.disable()
+pstats.Stats(pr).sort_stats("tottime").print_stats(6)
