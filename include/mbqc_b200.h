@@ -155,7 +155,19 @@ typedef struct mbqc_stream_desc {
     uint64_t n_groups;       /* 2^(live local bits - K) */
     uint64_t index_or;       /* rank << local_bits: completes the index for sign parities */
     double scale;            /* exact power-of-two rescale applied on load */
+    uint64_t elem_bit[MBQC_STREAM_MAX_FUSE];      /* 1 << slot as an INDEX bit (elem_offset is an address
+                                                     offset and differs for the split top local slot) */
 } mbqc_stream_desc;
+
+/* Window seed (np_simulator_sv.py:103-128) for passes that generate the initial state on the fly. */
+typedef struct mbqc_stream_seed {
+    int32_t window;
+    int32_t n_inputs;
+    int32_t input_slot[16];
+    uint64_t init_cz_mask[MBQC_MAX_WINDOW];
+    const void* d_input;     /* NULL: |+> inputs */
+    double scale;            /* 2^{-(w-|I|)/2} (or 2^{-w/2} with |+> inputs) */
+} mbqc_stream_seed;
 
 /* Seed the local share of the window: input (x) |+>^(w-|I|), initial CZ signs (np_simulator_sv.py:103-128). */
 int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32_t window,
@@ -163,6 +175,11 @@ int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32
                      const void* d_input, double scale, void* stream);
 /* One in-place pass over the local share applying desc->n_fused measurements (np_simulator_sv.py:164-225). */
 int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream);
+/* Same pass, but the amplitudes it consumes are generated from the seed instead of being read:
+ * the first pass of a pattern then needs no separate init pass (saves one write + one read of
+ * the whole state). */
+int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const mbqc_stream_seed* seed,
+                             void* stream);
 /* Measurement of a shard slot fused with the NVLink transfer: d_peer is the partner GPU's half
  * (peer-mapped memory), read directly by the kernel.  role 0/1: this rank's shard bit; role 2:
  * tail step without append (whole shard, survivor side).  See csrc/stream.cuh. */

@@ -34,7 +34,13 @@ class StreamDesc(C.Structure):
                 ("elem_offset", C.c_uint64 * STREAM_MAX_FUSE), ("cos_t", C.c_double * STREAM_MAX_FUSE),
                 ("sin_t", C.c_double * STREAM_MAX_FUSE), ("nbr_mask", C.c_uint64 * STREAM_MAX_FUSE),
                 ("local_mask", C.c_uint32 * STREAM_MAX_FUSE), ("append_mask", C.c_uint32),
-                ("n_groups", C.c_uint64), ("index_or", C.c_uint64), ("scale", C.c_double)]
+                ("n_groups", C.c_uint64), ("index_or", C.c_uint64), ("scale", C.c_double),
+                ("elem_bit", C.c_uint64 * STREAM_MAX_FUSE)]
+
+
+class StreamSeed(C.Structure):
+    _fields_ = [("window", C.c_int32), ("n_inputs", C.c_int32), ("input_slot", C.c_int32 * 16),
+                ("init_cz_mask", C.c_uint64 * MAX_WINDOW), ("d_input", C.c_void_p), ("scale", C.c_double)]
 
 
 class Noise(C.Structure):
@@ -60,6 +66,7 @@ _SIGNATURES = {
     "mbqc_stream_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p, C.c_double, C.c_void_p]),
     "mbqc_stream_steps": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_void_p]),
+    "mbqc_stream_steps_seeded": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.POINTER(StreamSeed), C.c_void_p]),
     "mbqc_stream_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                                        C.c_double, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
     "mbqc_stream_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_int32),

@@ -538,39 +538,48 @@ int stream_grid(uint64_t work_items, int threads) {
 
 extern "C" {
 
-int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32_t window,
-                     int32_t n_inputs, const int32_t* input_slot, const uint64_t* init_cz_mask,
-                     const void* d_input, double scale, void* stream) {
-    if (!d_state) return fail(MBQC_E_ARG, "d_state is NULL");
-    if (window < 1 || window > MBQC_MAX_WINDOW || local_bits < 0 || local_bits > window) return fail(MBQC_E_ARG, "bad window/local_bits");
+}  // extern "C"
+
+static int make_seed(SeedDev& sd, int32_t window, int32_t n_inputs, const int32_t* input_slot,
+                     const uint64_t* init_cz_mask, const void* d_input, double scale) {
+    if (window < 1 || window > MBQC_MAX_WINDOW) return fail(MBQC_E_ARG, "bad window");
     if (n_inputs < 0 || n_inputs > kMaxIO || (n_inputs && !input_slot) || !init_cz_mask) return fail(MBQC_E_ARG, "bad input tables");
-    StreamInitParams p;
-    memset(&p, 0, sizeof(p));
-    p.state = (double2*)d_state;
-    p.input = (const double2*)d_input;
-    p.n_local = 1ull << local_bits;
-    p.index_or = index_or;
-    p.window = window;
-    p.n_in = n_inputs;
-    p.scale = scale;
-    for (int q = 0; q < n_inputs; ++q) p.in_slot[q] = input_slot[q];
+    memset(&sd, 0, sizeof(sd));
+    sd.input = (const double2*)d_input;
+    sd.n_in = n_inputs;
+    sd.scale = scale;
+    for (int q = 0; q < n_inputs; ++q) sd.in_slot[q] = input_slot[q];
     // cz[a] holds the slots b > a coupled to a: regroup by distance d = b - a
-    p.n_dist = 0;
     for (int d = 1; d < window; ++d) {
         uint64_t m = 0;
         for (int a = 0; a + d < window; ++a)
             if ((init_cz_mask[a] >> (a + d)) & 1ull) m |= 1ull << a;
         if (m) {
-            p.dist[p.n_dist] = d;
-            p.pair_mask[p.n_dist] = m;
-            ++p.n_dist;
+            sd.dist[sd.n_dist] = d;
+            sd.pair_mask[sd.n_dist] = m;
+            ++sd.n_dist;
         }
     }
+    return MBQC_OK;
+}
+
+extern "C" int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32_t window,
+                     int32_t n_inputs, const int32_t* input_slot, const uint64_t* init_cz_mask,
+                     const void* d_input, double scale, void* stream) {
+    if (!d_state) return fail(MBQC_E_ARG, "d_state is NULL");
+    if (local_bits < 0 || local_bits > window) return fail(MBQC_E_ARG, "bad window/local_bits");
+    StreamInitParams p;
+    int rc = make_seed(p.seed, window, n_inputs, input_slot, init_cz_mask, d_input, scale);
+    if (rc) return rc;
+    p.state = (double2*)d_state;
+    p.n_local = 1ull << local_bits;
+    p.index_or = index_or;
     stream_init_kernel<<<stream_grid(p.n_local, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return after_launch("stream_init_kernel");
 }
 
-int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream) {
+template <bool SEED>
+static int launch_stream_steps(void* d_state, const mbqc_stream_desc* desc, const SeedDev& seed, void* stream) {
     if (!d_state || !desc) return fail(MBQC_E_ARG, "NULL argument");
     if (desc->n_fused < 1 || desc->n_fused > MBQC_STREAM_MAX_FUSE) return fail(MBQC_E_ARG, "n_fused %d outside [1,%d]", desc->n_fused, MBQC_STREAM_MAX_FUSE);
     if (desc->n_ranges < 0 || desc->n_ranges > MBQC_STREAM_MAX_RANGES) return fail(MBQC_E_ARG, "n_ranges %d outside [0,%d]", desc->n_ranges, MBQC_STREAM_MAX_RANGES);
@@ -579,13 +588,30 @@ int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream)
     cudaStream_t st = (cudaStream_t)stream;
     double2* s = (double2*)d_state;
     switch (desc->n_fused) {
-        case 1: stream_steps_kernel<1><<<grid, 256, 0, st>>>(s, *desc); break;
-        case 2: stream_steps_kernel<2><<<grid, 256, 0, st>>>(s, *desc); break;
-        case 3: stream_steps_kernel<3><<<grid, 256, 0, st>>>(s, *desc); break;
-        case 4: stream_steps_kernel<4><<<grid, 256, 0, st>>>(s, *desc); break;
-        default: stream_steps_kernel<5><<<grid, 256, 0, st>>>(s, *desc); break;
+        case 1: stream_steps_kernel<1, SEED><<<grid, 256, 0, st>>>(s, *desc, seed); break;
+        case 2: stream_steps_kernel<2, SEED><<<grid, 256, 0, st>>>(s, *desc, seed); break;
+        case 3: stream_steps_kernel<3, SEED><<<grid, 256, 0, st>>>(s, *desc, seed); break;
+        case 4: stream_steps_kernel<4, SEED><<<grid, 256, 0, st>>>(s, *desc, seed); break;
+        default: stream_steps_kernel<5, SEED><<<grid, 256, 0, st>>>(s, *desc, seed); break;
     }
     return after_launch("stream_steps_kernel");
+}
+
+extern "C" {
+
+int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream) {
+    SeedDev none;
+    memset(&none, 0, sizeof(none));
+    return launch_stream_steps<false>(d_state, desc, none, stream);
+}
+
+int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const mbqc_stream_seed* seed,
+                             void* stream) {
+    if (!seed) return fail(MBQC_E_ARG, "seed is NULL");
+    SeedDev sd;
+    int rc = make_seed(sd, seed->window, seed->n_inputs, seed->input_slot, seed->init_cz_mask, seed->d_input, seed->scale);
+    if (rc) return rc;
+    return launch_stream_steps<true>(d_state, desc, sd, stream);
 }
 
 int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t role, double cos_t,

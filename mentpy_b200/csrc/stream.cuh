@@ -23,9 +23,41 @@ __device__ __forceinline__ uint64_t insert_zero_field(uint64_t g, uint32_t pos, 
     return ((g >> pos) << (pos + width)) | lo;
 }
 
-template <int K>
+// window seed in kernel-friendly form: input gather + initial CZ signs grouped by slot distance d,
+// sign = parity( XOR_d  g & (g >> d) & pair_mask[d] )  (1 distance for a linear cluster, {1, rows}
+// for a grid) instead of a loop over all window bits per amplitude
+struct SeedDev {
+    const double2* input;  // null: |+> inputs
+    int32_t n_in;
+    int32_t n_dist;
+    double scale;
+    int32_t in_slot[kMaxIO];
+    int32_t dist[MBQC_MAX_WINDOW];
+    uint64_t pair_mask[MBQC_MAX_WINDOW];
+};
+
+__device__ __forceinline__ double2 seed_amplitude(const SeedDev& p, uint64_t g) {
+    double2 v = make_double2(p.scale, 0.0);
+    if (p.input) {
+        uint32_t src = 0;
+        for (int q = 0; q < p.n_in; ++q) src |= (uint32_t)((g >> p.in_slot[q]) & 1ull) << (p.n_in - 1 - q);
+        v = __ldg(p.input + src);
+        v.x *= p.scale;
+        v.y *= p.scale;
+    }
+    uint64_t acc = 0;
+    for (int q = 0; q < p.n_dist; ++q) acc ^= g & (g >> p.dist[q]) & p.pair_mask[q];
+    if (__popcll(acc) & 1) {
+        v.x = -v.x;
+        v.y = -v.y;
+    }
+    return v;
+}
+
+template <int K, bool SEED>
 __global__ void __launch_bounds__(256) stream_steps_kernel(double2* __restrict__ state,
-                                                           const __grid_constant__ mbqc_stream_desc d) {
+                                                           const __grid_constant__ mbqc_stream_desc d,
+                                                           const __grid_constant__ SeedDev seed) {
     constexpr int N = 1 << K;
     uint64_t ofs[N];
 #pragma unroll
@@ -46,13 +78,27 @@ __global__ void __launch_bounds__(256) stream_steps_kernel(double2* __restrict__
         for (int r = 0; r < d.n_ranges; ++r) g = insert_zero_field(g, d.range_pos[r], d.range_width[r]);
         double2* base = state + g;
         double re[N], im[N];
+        if constexpr (!SEED) {
 #pragma unroll
-        for (int l = 0; l < N; ++l) {
-            const double2 v = base[ofs[l]];
-            re[l] = v.x * d.scale;
-            im[l] = v.y * d.scale;
+            for (int l = 0; l < N; ++l) {
+                const double2 v = base[ofs[l]];
+                re[l] = v.x * d.scale;
+                im[l] = v.y * d.scale;
+            }
         }
         const uint64_t gfull = g | d.index_or;
+        if constexpr (SEED) {  // first pass of a pattern: generate the seed instead of reading it
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+                uint64_t idx = gfull;
+#pragma unroll
+                for (int j = 0; j < K; ++j)
+                    if (l & (1 << j)) idx |= d.elem_bit[j];
+                const double2 v = seed_amplitude(seed, idx);
+                re[l] = v.x * d.scale;
+                im[l] = v.y * d.scale;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const double c = d.cos_t[j], s = d.sin_t[j];
@@ -126,41 +172,15 @@ __global__ void __launch_bounds__(256) stream_exchange_kernel(const __grid_const
 
 struct StreamInitParams {
     double2* state;
-    const double2* input;  // null: |+> inputs
     uint64_t n_local;
     uint64_t index_or;
-    int32_t window, n_in;
-    double scale;
-    int32_t in_slot[kMaxIO];
-    // initial CZ signs grouped by slot distance d: parity(g & (g >> d) & pair_mask[d]) summed over
-    // the distances present (1 for a linear cluster, {1, rows} for a grid) instead of a loop
-    // over all window bits per amplitude
-    int32_t n_dist;
-    int32_t dist[MBQC_MAX_WINDOW];
-    uint64_t pair_mask[MBQC_MAX_WINDOW];
+    SeedDev seed;
 };
 
 __global__ void __launch_bounds__(256) stream_init_kernel(const __grid_constant__ StreamInitParams p) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_local; i += stride) {
-        const uint64_t g = i | p.index_or;
-        double2 v = make_double2(p.scale, 0.0);
-        if (p.input) {
-            uint32_t src = 0;
-            for (int q = 0; q < p.n_in; ++q) src |= (uint32_t)((g >> p.in_slot[q]) & 1ull) << (p.n_in - 1 - q);
-            v = __ldg(p.input + src);
-            v.x *= p.scale;
-            v.y *= p.scale;
-        }
-        uint64_t acc = 0;
-        for (int q = 0; q < p.n_dist; ++q) acc ^= g & (g >> p.dist[q]) & p.pair_mask[q];
-        const uint32_t sg = (uint32_t)__popcll(acc) & 1u;
-        if (sg) {
-            v.x = -v.x;
-            v.y = -v.y;
-        }
-        p.state[i] = v;
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n_local; i += stride)
+        p.state[i] = seed_amplitude(p.seed, i | p.index_or);
 }
 
 struct StreamGatherParams {

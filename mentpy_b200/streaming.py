@@ -221,12 +221,15 @@ class StreamExecutor:
         self.last_schedule = sched
         L, rank = sched.local_bits, self.rank
         eng = self.engine
-        eng.init(self.plan, L, rank, input_state)
+        # when the pattern starts with a local pass, the engine may generate the seed inside that
+        # pass instead of writing it out first (one write + one read of the whole state saved)
+        first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass)
+        eng.init(self.plan, L, rank, input_state, defer=first_local)
         alive = True
-        for p in sched.passes:
+        for n_pass, p in enumerate(sched.passes):
             if isinstance(p, LocalPass):
                 if alive:
-                    eng.local_pass(p, rank << L)
+                    eng.local_pass(p, rank << L, seeded=(n_pass == 0))
                 continue
             v = (rank >> p.shard_bit) & 1
             partner = rank ^ (1 << p.shard_bit)
@@ -353,7 +356,7 @@ class CudaStreamEngine:
     def _stream(self):
         return self.torch.cuda.current_stream(self.device).cuda_stream
 
-    def init(self, plan: LoweredPlan, L: int, rank: int, input_state):
+    def init(self, plan: LoweredPlan, L: int, rank: int, input_state, defer: bool = False):
         import ctypes as C
 
         world = 1 << (plan.window - L)
@@ -374,6 +377,18 @@ class CudaStreamEngine:
             scale = 2.0 ** (-w / 2)
         in_arr = (C.c_int32 * max(n_in, 1))(*plan.input_slot)
         cz_arr = (C.c_uint64 * w)(*plan.init_cz_mask)
+        seed = self._lib.StreamSeed()
+        seed.window, seed.n_inputs, seed.scale = w, n_in, scale
+        for q, sl in enumerate(plan.input_slot):
+            seed.input_slot[q] = sl
+        for a, m in enumerate(plan.init_cz_mask):
+            seed.init_cz_mask[a] = m
+        seed.d_input = None if d_in is None else d_in.data_ptr()
+        self._seed = seed
+        self._keep = d_in
+        self.rank = rank
+        if defer:
+            return
         with self.torch.cuda.device(self.device):
             for h in (0, 1):
                 index_or = (rank << L) | (h << (L - 1))
@@ -387,8 +402,15 @@ class CudaStreamEngine:
         r = self.roles[self.rank]
         return ((self.bufs[r[1]] - self.bufs[r[0]]) // 16) & 0xFFFFFFFFFFFFFFFF
 
-    def local_pass(self, p: LocalPass, index_or: int):
+    def local_pass(self, p: LocalPass, index_or: int, seeded: bool = False):
         import ctypes as C
+
+        def launch(buf, desc):
+            if seeded:
+                self._lib.check(self.lib.mbqc_stream_steps_seeded(C.c_void_p(buf), C.byref(desc), C.byref(self._seed),
+                                                                  C.c_void_p(self._stream())))
+            else:
+                self._lib.check(self.lib.mbqc_stream_steps(C.c_void_p(buf), C.byref(desc), C.c_void_p(self._stream())))
 
         d = self._lib.StreamDesc()
         top = self.L - 1
@@ -401,6 +423,7 @@ class CudaStreamEngine:
         top_dead = any(pos <= top < pos + wd for pos, wd in rng) and not top_fused
         for k, sl in enumerate(p.slots):
             d.elem_offset[k] = hi if sl == top else (1 << sl)
+            d.elem_bit[k] = 1 << sl
             d.cos_t[k], d.sin_t[k] = p.cos_t[k], p.sin_t[k]
             d.nbr_mask[k], d.local_mask[k] = p.nbr_masks[k], p.local_masks[k]
         d.append_mask = p.append_mask
@@ -413,7 +436,7 @@ class CudaStreamEngine:
                     d.range_pos[q], d.range_width[q] = pos, wd
                 d.n_groups = p.n_groups
                 d.index_or = index_or
-                self._lib.check(self.lib.mbqc_stream_steps(C.c_void_p(self.bufs[r[0]]), C.byref(d), C.c_void_p(self._stream())))
+                launch(self.bufs[r[0]], d)
             else:
                 # ranges never reach the top bit here: run the pass on each half separately
                 d.n_ranges = len(rng)
@@ -422,7 +445,7 @@ class CudaStreamEngine:
                 d.n_groups = p.n_groups >> 1
                 for h in (0, 1):
                     d.index_or = index_or | (h << top)
-                    self._lib.check(self.lib.mbqc_stream_steps(C.c_void_p(self.bufs[r[h]]), C.byref(d), C.c_void_p(self._stream())))
+                    launch(self.bufs[r[h]], d)
 
     def exchange(self, p: ExchangePass, role: int, partner: int, const_parity: int):
         import ctypes as C
@@ -495,14 +518,23 @@ class CudaSimulatorSVStream:
         from .plan import lower
 
         self.mbqcircuit = mbqcircuit
+        self.group = kwargs.get("group", None)
         self.window_size = kwargs.pop("window_size", 1)
         self.schedule = kwargs.pop("schedule", None)
-        self.fuse = kwargs.pop("fuse", 4)
+        self.fuse = kwargs.pop("fuse", 5)
         self.group = kwargs.pop("group", None)
         self.force0 = kwargs.pop("force0", True)
         if not self.force0:
             raise NotImplementedError("Numpy simulator does not support force0=False.")
-        self.plan = lower(mbqcircuit, self.window_size, self.schedule, mixed=False)
+        # Sharded runs put the window position measured LAST into the highest (shard) slots: a
+        # shard slot costs an NVLink exchange every time it is measured, so the first w - g
+        # measurements are all local and, for patterns not much longer than the window, shard
+        # slots are only reached in the tail when the live state is already tiny.
+        slot_order = kwargs.pop("slot_order", None)
+        if slot_order is None:
+            slot_order = "lsb" if self._dist()[1] > 1 else "msb"
+        self.slot_order = slot_order
+        self.plan = lower(mbqcircuit, self.window_size, self.schedule, mixed=False, slot_order=slot_order)
         self.window_size = self.plan.window
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure

@@ -24,7 +24,7 @@ class NumpyStreamEngine:
     def __init__(self, dist=None):
         self.dist = dist  # torch.distributed module when world > 1
 
-    def init(self, plan, L, rank, input_state):
+    def init(self, plan, L, rank, input_state, defer=False):  # the emulation always materialises the seed
         w = plan.window
         self.L, self.rank = L, rank
         n = 1 << L
@@ -52,7 +52,7 @@ class NumpyStreamEngine:
         half = len(v) // 2
         self.H = [v[:half].copy(), v[half:].copy()]
 
-    def local_pass(self, p, index_or):
+    def local_pass(self, p, index_or, seeded=False):
         psi = self._full()
         K = len(p.slots)
         t = np.arange(p.n_groups, dtype=np.uint64)

@@ -71,7 +71,7 @@ def test_haar_input_and_fixed_angles():
     assert np.allclose(got, _want(gs, 8, ang, inp), atol=1e-9)
 
 
-def _gloo_worker(rank, world, port, spec, w, fuse, seed, q):
+def _gloo_worker(rank, world, port, spec, w, fuse, seed, q, order="msb"):
     import torch.distributed as dist
 
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -82,7 +82,7 @@ def _gloo_worker(rank, world, port, spec, w, fuse, seed, q):
     try:
         name, args = spec
         gs = getattr(mb.templates, name)(*args)
-        plan = lower(gs, window_size=w)
+        plan = lower(gs, window_size=w, slot_order=order)
         ang = np.random.default_rng(seed).uniform(0, 2 * np.pi, plan.n_angles)
         g = world.bit_length() - 1
         out = StreamExecutor(plan, Eng(dist), rank, g, fuse).run(ang)
@@ -92,17 +92,18 @@ def _gloo_worker(rank, world, port, spec, w, fuse, seed, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,spec,w,fuse", [(2, ("linear_cluster", [18]), 8, 3),
-                                               (2, ("grid_cluster", [3, 6]), 7, 4),
-                                               (4, ("linear_cluster", [16]), 7, 2),
-                                               (4, ("grid_cluster", [2, 8]), 6, 5)])
-def test_sharded_schedule_gloo(world, spec, w, fuse):
+@pytest.mark.parametrize("world,spec,w,fuse,order", [(2, ("linear_cluster", [18]), 8, 3, "msb"),
+                                                     (2, ("grid_cluster", [3, 6]), 7, 4, "lsb"),
+                                                     (4, ("linear_cluster", [16]), 7, 2, "lsb"),
+                                                     (4, ("grid_cluster", [2, 8]), 6, 5, "msb"),
+                                                     (2, ("linear_cluster", [40]), 8, 5, "lsb")])
+def test_sharded_schedule_gloo(world, spec, w, fuse, order):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + world * 7 + w
-    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, spec, w, fuse, 11, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + world * 7 + w + fuse * 13
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, spec, w, fuse, 11, q, order)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=120)
