@@ -607,10 +607,33 @@ int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream)
 
 int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const mbqc_stream_seed* seed,
                              void* stream) {
-    if (!seed) return fail(MBQC_E_ARG, "seed is NULL");
+    if (!seed || !desc) return fail(MBQC_E_ARG, "seed/desc is NULL");
+    if (seed->d_input) return fail(MBQC_E_UNSUPPORTED, "seeded passes cover the |+> input; write other inputs with mbqc_stream_init");
     SeedDev sd;
-    int rc = make_seed(sd, seed->window, seed->n_inputs, seed->input_slot, seed->init_cz_mask, seed->d_input, seed->scale);
+    int rc = make_seed(sd, seed->window, seed->n_inputs, seed->input_slot, seed->init_cz_mask, nullptr, seed->scale);
     if (rc) return rc;
+    // symmetric initial-CZ adjacency of the fused slots, and the parity of edges inside each subset
+    const int K = desc->n_fused;
+    if (K < 1 || K > MBQC_STREAM_MAX_FUSE) return fail(MBQC_E_ARG, "n_fused out of range");
+    int slot[MBQC_STREAM_MAX_FUSE];
+    for (int j = 0; j < K; ++j) {
+        const uint64_t b = desc->elem_bit[j];
+        if (!b || (b & (b - 1))) return fail(MBQC_E_ARG, "elem_bit[%d] is not a single bit", j);
+        slot[j] = __builtin_ctzll(b);
+        uint64_t nb = (slot[j] < seed->window) ? seed->init_cz_mask[slot[j]] : 0ull;
+        for (int a = 0; a < seed->window && a < slot[j]; ++a)
+            if ((seed->init_cz_mask[a] >> slot[j]) & 1ull) nb |= 1ull << a;
+        sd.nbr[j] = nb;
+    }
+    sd.pair_parity = 0;
+    for (uint32_t l = 0; l < (1u << K); ++l) {
+        uint32_t par = 0;
+        for (int i = 0; i < K; ++i)
+            for (int j = i + 1; j < K; ++j)
+                if (((l >> i) & 1u) && ((l >> j) & 1u) && ((sd.nbr[i] >> slot[j]) & 1ull)) par ^= 1u;
+        sd.pair_parity |= par << l;
+    }
+    // the base index has the fused bits clear, so nbr[j] & base never sees another fused slot
     return launch_stream_steps<true>(d_state, desc, sd, stream);
 }
 

@@ -34,6 +34,10 @@ struct SeedDev {
     int32_t in_slot[kMaxIO];
     int32_t dist[MBQC_MAX_WINDOW];
     uint64_t pair_mask[MBQC_MAX_WINDOW];
+    // seeded passes (|+> inputs only): sign of group element l relative to the group's base index
+    //   sign(l) = sign(base) ^ XOR_{j in l} parity(base & nbr[j]) ^ bit l of pair_parity
+    uint64_t nbr[MBQC_STREAM_MAX_FUSE];  // initial-CZ neighbours of fused slot j (both directions)
+    uint32_t pair_parity;                // bit l: parity of the initial CZ edges inside subset l
 };
 
 __device__ __forceinline__ double2 seed_amplitude(const SeedDev& p, uint64_t g) {
@@ -87,16 +91,19 @@ __global__ void __launch_bounds__(256) stream_steps_kernel(double2* __restrict__
             }
         }
         const uint64_t gfull = g | d.index_or;
-        if constexpr (SEED) {  // first pass of a pattern: generate the seed instead of reading it
+        if constexpr (SEED) {  // first pass of a pattern: generate the |+>^w seed instead of reading it
+            uint64_t acc = 0;
+            for (int q = 0; q < seed.n_dist; ++q) acc ^= gfull & (gfull >> seed.dist[q]) & seed.pair_mask[q];
+            uint32_t pj = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) pj |= ((uint32_t)__popcll(gfull & seed.nbr[j]) & 1u) << j;
+            const uint32_t par0 = (uint32_t)__popcll(acc) & 1u;
+            const double a = seed.scale * d.scale;
 #pragma unroll
             for (int l = 0; l < N; ++l) {
-                uint64_t idx = gfull;
-#pragma unroll
-                for (int j = 0; j < K; ++j)
-                    if (l & (1 << j)) idx |= d.elem_bit[j];
-                const double2 v = seed_amplitude(seed, idx);
-                re[l] = v.x * d.scale;
-                im[l] = v.y * d.scale;
+                const uint32_t sg = (par0 ^ ((uint32_t)__popc((uint32_t)l & pj) & 1u) ^ ((seed.pair_parity >> l) & 1u)) << 31;
+                re[l] = flip_sign(a, sg);
+                im[l] = 0.0;
             }
         }
 #pragma unroll

@@ -223,13 +223,13 @@ class StreamExecutor:
         eng = self.engine
         # when the pattern starts with a local pass, the engine may generate the seed inside that
         # pass instead of writing it out first (one write + one read of the whole state saved)
-        first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass)
+        first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass) and input_state is None
         eng.init(self.plan, L, rank, input_state, defer=first_local)
         alive = True
         for n_pass, p in enumerate(sched.passes):
             if isinstance(p, LocalPass):
                 if alive:
-                    eng.local_pass(p, rank << L, seeded=(n_pass == 0))
+                    eng.local_pass(p, rank << L, seeded=(n_pass == 0 and first_local))
                 continue
             v = (rank >> p.shard_bit) & 1
             partner = rank ^ (1 << p.shard_bit)
