@@ -225,6 +225,9 @@ class StreamExecutor:
         # pass instead of writing it out first (one write + one read of the whole state saved)
         first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass) and input_state is None
         eng.init(self.plan, L, rank, input_state, defer=first_local)
+        if first_local:  # the first pass generates its input: no read of the state in that pass
+            p0 = sched.passes[0]
+            sched.streamed_bytes -= (1 << self.shard_bits) * 16 * (1 << p0.live_bits)
         alive = True
         for n_pass, p in enumerate(sched.passes):
             if isinstance(p, LocalPass):
