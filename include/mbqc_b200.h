@@ -175,6 +175,11 @@ int mbqc_stream_init(void* d_state, int32_t local_bits, uint64_t index_or, int32
                      const void* d_input, double scale, void* stream);
 /* One in-place pass over the local share applying desc->n_fused measurements (np_simulator_sv.py:164-225). */
 int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream);
+/* Variant for fused slots that are all among the 5 lowest index bits: one element per thread, pair
+ * partners exchanged with warp shuffles, every access a contiguous 512-byte span per warp.
+ * Descriptor convention differs: ranges squeeze out DEAD slots only (all >= 5) and n_groups is the
+ * number of live local elements (multiple of 32); elem_bit[j] = 1 << slot_j < 32. */
+int mbqc_stream_steps_lanes(void* d_state, const mbqc_stream_desc* desc, void* stream);
 /* Same pass, but the amplitudes it consumes are generated from the seed instead of being read:
  * the first pass of a pattern then needs no separate init pass (saves one write + one read of
  * the whole state). */

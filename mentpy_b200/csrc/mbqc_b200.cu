@@ -605,6 +605,21 @@ int mbqc_stream_steps(void* d_state, const mbqc_stream_desc* desc, void* stream)
     return launch_stream_steps<false>(d_state, desc, none, stream);
 }
 
+int mbqc_stream_steps_lanes(void* d_state, const mbqc_stream_desc* desc, void* stream) {
+    if (!d_state || !desc) return fail(MBQC_E_ARG, "NULL argument");
+    if (desc->n_fused < 1 || desc->n_fused > MBQC_STREAM_MAX_FUSE) return fail(MBQC_E_ARG, "n_fused %d outside [1,%d]", desc->n_fused, MBQC_STREAM_MAX_FUSE);
+    if (desc->n_ranges < 0 || desc->n_ranges > MBQC_STREAM_MAX_RANGES) return fail(MBQC_E_ARG, "n_ranges %d outside [0,%d]", desc->n_ranges, MBQC_STREAM_MAX_RANGES);
+    for (int j = 0; j < desc->n_fused; ++j)
+        if (desc->elem_bit[j] == 0 || desc->elem_bit[j] >= 32 || (desc->elem_bit[j] & (desc->elem_bit[j] - 1)))
+            return fail(MBQC_E_ARG, "lane pass: fused slot %d is not one of the 5 lane bits", j);
+    for (int r = 0; r < desc->n_ranges; ++r)
+        if (desc->range_pos[r] < 5) return fail(MBQC_E_ARG, "lane pass: dead slot below bit 5");
+    if (desc->n_groups == 0) return MBQC_OK;
+    if (desc->n_groups & 31) return fail(MBQC_E_ARG, "lane pass: element count must be a multiple of 32");
+    stream_lane_kernel<<<stream_grid(desc->n_groups, 256), 256, 0, (cudaStream_t)stream>>>((double2*)d_state, *desc);
+    return after_launch("stream_lane_kernel");
+}
+
 int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const mbqc_stream_seed* seed,
                              void* stream) {
     if (!seed || !desc) return fail(MBQC_E_ARG, "seed/desc is NULL");

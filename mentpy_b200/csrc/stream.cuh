@@ -130,6 +130,50 @@ __global__ void __launch_bounds__(256) stream_steps_kernel(double2* __restrict__
     }
 }
 
+// Low-slot variant: every fused slot is one of the 5 lane bits of the index (slot < 5).  The
+// register-group kernel above would make each thread walk 2^K neighbouring elements (lanes 2^K * 16
+// bytes apart: uncoalesced); here a thread owns ONE element, a warp one contiguous 512-byte span,
+// and the pair partner is fetched with __shfl_xor -- the in-warp form of the "high strides through
+// shared memory" staging.  Descriptor convention: ranges squeeze out dead slots only (all >= 5),
+// n_groups = number of live local elements (a multiple of 32).
+__global__ void __launch_bounds__(256) stream_lane_kernel(double2* __restrict__ state,
+                                                          const __grid_constant__ mbqc_stream_desc d) {
+    const int K = d.n_fused;
+    uint32_t dead_mask = 0;
+    for (int j = 0; j < K; ++j)
+        if (!((d.append_mask >> j) & 1u)) dead_mask |= (uint32_t)d.elem_bit[j];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < d.n_groups; t += stride) {
+        uint64_t i = t;
+        for (int r = 0; r < d.n_ranges; ++r) i = insert_zero_field(i, d.range_pos[r], d.range_width[r]);
+        double2 v = state[i];
+        v.x *= d.scale;
+        v.y *= d.scale;
+        const uint64_t gfull = i | d.index_or;
+#pragma unroll
+        for (int j = 0; j < MBQC_STREAM_MAX_FUSE; ++j) {
+            if (j < K) {
+                const uint32_t bit = (uint32_t)d.elem_bit[j];
+                const double px = __shfl_xor_sync(0xffffffffu, v.x, (int)bit);
+                const double py = __shfl_xor_sync(0xffffffffu, v.y, (int)bit);
+                const bool hi = ((uint32_t)i & bit) != 0;
+                const double a0x = hi ? px : v.x, a0y = hi ? py : v.y;  // bit-0 partner
+                const double a1x = hi ? v.x : px, a1y = hi ? v.y : py;  // bit-1 partner
+                const double c = d.cos_t[j], s = d.sin_t[j];
+                double tr = fma(c, a1x, fma(s, a1y, a0x));
+                double ti = fma(c, a1y, fma(-s, a1x, a0y));
+                if (hi && (((uint32_t)__popcll(gfull & d.nbr_mask[j]) & 1u) != 0)) {
+                    tr = -tr;
+                    ti = -ti;
+                }
+                v.x = tr;
+                v.y = ti;
+            }
+        }
+        if (((uint32_t)i & dead_mask) == 0) state[i] = v;
+    }
+}
+
 // Measurement of a SHARD slot (the pair partner lives on another GPU), fused with the transfer:
 // the kernel reads the partner's half straight from peer memory over NVLink and leaves both
 // results local, which moves the appended qubit into the top LOCAL slot and the qubit that

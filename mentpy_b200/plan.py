@@ -80,10 +80,13 @@ def _fixed_cos_sin(plane: str, angle):
 
 
 def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = None,
-          mixed: bool = False, slot_order: str = "msb") -> LoweredPlan:
+          mixed: bool = False, slot_order: str = "msb", shard_bits: int = 0) -> LoweredPlan:
     """slot_order: "msb" puts window position p at slot w-1-p (reference layout; the measured slots
     then cycle w-1, w-2, ..., 0 and the register kernel takes its unrolled path); "lsb" puts it at
-    slot p (exercises the kernels' generic slot path; results are identical)."""
+    slot p (exercises the kernels' generic slot path; results are identical); "shard-last" (with
+    shard_bits = g) is "msb" inside the w-g local slots and keeps the g window positions measured
+    LAST in the shard slots, so the first w-g measurements of a sharded run are local AND hit high,
+    coalesced slots first."""
     nodes = list(circuit.graph.nodes())
     n_nodes = len(nodes)
     outputs_excluded = circuit.quantum_output_nodes if mixed else circuit.output_nodes
@@ -140,9 +143,18 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
 
     w = window_size
     first_window = schedule[:w]
-    if slot_order not in ("msb", "lsb"):
-        raise ValueError("slot_order must be 'msb' or 'lsb'")
-    slot_of: Dict[int, int] = {v: (w - 1 - p if slot_order == "msb" else p) for p, v in enumerate(first_window)}
+    if slot_order not in ("msb", "lsb", "shard-last"):
+        raise ValueError("slot_order must be 'msb', 'lsb' or 'shard-last'")
+    n_local = w - max(int(shard_bits), 0)
+
+    def first_slot(p: int) -> int:
+        if slot_order == "msb":
+            return w - 1 - p
+        if slot_order == "lsb":
+            return p
+        return n_local - 1 - p if p < n_local else p
+
+    slot_of: Dict[int, int] = {v: first_slot(p) for p, v in enumerate(first_window)}
     init_cz = [0] * w
     for a, b in circuit.graph.edges():
         if a in slot_of and b in slot_of and a != b:

@@ -23,6 +23,7 @@ from .plan import LoweredPlan
 
 MAX_FUSE = 5
 MAX_RANGES = 16
+LANE_BITS = 5   # index bits that map to lanes of a warp
 
 
 @dataclass
@@ -39,6 +40,8 @@ class LocalPass:
     scale: float
     steps: List[int]                # plan step indices (bookkeeping)
     live_bits: int = 0              # live local bits before the pass (traffic accounting)
+    dead_bits: List[int] = field(default_factory=list)   # dead local slots before the pass
+    lane: bool = False              # all fused slots < 5, no dead slot < 5: warp-shuffle kernel
 
 
 @dataclass
@@ -160,6 +163,8 @@ def build_schedule(plan: LoweredPlan, angles, shard_bits: int = 0, fuse: int = 4
             pj = phys[steps[j].slot]
             if pj >= L or pj in [g[1] for g in grp]:
                 break
+            if grp and (pj < LANE_BITS) != (grp[0][1] < LANE_BITS):
+                break                 # lane-bit slots and register slots go to different kernels
             grp.append((j, pj))   # distinct slots <=> all measured qubits were live at pass start
             j += 1
         slots = [p for _, p in grp]
@@ -193,8 +198,11 @@ def build_schedule(plan: LoweredPlan, angles, shard_bits: int = 0, fuse: int = 4
         # reads 2^live_local, writes the survivors
         n_written = (1 << (live_local_before - (len(slots) - n_app)))
         streamed += active_ranks * 16 * ((1 << live_local_before) + n_written)
+        lane = (all(p < LANE_BITS for p in slots) and all(dd >= LANE_BITS for dd in dead_local)
+                and live_local_before >= LANE_BITS + 2 and L - 1 >= LANE_BITS)
         passes.append(LocalPass(slots, cos_l, sin_l, nbr_l, loc_l, amask, rng, n_groups,
-                                scale_for(n_app), [sj for sj, _ in grp], live_local_before))
+                                scale_for(n_app), [sj for sj, _ in grp], live_local_before,
+                                sorted(dead_local), lane))
         for sj, pj in grp:
             if not steps[sj].append:
                 dead.add(pj)
@@ -415,6 +423,8 @@ class CudaStreamEngine:
             else:
                 self._lib.check(self.lib.mbqc_stream_steps(C.c_void_p(buf), C.byref(desc), C.c_void_p(self._stream())))
 
+        if p.lane and not seeded:
+            return self._lane_pass(p, index_or)
         d = self._lib.StreamDesc()
         top = self.L - 1
         hi = self._hi_offset()
@@ -449,6 +459,37 @@ class CudaStreamEngine:
                 for h in (0, 1):
                     d.index_or = index_or | (h << top)
                     launch(self.bufs[r[h]], d)
+
+    def _lane_pass(self, p: LocalPass, index_or: int):
+        """Fused slots are lane bits: one element per thread, partners via warp shuffles."""
+        import ctypes as C
+
+        d = self._lib.StreamDesc()
+        top = self.L - 1
+        d.n_fused = len(p.slots)
+        for k, sl in enumerate(p.slots):
+            d.elem_bit[k] = 1 << sl
+            d.elem_offset[k] = 1 << sl
+            d.cos_t[k], d.sin_t[k] = p.cos_t[k], p.sin_t[k]
+            d.nbr_mask[k], d.local_mask[k] = p.nbr_masks[k], p.local_masks[k]
+        d.append_mask = p.append_mask
+        d.scale = p.scale
+        rng = _ranges(p.dead_bits)
+        d.n_ranges = len(rng)
+        for q, (pos, wd) in enumerate(rng):
+            d.range_pos[q], d.range_width[q] = pos, wd
+        top_dead = top in p.dead_bits
+        n_elems = 1 << (self.L - len(p.dead_bits))
+        r = self.roles[self.rank]
+        with self.torch.cuda.device(self.device):
+            if top_dead:
+                d.n_groups, d.index_or = n_elems, index_or
+                self._lib.check(self.lib.mbqc_stream_steps_lanes(C.c_void_p(self.bufs[r[0]]), C.byref(d), C.c_void_p(self._stream())))
+            else:
+                d.n_groups = n_elems >> 1
+                for h in (0, 1):
+                    d.index_or = index_or | (h << top)
+                    self._lib.check(self.lib.mbqc_stream_steps_lanes(C.c_void_p(self.bufs[r[h]]), C.byref(d), C.c_void_p(self._stream())))
 
     def exchange(self, p: ExchangePass, role: int, partner: int, const_parity: int):
         import ctypes as C
@@ -529,15 +570,17 @@ class CudaSimulatorSVStream:
         self.force0 = kwargs.pop("force0", True)
         if not self.force0:
             raise NotImplementedError("Numpy simulator does not support force0=False.")
-        # Sharded runs put the window position measured LAST into the highest (shard) slots: a
-        # shard slot costs an NVLink exchange every time it is measured, so the first w - g
-        # measurements are all local and, for patterns not much longer than the window, shard
-        # slots are only reached in the tail when the live state is already tiny.
+        # Sharded runs keep the window positions measured LAST in the shard slots: a shard slot costs
+        # an NVLink exchange every time it is measured, so the first w - g measurements are all
+        # local (and start on the high, coalesced local slots); for patterns not much longer than
+        # the window, shard slots are only reached in the tail when the live state is already tiny.
+        world = self._dist()[1]
         slot_order = kwargs.pop("slot_order", None)
         if slot_order is None:
-            slot_order = "lsb" if self._dist()[1] > 1 else "msb"
+            slot_order = "shard-last" if world > 1 else "msb"
         self.slot_order = slot_order
-        self.plan = lower(mbqcircuit, self.window_size, self.schedule, mixed=False, slot_order=slot_order)
+        self.plan = lower(mbqcircuit, self.window_size, self.schedule, mixed=False, slot_order=slot_order,
+                          shard_bits=max(world.bit_length() - 1, 0))
         self.window_size = self.plan.window
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure

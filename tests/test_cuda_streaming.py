@@ -72,3 +72,20 @@ def test_sharded_stream_under_torchrun():
            os.path.join(ROOT, "tests", "multi_gpu_stream_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert "STREAM_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("fuse", [1, 3, 5])
+def test_stream_long_pattern_hits_lane_slots_at_full_size(fuse):
+    """Pattern several windows long: the low (lane-bit) slots are measured while the window is
+    still full, which takes the warp-shuffle kernel (stream_lane_kernel)."""
+    from mentpy_b200.streaming import LocalPass
+
+    for name, args, w in (("linear_cluster", [60], 14), ("grid_cluster", [3, 12], 11)):
+        gs = getattr(mb.templates, name)(*args)
+        ang = np.random.default_rng(21).uniform(0, 2 * np.pi, len(gs.trainable_nodes))
+        ps = mb.PatternSimulator(gs, backend="cuda-sv-stream", window_size=w, fuse=fuse)
+        got = ps.run(ang, output_form="sv")
+        want = matrix_free.run_sv_batch(PatternData.from_circuit(gs), ang, window_size=w)[0]
+        assert infidelity_pure(got, want) < 1e-10
+        assert np.allclose(got, want, atol=1e-9)
+        assert any(isinstance(p, LocalPass) and p.lane for p in ps.simulator.last_schedule.passes)

@@ -42,13 +42,13 @@ def test_schedule_accounting_and_fusion():
     ang = np.zeros(plan.n_angles)
     s1 = build_schedule(plan, ang, 0, fuse=1)
     s4 = build_schedule(plan, ang, 0, fuse=4)
-    assert len(s1.passes) == len(plan.steps) and len(s4.passes) < len(s1.passes) / 3
+    assert len(s1.passes) == len(plan.steps) and len(s4.passes) < len(s1.passes) / 2
     assert s1.algorithmic_bytes == s4.algorithmic_bytes
     # 2*16*2^n per measurement at live window n: 16 full steps + halving tail
     full = 2 * 16 * 2**10
     # 25 measurements: 16 with an append at live window 10, then the tail reads 2^10, 2^9, ..., 2^2
     assert s1.algorithmic_bytes == 16 * full + sum(2 * 16 * 2**n for n in range(10, 1, -1))
-    assert s4.streamed_bytes < 0.4 * s1.streamed_bytes
+    assert s4.streamed_bytes < 0.5 * s1.streamed_bytes
     assert all(isinstance(p, LocalPass) for p in s4.passes)
     s2 = build_schedule(plan, ang, shard_bits=2, fuse=4)
     assert any(isinstance(p, ExchangePass) for p in s2.passes)
@@ -82,7 +82,7 @@ def _gloo_worker(rank, world, port, spec, w, fuse, seed, q, order="msb"):
     try:
         name, args = spec
         gs = getattr(mb.templates, name)(*args)
-        plan = lower(gs, window_size=w, slot_order=order)
+        plan = lower(gs, window_size=w, slot_order=order, shard_bits=world.bit_length() - 1)
         ang = np.random.default_rng(seed).uniform(0, 2 * np.pi, plan.n_angles)
         g = world.bit_length() - 1
         out = StreamExecutor(plan, Eng(dist), rank, g, fuse).run(ang)
@@ -96,7 +96,9 @@ def _gloo_worker(rank, world, port, spec, w, fuse, seed, q, order="msb"):
                                                      (2, ("grid_cluster", [3, 6]), 7, 4, "lsb"),
                                                      (4, ("linear_cluster", [16]), 7, 2, "lsb"),
                                                      (4, ("grid_cluster", [2, 8]), 6, 5, "msb"),
-                                                     (2, ("linear_cluster", [40]), 8, 5, "lsb")])
+                                                     (2, ("linear_cluster", [40]), 8, 5, "lsb"),
+                                                     (4, ("linear_cluster", [24]), 9, 5, "shard-last"),
+                                                     (2, ("grid_cluster", [3, 7]), 8, 4, "shard-last")])
 def test_sharded_schedule_gloo(world, spec, w, fuse, order):
     import torch.multiprocessing as mp
 
