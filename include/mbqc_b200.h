@@ -187,10 +187,12 @@ int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const 
                              void* stream);
 /* Measurement of a shard slot fused with the NVLink transfer: d_peer is the partner GPU's half
  * (peer-mapped memory), read directly by the kernel.  role 0/1: this rank's shard bit; role 2:
- * tail step without append (whole shard, survivor side).  See csrc/stream.cuh. */
+ * tail step without append (survivor side).  n = live elements of the half; dead slots are squeezed
+ * out of the loop index with the zero-field ranges (as in mbqc_stream_desc).  See csrc/stream.cuh. */
 int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t role, double cos_t,
                          double sin_t, double scale, uint64_t nbr_mask, int32_t const_parity,
-                         uint64_t n, void* stream);
+                         uint64_t n, int32_t n_ranges, const uint32_t* range_pos,
+                         const uint32_t* range_width, void* stream);
 /* Collect the output amplitudes this rank owns into d_out [2^k] (others untouched; np_simulator_sv.py:286-297). */
 int mbqc_stream_gather(const void* d_state, int32_t local_bits, uint64_t index_or,
                        int32_t n_outputs, const int32_t* output_slot, void* d_out, void* stream);

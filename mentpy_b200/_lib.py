@@ -69,7 +69,8 @@ _SIGNATURES = {
     "mbqc_stream_steps_lanes": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_void_p]),
     "mbqc_stream_steps_seeded": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.POINTER(StreamSeed), C.c_void_p]),
     "mbqc_stream_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double,
-                                       C.c_double, C.c_uint64, C.c_int32, C.c_uint64, C.c_void_p]),
+                                       C.c_double, C.c_uint64, C.c_int32, C.c_uint64, C.c_int32,
+                                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p]),
     "mbqc_stream_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.POINTER(C.c_int32),
                                      C.c_void_p, C.c_void_p]),
     "mbqc_device_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),

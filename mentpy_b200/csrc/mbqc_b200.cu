@@ -654,7 +654,10 @@ int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const 
 
 int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t role, double cos_t,
                          double sin_t, double scale, uint64_t nbr_mask, int32_t const_parity,
-                         uint64_t n, void* stream) {
+                         uint64_t n, int32_t n_ranges, const uint32_t* range_pos,
+                         const uint32_t* range_width, void* stream) {
+    if (n_ranges < 0 || n_ranges > MBQC_STREAM_MAX_RANGES || (n_ranges && (!range_pos || !range_width)))
+        return fail(MBQC_E_ARG, "bad dead-slot ranges");
     if (!d_own || !d_peer || (role != 2 && !d_spare)) return fail(MBQC_E_ARG, "NULL buffer");
     if (role < 0 || role > 2) return fail(MBQC_E_ARG, "role %d unknown", role);
     if (n == 0) return MBQC_OK;
@@ -669,6 +672,11 @@ int mbqc_stream_exchange(void* d_own, const void* d_peer, void* d_spare, int32_t
     p.nbr_mask = nbr_mask;
     p.const_parity = (uint32_t)(const_parity & 1);
     p.n = n;
+    p.n_ranges = n_ranges;
+    for (int r = 0; r < n_ranges; ++r) {
+        p.range_pos[r] = range_pos[r];
+        p.range_width[r] = range_width[r];
+    }
     stream_exchange_kernel<<<stream_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
     return after_launch("stream_exchange_kernel");
 }

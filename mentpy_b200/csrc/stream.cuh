@@ -192,12 +192,17 @@ struct ExchangeParams {
     double c, s, scale;
     uint64_t nbr_mask;  // over the bits of i
     uint32_t const_parity;
-    uint64_t n;
+    uint64_t n;         // live elements of the half (dead slots squeezed out of the loop index)
+    int32_t n_ranges;
+    uint32_t range_pos[MBQC_STREAM_MAX_RANGES];
+    uint32_t range_width[MBQC_STREAM_MAX_RANGES];
 };
 
 __global__ void __launch_bounds__(256) stream_exchange_kernel(const __grid_constant__ ExchangeParams p) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.n; e += stride) {
+        uint64_t i = e;
+        for (int r = 0; r < p.n_ranges; ++r) i = insert_zero_field(i, p.range_pos[r], p.range_width[r]);
         const double2 mine = p.own[i];
         const double2 theirs = p.peer[i];  // NVLink peer load
         const double2 a0 = (p.role == 1) ? theirs : mine;  // bit-0 partner

@@ -56,6 +56,7 @@ class ExchangePass:
     top_is_neighbour: bool          # neighbour mask contains the top local slot
     scale: float
     step: int
+    dead_bits: List[int] = field(default_factory=list)   # dead local slots before the pass
 
 
 @dataclass
@@ -140,7 +141,8 @@ def build_schedule(plan: LoweredPlan, angles, shard_bits: int = 0, fuse: int = 4
             passes.append(ExchangePass(
                 shard_bit=ps - L, cos_t=c, sin_t=s, append=st.append,
                 half_mask=pm & ((1 << top) - 1), rank_mask=pm >> L,
-                top_is_neighbour=bool((pm >> top) & 1), scale=scale_for(1 if st.append else 0), step=i))
+                top_is_neighbour=bool((pm >> top) & 1), scale=scale_for(1 if st.append else 0), step=i,
+                dead_bits=sorted(d for d in dead if d < L)))
             live_local = L - len([d for d in dead if d < L])
             active = 1 << (shard_bits - len([d for d in dead if d >= L]))
             if st.append:
@@ -232,15 +234,30 @@ class StreamExecutor:
         # when the pattern starts with a local pass, the engine may generate the seed inside that
         # pass instead of writing it out first (one write + one read of the whole state saved)
         first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass) and input_state is None
+        import os
+        import time
+
+        prof = os.environ.get("MBQC_STREAM_PROFILE") == "1"
+        self.timeline = []
+
+        def mark(label, t0):
+            if prof:
+                eng.barrier()
+                self.timeline.append((label, (time.perf_counter() - t0) * 1e3))
+
+        t0 = time.perf_counter()
         eng.init(self.plan, L, rank, input_state, defer=first_local)
+        mark("init", t0)
         if first_local:  # the first pass generates its input: no read of the state in that pass
             p0 = sched.passes[0]
             sched.streamed_bytes -= (1 << self.shard_bits) * 16 * (1 << p0.live_bits)
         alive = True
         for n_pass, p in enumerate(sched.passes):
+            t0 = time.perf_counter()
             if isinstance(p, LocalPass):
                 if alive:
                     eng.local_pass(p, rank << L, seeded=(n_pass == 0 and first_local))
+                mark(f"local K={len(p.slots)} slots={p.slots} live={p.live_bits} lane={p.lane}", t0)
                 continue
             v = (rank >> p.shard_bit) & 1
             partner = rank ^ (1 << p.shard_bit)
@@ -260,8 +277,11 @@ class StreamExecutor:
                 if v == 1:
                     alive = False             # this rank's share died with the slot
             eng.barrier()
+            mark(f"exchange append={p.append}", t0)
+        t0 = time.perf_counter()
         vec = eng.gather(sched.output_slots, L, rank, alive)
         vec = eng.allreduce(vec)
+        mark("gather+allreduce", t0)
         nrm = np.linalg.norm(vec)
         if not np.isfinite(nrm) or nrm == 0.0:
             raise ValueError("qstate has nan, you might want to increase the window size")
@@ -495,21 +515,26 @@ class CudaStreamEngine:
         import ctypes as C
 
         mine, theirs = self.roles[self.rank], self.roles[partner]
-        n = self.half_elems
+        top = self.L - 1
+        dead_half = [d for d in p.dead_bits if d < top]          # dead slots inside the half index
+        rng = _ranges(dead_half)
+        pos = (C.c_uint32 * max(len(rng), 1))(*[r[0] for r in rng])
+        wid = (C.c_uint32 * max(len(rng), 1))(*[r[1] for r in rng])
+        n = 1 << (top - len(dead_half))                          # live elements per half
         with self.torch.cuda.device(self.device):
             st = C.c_void_p(self._stream())
             if role == 2:
-                for h in (0, 1):
+                for h in ((0,) if top in p.dead_bits else (0, 1)):
                     self._lib.check(self.lib.mbqc_stream_exchange(
                         C.c_void_p(self.bufs[mine[h]]), C.c_void_p(self.peer_ptrs[partner][theirs[h]]), None, 2,
-                        p.cos_t, p.sin_t, p.scale, 0, 0, n, st))
+                        p.cos_t, p.sin_t, p.scale, 0, 0, n, len(rng), pos, wid, st))
                 return
             own = self.bufs[mine[role]]
             peer = self.peer_ptrs[partner][theirs[role]]
             spare = self.bufs[mine[2]]
             self._lib.check(self.lib.mbqc_stream_exchange(
                 C.c_void_p(own), C.c_void_p(peer), C.c_void_p(spare), role, p.cos_t, p.sin_t, p.scale,
-                p.half_mask, const_parity, n, st))
+                p.half_mask, const_parity, n, len(rng), pos, wid, st))
 
     def rotate_roles(self, shard_bit: int):
         """After an append exchange on `shard_bit`: ranks with 0 there adopted the spare as H1,
