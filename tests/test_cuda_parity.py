@@ -402,3 +402,53 @@ def test_full_size_properties_c3_c4():
         fp = 1 - np.abs(ps.run_batch(X[idx] + e) @ tgt) ** 2
         fm = 1 - np.abs(ps.run_batch(X[idx] - e) @ tgt) ** 2
         assert np.allclose(g[idx, i], (fp - fm) / 3.0, atol=1e-11)
+
+
+def test_edge_cases_sizes_and_shapes():
+    """Smallest / largest windows of every batched kernel, patterns without trainable angles,
+    batch sizes around CTA boundaries."""
+    rng = np.random.default_rng(31)
+    # window 1..2 (register kernel W=1,2), including the all-fixed-angle pattern (T = 0)
+    gs = mb.templates.linear_cluster(4)
+    for v in (0, 1, 2):
+        gs[v] = mb.Ment("X") if v != 1 else mb.Ment(0.9, "XY")
+    assert gs.trainable_nodes == []
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    got = ps.run_batch(np.zeros((5, 0)))
+    want = matrix_free.run_sv_batch(PatternData.from_circuit(gs), np.zeros((5, 0)))
+    assert np.allclose(got, want, atol=1e-12)
+    assert np.allclose(ps.run([]), np.outer(want[0], want[0].conj()), atol=1e-12)
+    pd = mb.PatternSimulator(gs, backend="cuda-dm")
+    assert np.allclose(pd.run([]), np.outer(want[0], want[0].conj()), atol=1e-12)
+    # batch sizes straddling the 128-thread CTA
+    gs = mb.templates.grid_cluster(2, 5)
+    pat = PatternData.from_circuit(gs)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    for B in (1, 127, 128, 129, 255, 257):
+        ang = rng.uniform(0, 2 * np.pi, (B, 8))
+        assert np.allclose(ps.run_batch(torch.from_numpy(ang).cuda()).cpu().numpy(),
+                           matrix_free.run_sv_batch(pat, ang), atol=1e-10)
+    # strided (non-contiguous rows) device input
+    big = torch.from_numpy(rng.uniform(0, 2 * np.pi, (64, 16))).cuda()
+    view = big[:, :8]
+    assert np.allclose(ps.run_batch(view).cpu().numpy(), matrix_free.run_sv_batch(pat, view.cpu().numpy()), atol=1e-10)
+    # largest shared-memory windows: SV w = 12, DM w = 6
+    gs = mb.templates.linear_cluster(18)
+    ang = rng.uniform(0, 2 * np.pi, (3, 17))
+    got = mb.PatternSimulator(gs, backend="cuda-sv", window_size=12).run_batch(ang)
+    assert np.max(np.abs(1 - np.abs(np.sum(got.conj() * matrix_free.linear_cluster_analytic(ang), axis=1)) ** 2)) < 1e-10
+    gs = mb.templates.grid_cluster(2, 6)
+    ang = rng.uniform(0, 2 * np.pi, (3, 10))
+    got = mb.PatternSimulator(gs, backend="cuda-dm", window_size=6).run_batch(ang)
+    assert dm_distance(got, matrix_free.run_dm_batch(PatternData.from_circuit(gs), ang, window_size=6)) < 1e-10
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(gs, backend="cuda-dm", window_size=7).run_batch(ang)
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(mb.templates.linear_cluster(20), backend="cuda-sv", window_size=13).run_batch(np.zeros((1, 19)))
+    # wrong shapes
+    with pytest.raises(ValueError):
+        ps.run_batch(np.zeros((4, 7)))
+    with pytest.raises(ValueError):
+        ps.run_batch(np.zeros((4, 8)), input_states=np.zeros((3, 4)))
+    with pytest.raises(ValueError):
+        mb.PatternSimulator(mb.templates.grid_cluster(2, 5), input_state=np.ones(3), backend="cuda-sv").run(np.zeros(8))
