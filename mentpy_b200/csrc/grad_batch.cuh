@@ -17,7 +17,7 @@ __device__ __forceinline__ double sv_reg_cost(const SvBatchParams& p, const RegS
                                               int64_t b, const AngleSrc& ang) {
     constexpr int N = 1 << W;
     double re[N], im[N], zr, zi;
-    const double n2 = sv_reg_evolve<W>(p, sm, periodic, b, ang, re, im, zr, zi);
+    const double n2 = sv_reg_evolve<W, true, true>(p, sm, periodic, b, ang, re, im, zr, zi);
     double ar = 0.0, ai = 0.0;  // <t|psi>
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
     const bool live = bl < samples;
     if (live) {  // one angle per thread: a single round of loads for the whole CTA
         double sn, cs;
-        sincos_cw(__ldg(p.angles + (b0 + bl) * p.stride + i), sn, cs);
+        sincos_cw(__ldg(p.angles + (b0 + bl) * p.stride + i), sn, cs);  // one angle per thread: no table needed
         l.cs[threadIdx.x] = make_double2(cs, sn);
     }
     cp_async_wait_all();

@@ -50,19 +50,26 @@ struct AngleStaged {
     const double2* fixed;
     int shift_col;
     double cs, ss;
+    // FIXED: the plan has fixed-angle steps; SHIFT: one column carries a parameter shift.  Plain
+    // runs of all-trainable patterns compile both checks away.
+    template <bool FIXED, bool SHIFT>
     __device__ __forceinline__ void get(uint32_t col, double& c, double& s) const {
-        if ((int)col >= n_angles) {
-            const double2 f = fixed[col - n_angles];
-            c = f.x;
-            s = f.y;
-            return;
+        if constexpr (FIXED) {
+            if ((int)col >= n_angles) {
+                const double2 f = fixed[col - n_angles];
+                c = f.x;
+                s = f.y;
+                return;
+            }
         }
         const double2 v = col0[col * pitch];
         c = v.x;
         s = v.y;
-        if ((int)col == shift_col) {
-            c = v.x * cs - v.y * ss;
-            s = v.y * cs + v.x * ss;
+        if constexpr (SHIFT) {
+            if ((int)col == shift_col) {
+                c = v.x * cs - v.y * ss;
+                s = v.y * cs + v.x * ss;
+            }
         }
     }
 };
@@ -72,6 +79,7 @@ struct AngleGlobal {
     const double2* fixed;
     int shift_col;
     double shift;
+    template <bool FIXED, bool SHIFT>
     __device__ __forceinline__ void get(uint32_t col, double& c, double& s) const {
         if ((int)col >= n_angles) {
             const double2 f = fixed[col - n_angles];
@@ -162,7 +170,7 @@ struct RegSmem {
 
 // Evolve one sample through the whole pattern.  Returns the squared norm over the output entries;
 // (zr, zi) accumulates the unnormalised reference phase prod_j (1 + e^{i theta_j}).
-template <int W, class AngleSrc>
+template <int W, bool FIXED, bool SHIFT, class AngleSrc>
 __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const RegSmem& sm, bool periodic,
                                                 int64_t b, const AngleSrc& ang, double (&re)[1 << W],
                                                 double (&im)[1 << W], double& zr, double& zi) {
@@ -201,7 +209,7 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const Re
                 const int m = m0 + u;
                 if (m < M) {
                     double c, s;
-                    ang.get(sm.cols[m] & 0xffffu, c, s);
+                    ang.template get<FIXED, SHIFT>(sm.cols[m] & 0xffffu, c, s);
                     phase(c, s);
                     reg_stage<W, W - 1 - u>(re, im, c, s, sm.signs + m * sm.sign_pitch);
                 }
@@ -212,7 +220,7 @@ __device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const Re
         for (int m = 0; m < M; ++m) {
             const uint32_t cw = sm.cols[m];
             double c, s;
-            ang.get(cw & 0xffffu, c, s);
+            ang.template get<FIXED, SHIFT>(cw & 0xffffu, c, s);
             phase(c, s);
             reg_step_any<W>(re, im, (int)(cw >> 16), c, s, sm.signs + m * sm.sign_pitch);
             if ((m & 15) == 15) reg_renorm<W>(re, im, zr, zi);
@@ -250,10 +258,11 @@ struct RegSmemLayout {
     uint32_t* signs;   // [M][SP]
     uint32_t* cols;    // [M] padded to 4
     double2* fixed;    // [n_fixed]
+    double2* trig;     // [64] copy of kTrigTable for the per-lane gather in sincos_tab
     double2* cs;       // [T][pitch] (cos, sin), column-major   (staged only)
 };
 __host__ __device__ __forceinline__ size_t reg_smem_tables_bytes(int M, int sp, int n_fixed) {
-    return (size_t)M * sp * 4 + (size_t)((M + 3) & ~3) * 4 + (size_t)n_fixed * 16;
+    return (size_t)M * sp * 4 + (size_t)((M + 3) & ~3) * 4 + (size_t)n_fixed * 16 + (size_t)MBQC_TRIG_N * 16;
 }
 __device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int sp, int n_fixed) {
     RegSmemLayout l;
@@ -264,6 +273,8 @@ __device__ __forceinline__ RegSmemLayout reg_smem_carve(void* base, int M, int s
     p += (size_t)((M + 3) & ~3) * 4;
     l.fixed = reinterpret_cast<double2*>(p);
     p += (size_t)n_fixed * 16;
+    l.trig = reinterpret_cast<double2*>(p);
+    p += (size_t)MBQC_TRIG_N * 16;
     l.cs = reinterpret_cast<double2*>(p);
     return l;
 }
@@ -278,6 +289,7 @@ __device__ __forceinline__ void stage_reg_tables(const SvRegParams& p, const Reg
     for (int i = threadIdx.x; i < ncol; i += kRegThreads)
         cp_async16(reinterpret_cast<uint4*>(l.cols) + i, reinterpret_cast<const uint4*>(p.reg.cols) + i);
     for (int i = threadIdx.x; i < p.reg.n_fixed; i += kRegThreads) cp_async16(l.fixed + i, p.reg.fixed + i);
+    if (threadIdx.x < MBQC_TRIG_N) cp_async16(l.trig + threadIdx.x, kTrigTable + threadIdx.x);
 }
 
 // Thread `row` fetches its own angle row straight into the low halves of its (cos, sin) slots:
@@ -291,11 +303,11 @@ __device__ __forceinline__ void fetch_own_row(const double* __restrict__ grow, d
 
 // ... and converts them in place to (cos, sin): independent evaluations, no barrier needed since
 // every slot is written and read by the same thread.
-__device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pitch) {
+__device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pitch, const double2* trig) {
 #pragma unroll 2
     for (int j = 0; j < T; ++j) {
         double sn, c;
-        sincos_cw(cs_col0[j * pitch].x, sn, c);
+        sincos_tab(cs_col0[j * pitch].x, sn, c, trig);
         cs_col0[j * pitch] = make_double2(c, sn);
     }
 }
@@ -325,12 +337,15 @@ __global__ void __launch_bounds__(128, (W <= 3 ? MBQC_REG_MINBLOCKS_W3 : (W == 4
     double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
     if (live) {
         if (staged & 1) {
-            convert_own_row(l.cs + threadIdx.x, T, kRegThreads);
+            convert_own_row(l.cs + threadIdx.x, T, kRegThreads, l.trig);
             const AngleStaged ang{l.cs + threadIdx.x, kRegThreads, T, l.fixed, -1, 1.0, 0.0};
-            n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+            if (pp.reg.n_fixed == 0)
+                n2 = sv_reg_evolve<W, false, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+            else
+                n2 = sv_reg_evolve<W, true, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
         } else {
             const AngleGlobal ang{p.angles + b * p.stride, T, l.fixed, -1, 0.0};
-            n2 = sv_reg_evolve<W>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+            n2 = sv_reg_evolve<W, true, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
         }
     }
     // Output.  Device-resident callers get direct 16-byte stores from registers.  With
