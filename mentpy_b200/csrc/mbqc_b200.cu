@@ -252,29 +252,34 @@ static void fill_reg_params(SvRegParams& rp, const SvBatchParams& p, const mbqc_
 
 // dynamic shared memory of the register kernels: plan tables + (staged) the CTA's (cos, sin)
 // tile and raw angle tile; staging is skipped when the tile does not fit the budget
-template <bool DM>
-static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st, bool coalesced_out) {
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((p.batch + threads - 1) / threads);
+template <int W, bool DM>
+static int launch_sv_reg_w(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st, bool coalesced_out) {
+    constexpr int spt = RegKernelTraits<W>::kSPT;
+    const int threads = kRegThreads;
+    const int per_cta = threads * spt;
+    const unsigned blocks = (unsigned)((p.batch + per_cta - 1) / per_cta);
     SvRegParams rp;
     fill_reg_params(rp, p, plan);
     const size_t tables = reg_smem_tables_bytes(p.tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
-    const size_t tile = (size_t)threads * p.tab.n_angles * sizeof(double2);
+    const size_t tile = (size_t)per_cta * p.tab.n_angles * sizeof(double2);
     const int staged = (p.tab.n_angles > 0 && tables + tile <= 100 * 1024) ? 1 : 0;
     size_t smem = tables + (staged ? tile : 0);
-    const size_t stage = ((size_t)threads << p.tab.n_out) * sizeof(double2);  // output stage re-uses the buffer
-    if (stage > smem) smem = stage;
-    auto go = [&](auto kern) -> int {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<blocks, threads, smem, st>>>(rp, staged | (coalesced_out ? 2 : 0));
-        return after_launch("sv_reg_kernel");
-    };
+    const size_t stage = ((size_t)per_cta << p.tab.n_out) * sizeof(double2);  // output stage re-uses the buffer
+    if ((DM || coalesced_out) && stage > smem) smem = stage;
+    auto kern = sv_reg_kernel<W, DM>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, threads, smem, st>>>(rp, staged | ((DM || coalesced_out) ? 2 : 0));
+    return after_launch("sv_reg_kernel");
+}
+
+template <bool DM>
+static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st, bool coalesced_out) {
     switch (p.tab.window) {
-        case 1: return go(sv_reg_kernel<1, DM>);
-        case 2: return go(sv_reg_kernel<2, DM>);
-        case 3: return go(sv_reg_kernel<3, DM>);
-        case 4: return go(sv_reg_kernel<4, DM>);
-        default: return go(sv_reg_kernel<5, DM>);
+        case 1: return launch_sv_reg_w<1, DM>(p, plan, st, coalesced_out);
+        case 2: return launch_sv_reg_w<2, DM>(p, plan, st, coalesced_out);
+        case 3: return launch_sv_reg_w<3, DM>(p, plan, st, coalesced_out);
+        case 4: return launch_sv_reg_w<4, DM>(p, plan, st, coalesced_out);
+        default: return launch_sv_reg_w<5, DM>(p, plan, st, coalesced_out);
     }
 }
 

@@ -168,69 +168,100 @@ struct RegSmem {
     int sign_pitch;
 };
 
-// Evolve one sample through the whole pattern.  Returns the squared norm over the output entries;
-// (zr, zi) accumulates the unnormalised reference phase prod_j (1 + e^{i theta_j}).
-template <int W, bool FIXED, bool SHIFT, class AngleSrc>
-__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const RegSmem& sm, bool periodic,
-                                                int64_t b, const AngleSrc& ang, double (&re)[1 << W],
-                                                double (&im)[1 << W], double& zr, double& zi) {
+// Evolve SPT samples of one thread through the whole pattern, interleaved step by step so that
+// their (independent) FP64 dependency chains overlap and the per-step table reads are shared.
+// n2[s] receives the squared norm over the output entries; (zr, zi)[s] accumulates the
+// unnormalised reference phase prod_j (1 + e^{i theta_j}).
+template <int W, int SPT, bool FIXED, bool SHIFT, class AngleSrc>
+__device__ __forceinline__ void sv_reg_evolve_multi(const SvBatchParams& p, const RegSmem& sm, bool periodic,
+                                                    const int64_t (&b)[SPT], const AngleSrc (&ang)[SPT],
+                                                    double (&re)[SPT][1 << W], double (&im)[SPT][1 << W],
+                                                    double (&zr)[SPT], double (&zi)[SPT], double (&n2)[SPT]) {
     constexpr int N = 1 << W;
     const PlanTables& t = p.tab;
-    if (p.input_mode == MBQC_INPUT_PLUS) {
-        const double a = t.plus_amp;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            re[i] = flip_sign(a, (t.init_sign << (31 - i)) & 0x80000000u);
-            im[i] = 0.0;
-        }
-    } else {
-        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+    for (int q = 0; q < SPT; ++q) {
+        if (p.input_mode == MBQC_INPUT_PLUS) {
+            const double a = t.plus_amp;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double2 v = __ldg(in + t.init_src[i]);
-            const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
-            re[i] = flip_sign(v.x * t.init_scale, sb);
-            im[i] = flip_sign(v.y * t.init_scale, sb);
+            for (int i = 0; i < N; ++i) {
+                re[q][i] = flip_sign(a, (t.init_sign << (31 - i)) & 0x80000000u);
+                im[q][i] = 0.0;
+            }
+        } else {
+            const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b[q] << t.n_in) : 0);
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double2 v = __ldg(in + t.init_src[i]);
+                const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
+                re[q][i] = flip_sign(v.x * t.init_scale, sb);
+                im[q][i] = flip_sign(v.y * t.init_scale, sb);
+            }
         }
+        zr[q] = 1.0;
+        zi[q] = 0.0;
     }
-    zr = 1.0;
-    zi = 0.0;
     const int M = t.n_steps;
-    auto phase = [&](double c, double s) {  // (zr, zi) *= (1 + c, s)
-        const double pr = 1.0 + c;
-        const double nzr = fma(zr, pr, -zi * s);
-        zi = fma(zr, s, zi * pr);
-        zr = nzr;
+    auto step_all = [&](auto slot_tag, int m, uint32_t cw) {
+        const uint32_t* sg = sm.signs + m * sm.sign_pitch;
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+            double c, s;
+            ang[q].template get<FIXED, SHIFT>(cw & 0xffffu, c, s);
+            const double pr = 1.0 + c;  // (zr, zi) *= (1 + c, s)
+            const double nzr = fma(zr[q], pr, -zi[q] * s);
+            zi[q] = fma(zr[q], s, zi[q] * pr);
+            zr[q] = nzr;
+            constexpr int S = decltype(slot_tag)::value;
+            if constexpr (S >= 0) reg_stage<W, S>(re[q], im[q], c, s, sg);
+            else reg_step_any<W>(re[q], im[q], (int)(cw >> 16), c, s, sg);
+        }
     };
     if (periodic) {
         for (int m0 = 0; m0 < M; m0 += W) {
             static_for<W>([&](auto uc) {
                 constexpr int u = decltype(uc)::value;
                 const int m = m0 + u;
-                if (m < M) {
-                    double c, s;
-                    ang.template get<FIXED, SHIFT>(sm.cols[m] & 0xffffu, c, s);
-                    phase(c, s);
-                    reg_stage<W, W - 1 - u>(re, im, c, s, sm.signs + m * sm.sign_pitch);
-                }
+                if (m < M) step_all(std::integral_constant<int, W - 1 - u>{}, m, sm.cols[m]);
             });
-            if (((m0 + W) >> 4) != (m0 >> 4)) reg_renorm<W>(re, im, zr, zi);  // long patterns
+            if (((m0 + W) >> 4) != (m0 >> 4)) {  // long patterns: keep magnitudes bounded
+#pragma unroll
+                for (int q = 0; q < SPT; ++q) reg_renorm<W>(re[q], im[q], zr[q], zi[q]);
+            }
         }
     } else {
         for (int m = 0; m < M; ++m) {
-            const uint32_t cw = sm.cols[m];
-            double c, s;
-            ang.template get<FIXED, SHIFT>(cw & 0xffffu, c, s);
-            phase(c, s);
-            reg_step_any<W>(re, im, (int)(cw >> 16), c, s, sm.signs + m * sm.sign_pitch);
-            if ((m & 15) == 15) reg_renorm<W>(re, im, zr, zi);
+            step_all(std::integral_constant<int, -1>{}, m, sm.cols[m]);
+            if ((m & 15) == 15) {
+#pragma unroll
+                for (int q = 0; q < SPT; ++q) reg_renorm<W>(re[q], im[q], zr[q], zi[q]);
+            }
         }
     }
-    double n2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i)
-        if (t.out_dst[i] >= 0) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
-    return n2;
+    for (int q = 0; q < SPT; ++q) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (t.out_dst[i] >= 0) acc = fma(re[q][i], re[q][i], fma(im[q][i], im[q][i], acc));
+        n2[q] = acc;
+    }
+}
+
+// single-sample form (gradient kernel)
+template <int W, bool FIXED, bool SHIFT, class AngleSrc>
+__device__ __forceinline__ double sv_reg_evolve(const SvBatchParams& p, const RegSmem& sm, bool periodic,
+                                                int64_t b, const AngleSrc& ang, double (&re)[1 << W],
+                                                double (&im)[1 << W], double& zr, double& zi) {
+    const int64_t bb[1] = {b};
+    const AngleSrc aa[1] = {ang};
+    double (&re1)[1][1 << W] = reinterpret_cast<double (&)[1][1 << W]>(re);
+    double (&im1)[1][1 << W] = reinterpret_cast<double (&)[1][1 << W]>(im);
+    double z1[1], z2[1], n2[1];
+    sv_reg_evolve_multi<W, 1, FIXED, SHIFT>(p, sm, periodic, bb, aa, re1, im1, z1, z2, n2);
+    zr = z1[0];
+    zi = z2[0];
+    return n2[0];
 }
 
 // ---- shared-memory staging ---------------------------------------------------------------------
@@ -248,8 +279,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-#ifndef MBQC_REG_MINBLOCKS_W3
-#define MBQC_REG_MINBLOCKS_W3 8
+#ifndef MBQC_REG_SPT_SMALL
+#define MBQC_REG_SPT_SMALL 2  // samples per thread for windows <= 3
 #endif
 constexpr int kRegThreads = 128;  // CTA size of the register kernels
 
@@ -303,49 +334,93 @@ __device__ __forceinline__ void fetch_own_row(const double* __restrict__ grow, d
 
 // ... and converts them in place to (cos, sin): independent evaluations, no barrier needed since
 // every slot is written and read by the same thread.
+#ifndef MBQC_SINCOS_TAB
+#define MBQC_SINCOS_TAB 0
+#endif
+#ifndef MBQC_CONVERT_UNROLL
+#define MBQC_CONVERT_UNROLL 2
+#endif
+#define MBQC_DO_PRAGMA(x) _Pragma(#x)
+#define MBQC_UNROLL(n) MBQC_DO_PRAGMA(unroll n)
 __device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pitch, const double2* trig) {
-#pragma unroll 2
+    MBQC_UNROLL(MBQC_CONVERT_UNROLL)
     for (int j = 0; j < T; ++j) {
         double sn, c;
+#if MBQC_SINCOS_TAB
         sincos_tab(cs_col0[j * pitch].x, sn, c, trig);
+#else
+        sincos_cw(cs_col0[j * pitch].x, sn, c);
+#endif
         cs_col0[j * pitch] = make_double2(c, sn);
     }
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
 // DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
-// (np_simulator_sv.py:292-293, the reference's default output form); the CTA stages its
-// normalised amplitudes in shared memory and writes the outer products fully coalesced.
+// (np_simulator_sv.py:292-293, the reference's default output form).
+// SPT = samples per thread: the CTA covers 128 * SPT samples, thread t owns samples
+// b0 + t + q * 128 (so the (cos, sin) column reads stay conflict-free).  SPT = 2 for small windows:
+// two independent dependency chains per thread keep the FP64 pipe busier than extra warps could
+// (the kernel is latency-, not issue-bound: profiles/README.md).
 // `staged`: bit 0 = angle tile staged in shared memory, bit 1 = CTA-coalesced output stage.
+template <int W>
+struct RegKernelTraits {
+    static constexpr int kSPT = (W <= 3) ? MBQC_REG_SPT_SMALL : 1;
+    static constexpr int kMinBlocks = (W <= 3) ? (kSPT == 1 ? 8 : 4) : (W == 4 ? 5 : 3);
+};
+
 template <int W, bool DM>
-__global__ void __launch_bounds__(128, (W <= 3 ? MBQC_REG_MINBLOCKS_W3 : (W == 4 ? 5 : 3))) sv_reg_kernel(const __grid_constant__ SvRegParams pp, int staged) {
+__global__ void __launch_bounds__(128, RegKernelTraits<W>::kMinBlocks)
+sv_reg_kernel(const __grid_constant__ SvRegParams pp, int staged) {
     constexpr int N = 1 << W;
+    constexpr int SPT = RegKernelTraits<W>::kSPT;
+    constexpr int kPitch = kRegThreads * SPT;
     extern __shared__ double2 dyn[];
     const SvBatchParams& p = pp.base;
     const int T = p.tab.n_angles, M = p.tab.n_steps;
     const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed);
-    const int64_t b0 = (int64_t)blockIdx.x * kRegThreads;
-    const int64_t b = b0 + threadIdx.x;
-    const bool live = b < p.batch;
+    const int64_t b0 = (int64_t)blockIdx.x * kPitch;
     const int k = p.tab.n_out;
-    const int samples = (int)min((int64_t)kRegThreads, p.batch - b0);
+    const int samples = (int)min((int64_t)kPitch, p.batch - b0);
+    int64_t b[SPT];
+    bool live[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+        b[q] = b0 + threadIdx.x + q * kRegThreads;
+        live[q] = b[q] < p.batch;
+    }
     stage_reg_tables(pp, l);
-    if ((staged & 1) && live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
+    if (staged & 1) {
+#pragma unroll
+        for (int q = 0; q < SPT; ++q)
+            if (live[q]) fetch_own_row(p.angles + b[q] * p.stride, l.cs + threadIdx.x + q * kRegThreads, T, kPitch);
+    }
     cp_async_wait_all();
     __syncthreads();
     const RegSmem sm{l.cols, l.signs, pp.reg.sign_pitch};
-    double re[N], im[N], zr = 1.0, zi = 0.0, n2 = 1.0;
-    if (live) {
+    double re[SPT][N], im[SPT][N], zr[SPT], zi[SPT], n2[SPT];
+    // a thread with a dead second sample simply recomputes its first one (no divergence, results unused)
+    int64_t be[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) be[q] = live[q] ? b[q] : b[0];
+    if (live[0]) {
         if (staged & 1) {
-            convert_own_row(l.cs + threadIdx.x, T, kRegThreads, l.trig);
-            const AngleStaged ang{l.cs + threadIdx.x, kRegThreads, T, l.fixed, -1, 1.0, 0.0};
+            AngleStaged ang[SPT];
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) {
+                double2* col0 = l.cs + threadIdx.x + (live[q] ? q : 0) * kRegThreads;
+                if (live[q]) convert_own_row(col0, T, kPitch, l.trig);
+                ang[q] = AngleStaged{col0, kPitch, T, l.fixed, -1, 1.0, 0.0};
+            }
             if (pp.reg.n_fixed == 0)
-                n2 = sv_reg_evolve<W, false, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+                sv_reg_evolve_multi<W, SPT, false, false>(p, sm, pp.reg.periodic != 0, be, ang, re, im, zr, zi, n2);
             else
-                n2 = sv_reg_evolve<W, true, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+                sv_reg_evolve_multi<W, SPT, true, false>(p, sm, pp.reg.periodic != 0, be, ang, re, im, zr, zi, n2);
         } else {
-            const AngleGlobal ang{p.angles + b * p.stride, T, l.fixed, -1, 0.0};
-            n2 = sv_reg_evolve<W, true, false>(p, sm, pp.reg.periodic != 0, b, ang, re, im, zr, zi);
+            AngleGlobal ang[SPT];
+#pragma unroll
+            for (int q = 0; q < SPT; ++q) ang[q] = AngleGlobal{p.angles + be[q] * p.stride, T, l.fixed, -1, 0.0};
+            sv_reg_evolve_multi<W, SPT, true, false>(p, sm, pp.reg.periodic != 0, be, ang, re, im, zr, zi, n2);
         }
     }
     // Output.  Device-resident callers get direct 16-byte stores from registers.  With
@@ -355,18 +430,20 @@ __global__ void __launch_bounds__(128, (W <= 3 ? MBQC_REG_MINBLOCKS_W3 : (W == 4
     // (156 vs 261 us per 65,536-sample step in scripts/zerocopy_probe2.cu).
     const bool stage_out = DM || (staged & 2);
     if (stage_out) __syncthreads();  // everyone is done with the staged tables: re-use the buffer
-    if (live) {
-        const double zn = zr * zr + zi * zi;
-        const bool ok = (n2 > 0.0) && (zn > 0.0) && isfinite(n2) && isfinite(zn);
-        if (p.status) p.status[b] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+        if (!live[q]) continue;
+        const double zn = zr[q] * zr[q] + zi[q] * zi[q];
+        const bool ok = (n2[q] > 0.0) && (zn > 0.0) && isfinite(n2[q]) && isfinite(zn);
+        if (p.status) p.status[b[q]] = ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
         if (!ok && p.status_any) atomicOr(p.status_any, MBQC_STATUS_BAD_NORM);
-        const double r = rsqrt(n2 * zn);
-        const double ur = zr * r, ui = zi * r;  // unit phase / norm
-        double2* o = stage_out ? (dyn + ((size_t)threadIdx.x << k)) : (p.out + (b << k));
+        const double r = rsqrt(n2[q] * zn);
+        const double ur = zr[q] * r, ui = zi[q] * r;  // unit phase / norm
+        double2* o = stage_out ? (dyn + ((size_t)(threadIdx.x + q * kRegThreads) << k)) : (p.out + (b[q] << k));
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const int d = p.tab.out_dst[i];
-            if (d >= 0) o[d] = make_double2(re[i] * ur - im[i] * ui, re[i] * ui + im[i] * ur);
+            if (d >= 0) o[d] = make_double2(re[q][i] * ur - im[q][i] * ui, re[q][i] * ui + im[q][i] * ur);
         }
     }
     if (!stage_out) return;
