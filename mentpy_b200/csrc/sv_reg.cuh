@@ -280,7 +280,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 #ifndef MBQC_REG_SPT_SMALL
-#define MBQC_REG_SPT_SMALL 2  // samples per thread for windows <= 3
+#define MBQC_REG_SPT_SMALL 1  // samples per thread for windows <= 3 (2 measured slower on B200: 71.9 vs 62.7 us per 2^20 on C2)
 #endif
 constexpr int kRegThreads = 128;  // CTA size of the register kernels
 
@@ -359,9 +359,9 @@ __device__ __forceinline__ void convert_own_row(double2* cs_col0, int T, int pit
 // DM = false: out is [B][2^k] amplitudes.  DM = true: out is [B][2^k][2^k] = |psi><psi|
 // (np_simulator_sv.py:292-293, the reference's default output form).
 // SPT = samples per thread: the CTA covers 128 * SPT samples, thread t owns samples
-// b0 + t + q * 128 (so the (cos, sin) column reads stay conflict-free).  SPT = 2 for small windows:
-// two independent dependency chains per thread keep the FP64 pipe busier than extra warps could
-// (the kernel is latency-, not issue-bound: profiles/README.md).
+// b0 + t + q * 128 (so the (cos, sin) column reads stay conflict-free).  SPT = 2 was measured
+// SLOWER than 1 on B200 for w = 3 (fewer resident warps outweigh the extra ILP), so 1 is the default;
+// likewise the table-driven sincos (MBQC_SINCOS_TAB=1) loses to the polynomial one (profiles/README.md).
 // `staged`: bit 0 = angle tile staged in shared memory, bit 1 = CTA-coalesced output stage.
 template <int W>
 struct RegKernelTraits {
