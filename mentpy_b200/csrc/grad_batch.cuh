@@ -67,4 +67,137 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
     }
 }
 
+// ---- prefix-sharing variant --------------------------------------------------------------------
+// One thread per angle vector.  The state after measurements 0..m-1 is common to BOTH shifted
+// evaluations of the parameter used at measurement m and to every later parameter, so the thread
+// walks the pattern once, keeping that prefix state in (thread-private, conflict-free) shared
+// memory, and forks two suffix runs per trainable measurement:
+//     work = M + sum_m 2 (M - m)  ~  M^2   measurements instead of 2 T M ~ 2 M^2,
+// with no phase tracking (the cost is phase invariant) and the unshifted cost for free from the
+// final prefix.  Needs B >= ~100k angle vectors to fill the GPU (thread per vector).
+template <int W>
+__device__ __forceinline__ double fidelity_cost(const SvBatchParams& p, const double (&re)[1 << W],
+                                                const double (&im)[1 << W]) {
+    double ar = 0.0, ai = 0.0, n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) {
+        const int d = p.tab.out_dst[i];
+        if (d >= 0) {
+            const double2 tg = __ldg(p.target + d);
+            ar = fma(tg.x, re[i], fma(tg.y, im[i], ar));
+            ai = fma(tg.x, im[i], fma(-tg.y, re[i], ai));
+            n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+        }
+    }
+    return 1.0 - (ar * ar + ai * ai) / n2;
+}
+
+template <int W>
+__device__ __forceinline__ void rescale_state(double (&re)[1 << W], double (&im)[1 << W]) {
+    double n2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
+    const double r = rsqrt(n2);
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) {
+        re[i] *= r;
+        im[i] *= r;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_constant__ SvRegParams pp) {
+    constexpr int N = 1 << W;
+    extern __shared__ double2 dyn[];
+    const SvBatchParams& p = pp.base;
+    const PlanTables& t = p.tab;
+    const int T = t.n_angles, M = t.n_steps;
+    const RegSmemLayout l = reg_smem_carve(dyn, M, pp.reg.sign_pitch, pp.reg.n_fixed);
+    double2* prefix = l.cs + (size_t)T * kRegThreads;  // [N][128]: element-major, thread-minor
+    const int64_t b = (int64_t)blockIdx.x * kRegThreads + threadIdx.x;
+    const bool live = b < p.batch;
+    stage_reg_tables(pp, l);
+    if (live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!live) return;
+    double2* cs = l.cs + threadIdx.x;
+    convert_own_row(cs, T, kRegThreads, l.trig);
+    double2* pf = prefix + threadIdx.x;
+    double sh_s, sh_c;
+    sincos(p.shift, &sh_s, &sh_c);
+    // seed -> prefix
+    {
+        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
+            double2 v = make_double2(t.plus_amp, 0.0);
+            if (p.input_mode != MBQC_INPUT_PLUS) {
+                v = __ldg(in + t.init_src[i]);
+                v.x *= t.init_scale;
+                v.y *= t.init_scale;
+            }
+            pf[i * kRegThreads] = make_double2(flip_sign(v.x, sb), flip_sign(v.y, sb));
+        }
+    }
+    auto step_cs = [&](int m, double& c, double& s) -> int {  // returns the angle column or -1
+        const int col = (int)(l.cols[m] & 0xffffu);
+        if (col >= T) {
+            const double2 f = l.fixed[col - T];
+            c = f.x;
+            s = f.y;
+            return -1;
+        }
+        const double2 v = cs[col * kRegThreads];
+        c = v.x;
+        s = v.y;
+        return col;
+    };
+    double re[N], im[N];
+    bool bad = false;
+    for (int m = 0; m < M; ++m) {
+        double c, s;
+        const int col = step_cs(m, c, s);
+        if (col >= 0) {
+            double cost[2];
+#pragma unroll 1
+            for (int sgn = 0; sgn < 2; ++sgn) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double2 v = pf[i * kRegThreads];
+                    re[i] = v.x;
+                    im[i] = v.y;
+                }
+                const double ss = sgn ? -sh_s : sh_s;
+                reg_step_any<W>(re, im, (int)(l.cols[m] >> 16), c * sh_c - s * ss, s * sh_c + c * ss,
+                                l.signs + m * pp.reg.sign_pitch);
+                for (int m2 = m + 1; m2 < M; ++m2) {
+                    double c2, s2;
+                    step_cs(m2, c2, s2);
+                    reg_step_any<W>(re, im, (int)(l.cols[m2] >> 16), c2, s2, l.signs + m2 * pp.reg.sign_pitch);
+                    if (((m2 - m) & 15) == 15) rescale_state<W>(re, im);
+                }
+                cost[sgn] = fidelity_cost<W>(p, re, im);
+            }
+            p.grad[b * T + col] = (cost[0] - cost[1]) / (2.0 * p.shift);
+            bad |= !(cost[0] == cost[0]) || !(cost[1] == cost[1]);
+        }
+        // advance the prefix by the unshifted measurement m
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double2 v = pf[i * kRegThreads];
+            re[i] = v.x;
+            im[i] = v.y;
+        }
+        reg_step_any<W>(re, im, (int)(l.cols[m] >> 16), c, s, l.signs + m * pp.reg.sign_pitch);
+        if ((m & 7) == 7) rescale_state<W>(re, im);
+#pragma unroll
+        for (int i = 0; i < N; ++i) pf[i * kRegThreads] = make_double2(re[i], im[i]);
+    }
+    const double c0 = fidelity_cost<W>(p, re, im);
+    if (p.cost) p.cost[b] = c0;
+    if (p.status) p.status[b] = (bad || !(c0 == c0)) ? MBQC_STATUS_BAD_NORM : MBQC_STATUS_OK;
+}
+
 }  // namespace mbqc

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -502,14 +503,39 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     p.grad = d_grad;
     p.cost = d_cost;
     const int T = plan->tab.n_angles;
+    SvRegParams rp;
+    fill_reg_params(rp, p, plan);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t tables = reg_smem_tables_bytes(plan->tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
+    // Large batches: one thread per angle vector with prefix sharing (about half the measurements).
+    // Small batches (or tiles that do not fit shared memory): one thread per (vector, parameter).
+    const size_t prefix_smem = tables + (size_t)kRegThreads * ((size_t)T + ((size_t)1 << w)) * sizeof(double2);
+    const char* force = getenv("MBQC_GRAD_KERNEL");  // "prefix" | "pairs" (experiments / tests)
+    bool use_prefix = batch >= 32768 && prefix_smem <= 200 * 1024;
+    if (force && !strcmp(force, "prefix") && prefix_smem <= 200 * 1024) use_prefix = true;
+    if (force && !strcmp(force, "pairs")) use_prefix = false;
+    if (use_prefix) {
+        const unsigned blocks = (unsigned)((batch + kRegThreads - 1) / kRegThreads);
+        auto go = [&](auto kern) -> int {
+            if (prefix_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prefix_smem));
+            kern<<<blocks, kRegThreads, prefix_smem, st>>>(rp);
+            return MBQC_OK;
+        };
+        switch (w) {
+            case 1: rc = go(sv_reg_grad_prefix_kernel<1>); break;
+            case 2: rc = go(sv_reg_grad_prefix_kernel<2>); break;
+            case 3: rc = go(sv_reg_grad_prefix_kernel<3>); break;
+            case 4: rc = go(sv_reg_grad_prefix_kernel<4>); break;
+            default: rc = go(sv_reg_grad_prefix_kernel<5>); break;
+        }
+        if (rc) return rc;
+        return after_launch("sv_reg_grad_prefix_kernel");
+    }
     if (T > 128) return fail(MBQC_E_UNSUPPORTED, "fused gradient covers at most 128 angles (got %d)", T);
     const int spb = 128 / T;  // whole angle vectors per CTA
     const int threads = spb * T;
-    SvRegParams rp;
-    fill_reg_params(rp, p, plan);
-    const size_t smem = reg_smem_tables_bytes(plan->tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed) + (size_t)threads * sizeof(double2);
+    const size_t smem = tables + (size_t)threads * sizeof(double2);
     const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
-    cudaStream_t st = (cudaStream_t)stream;
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<blocks, threads, smem, st>>>(rp, spb);

@@ -452,3 +452,29 @@ def test_edge_cases_sizes_and_shapes():
         ps.run_batch(np.zeros((4, 8)), input_states=np.zeros((3, 4)))
     with pytest.raises(ValueError):
         mb.PatternSimulator(mb.templates.grid_cluster(2, 5), input_state=np.ones(3), backend="cuda-sv").run(np.zeros(8))
+
+
+@pytest.mark.parametrize("kernel", ["pairs", "prefix"])
+def test_gradient_kernels_agree(kernel, monkeypatch):
+    """Both gradient kernels (thread per (vector, parameter) / thread per vector with prefix
+    sharing) against explicit shifted evaluations, incl. fixed-angle and X nodes, Haar inputs."""
+    from mentpy_b200.gradients import psr_gradient_batched
+    from scipy.stats import unitary_group
+
+    monkeypatch.setenv("MBQC_GRAD_KERNEL", kernel)
+    for name, args, w in (("grid_cluster", [4, 5], None), ("grid_cluster", [2, 7], None), ("linear_cluster", [40], 4)):
+        gs = getattr(mb.templates, name)(*args)
+        gs[1] = mb.Ment("X")
+        gs[2] = mb.Ment(0.37, "XY")
+        T, k, n_in = len(gs.trainable_nodes), len(gs.output_nodes), len(gs.input_nodes)
+        ps = mb.PatternSimulator(gs, backend="cuda-sv", **({} if w is None else {"window_size": w}))
+        X = np.random.default_rng(6).uniform(0, 2 * np.pi, (37, T))
+        tgt = unitary_group.rvs(2**k, random_state=8)[:, 0]
+        ins = np.stack([unitary_group.rvs(2**n_in, random_state=s)[:, 0] for s in range(37)])
+        for inputs in (None, ins):
+            g, c = psr_gradient_batched(ps, X, tgt, input_states=inputs, return_cost=True)
+            f = lambda Y: 1 - np.abs(ps.run_batch(Y, input_states=inputs) @ tgt.conj()) ** 2
+            assert np.allclose(c, f(X), atol=1e-12)
+            for i in (0, T // 2, T - 1):
+                e = np.zeros(T); e[i] = 1.5
+                assert np.allclose(g[:, i], (f(X + e) - f(X - e)) / 3.0, atol=1e-11)
