@@ -104,6 +104,13 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
                       int32_t out_form, int32_t* d_status, void* stream);
 
+/* complex64 mode of mbqc_run_batch_sv (window <= MBQC_MAX_WINDOW_REG): fp32 state and arithmetic,
+ * d_inputs / d_out hold interleaved float pairs; angles stay fp64.  Accuracy target: infidelity
+ * <= 1e-5 against the fp64 path (BASELINE.json north_star). */
+int mbqc_run_batch_sv_f32(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                          const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                          int32_t out_form, int32_t* d_status, void* stream);
+
 /* Host-buffer form of mbqc_run_batch_sv -- the end-to-end plugin call: h_angles [B][T] and h_out
  * live in host memory (page-locked for full PCIe speed).  The batch is cut into n_chunks pieces
  * (<= 0: library default) whose H2D copy, kernel and D2H copy are queued on internal streams so

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "mbqc_plan_destroy": (None, [C.c_void_p]),
     "mbqc_run_batch_sv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                     C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mbqc_run_batch_sv_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                        C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mbqc_host_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int32]),
     "mbqc_run_batch_sv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,

@@ -12,6 +12,7 @@
 #include "grad_batch.cuh"
 #include "sv_batch.cuh"
 #include "sv_reg.cuh"
+#include "sv_reg_f32.cuh"
 #include "stream.cuh"
 #include <vector>
 
@@ -444,6 +445,52 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
 }
 
 extern "C" {
+
+}  // extern "C"
+
+template <int W, bool DM>
+static int launch_sv_reg_f32_w(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((p.batch + kRegThreads - 1) / kRegThreads);
+    SvRegParams rp;
+    fill_reg_params(rp, p, plan);
+    const size_t tables = reg_smem_tables_bytes(p.tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
+    const size_t tile = (size_t)kRegThreads * p.tab.n_angles * sizeof(double2);
+    const int staged = (p.tab.n_angles > 0 && tables + tile <= 100 * 1024) ? 1 : 0;
+    size_t smem = tables + (staged ? tile : 0);
+    const size_t stage = ((size_t)kRegThreads << p.tab.n_out) * sizeof(float2);
+    if (DM && stage > smem) smem = stage;
+    auto kern = sv_reg_kernel_f32<W, DM>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, kRegThreads, smem, st>>>(rp, staged | (DM ? 2 : 0));
+    return after_launch("sv_reg_kernel_f32");
+}
+
+extern "C" {
+
+int mbqc_run_batch_sv_f32(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                          const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                          int32_t out_form, int32_t* d_status, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
+    if (rc) return rc;
+    if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
+    if (plan->tab.window > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "complex64 mode covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, plan->tab.window);
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
+    if (batch == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool dm = out_form == MBQC_OUT_DM;
+    switch (plan->tab.window) {
+        case 1: return dm ? launch_sv_reg_f32_w<1, true>(p, plan, st) : launch_sv_reg_f32_w<1, false>(p, plan, st);
+        case 2: return dm ? launch_sv_reg_f32_w<2, true>(p, plan, st) : launch_sv_reg_f32_w<2, false>(p, plan, st);
+        case 3: return dm ? launch_sv_reg_f32_w<3, true>(p, plan, st) : launch_sv_reg_f32_w<3, false>(p, plan, st);
+        case 4: return dm ? launch_sv_reg_f32_w<4, true>(p, plan, st) : launch_sv_reg_f32_w<4, false>(p, plan, st);
+        default: return dm ? launch_sv_reg_f32_w<5, true>(p, plan, st) : launch_sv_reg_f32_w<5, false>(p, plan, st);
+    }
+}
 
 int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,

@@ -77,6 +77,12 @@ class _CudaPatternBase(BaseSimulator):
         self.wires = kwargs.pop("wires", None)
         self.device = kwargs.pop("device", None)
         self._slot_order = kwargs.pop("slot_order", "msb")
+        dtype = kwargs.pop("dtype", "complex128")
+        dtype = {"complex128": "complex128", "complex64": "complex64", np.complex128: "complex128",
+                 np.complex64: "complex64"}.get(dtype, str(dtype))
+        if dtype not in ("complex128", "complex64"):
+            raise ValueError("dtype must be 'complex128' or 'complex64'")
+        self.dtype = dtype
         if not self.force0:
             raise NotImplementedError("Numpy simulator does not support force0=False.")
         if self.dev_mode:
@@ -251,6 +257,8 @@ class CudaSimulatorSV(_CudaPatternBase):
     def _run_plan(self, dplan: DevicePlan, angles, input_states, code, check, copy=True):
         dev = self._dev()
         lib = _lib.load()
+        if self.dtype == "complex64":
+            return self._run_plan_f32(dplan, angles, input_states, code, check)
         on_host = not (isinstance(angles, torch.Tensor) and angles.is_cuda)
         if on_host and (input_states is None or np.ndim(input_states) == 1):
             return self._run_plan_host(dplan, angles, input_states, code, check, copy)
@@ -271,6 +279,33 @@ class CudaSimulatorSV(_CudaPatternBase):
                     self._check_status(status)
                 return res
             self.last_status = status
+            return out
+
+    def _run_plan_f32(self, dplan, angles, input_states, code, check):
+        """complex64 mode (mbqc_run_batch_sv_f32): fp32 state, complex64 outputs."""
+        dev = self._dev()
+        lib = _lib.load()
+        if self.plan.window > _lib.MAX_WINDOW_REG:
+            raise NotImplementedError(f"complex64 mode covers window <= {_lib.MAX_WINDOW_REG}")
+        with torch.cuda.device(dev):
+            a, on_host = self._stage_angles(angles, dev)
+            batch = a.shape[0]
+            inp, mode = self._stage_inputs(input_states, batch, dev)
+            inp = inp.to(torch.complex64).contiguous()
+            dim = 2 ** dplan.n_out
+            shape = (batch, dim) if code == _lib.OUT_SV else (batch, dim, dim)
+            out = torch.empty(shape, dtype=torch.complex64, device=dev)
+            status = torch.empty(max(batch, 1), dtype=torch.int32, device=dev)
+            if batch:
+                _lib.check(lib.mbqc_run_batch_sv_f32(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
+                                                     batch, _ptr(out), code, _ptr(status),
+                                                     torch.cuda.current_stream(dev).cuda_stream))
+            if on_host:
+                res = out.cpu().numpy()
+                if check and batch:
+                    self._check_status(status[:batch])
+                return res
+            self.last_status = status[:batch]
             return out
 
     def _run_plan_host(self, dplan, angles, input_states, code, check, copy):

@@ -478,3 +478,37 @@ def test_gradient_kernels_agree(kernel, monkeypatch):
             for i in (0, T // 2, T - 1):
                 e = np.zeros(T); e[i] = 1.5
                 assert np.allclose(g[:, i], (f(X + e) - f(X - e)) / 3.0, atol=1e-11)
+
+
+def test_complex64_mode():
+    """Optional complex64 mode: infidelity <= 1e-5 vs the fp64 reference (BASELINE north_star)."""
+    rng = np.random.default_rng(41)
+    for name, args, w in (("linear_cluster", [5], None), ("grid_cluster", [2, 6], None),
+                          ("grid_cluster", [4, 5], None), ("grid_cluster", [3, 5], 5), ("linear_cluster", [40], 3)):
+        gs = getattr(mb.templates, name)(*args)
+        gs[1] = mb.Ment("X")
+        pat = PatternData.from_circuit(gs)
+        T = len(gs.trainable_nodes)
+        ang = rng.uniform(0, 2 * np.pi, (300, T))
+        kw = {} if w is None else {"window_size": w}
+        ps = mb.PatternSimulator(gs, backend="cuda-sv", dtype="complex64", **kw)
+        got = ps.run_batch(ang)
+        assert got.dtype == np.complex64
+        want = matrix_free.run_sv_batch(pat, ang, window_size=(w or 1))
+        infid = np.abs(1 - np.abs(np.sum(got.astype(np.complex128).conj() * want, axis=1)) ** 2)
+        assert infid.max() < 1e-5, infid.max()
+        assert np.allclose(np.sum(np.abs(got.astype(np.complex128)) ** 2, axis=1), 1.0, atol=1e-5)
+        rho = ps.run_batch(ang[:7], output_form="dm")
+        assert rho.dtype == np.complex64 and np.abs(rho - want[:7, :, None] * want[:7, None, :].conj()).max() < 1e-4
+        tout = ps.run_batch(torch.from_numpy(ang).cuda())
+        assert tout.dtype == torch.complex64 and tout.is_cuda
+    # golden C2 vector through the single-sample API
+    case = next(c for c in CASES if c["spec"][1] == [2, 6] and c["output_form"] == "sv")
+    ps = mb.PatternSimulator(_build(case), backend="cuda-sv", dtype="complex64")
+    out = ps.run(np.asarray(case["angles"]), output_form="sv")
+    assert infidelity_pure(out.astype(np.complex128), from_cplx(case["output"])) < 1e-5
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(mb.templates.linear_cluster(12), backend="cuda-sv", dtype="complex64",
+                            window_size=8).run_batch(np.zeros((1, 11)))
+    with pytest.raises(ValueError):
+        mb.PatternSimulator(gs, backend="cuda-sv", dtype="float16")
