@@ -390,7 +390,8 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
     // kernels store their (CTA-coalesced) results straight into it over PCIe and the D2H copies
     // disappear: measured 156 us vs 198 us per 65,536-sample step on B200 / PCIe 5 (profiles/).
     double2* dev_view_of_host_out = nullptr;
-    {
+    static const bool direct_ok = []() { const char* e = getenv("MBQC_HOST_DIRECT"); return !(e && e[0] == '0'); }();
+    if (direct_ok) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, h_out) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
             dev_view_of_host_out = (double2*)attr.devicePointer;
@@ -701,9 +702,8 @@ int mbqc_stream_steps_lanes(void* d_state, const mbqc_stream_desc* desc, void* s
 int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const mbqc_stream_seed* seed,
                              void* stream) {
     if (!seed || !desc) return fail(MBQC_E_ARG, "seed/desc is NULL");
-    if (seed->d_input) return fail(MBQC_E_UNSUPPORTED, "seeded passes cover the |+> input; write other inputs with mbqc_stream_init");
     SeedDev sd;
-    int rc = make_seed(sd, seed->window, seed->n_inputs, seed->input_slot, seed->init_cz_mask, nullptr, seed->scale);
+    int rc = make_seed(sd, seed->window, seed->n_inputs, seed->input_slot, seed->init_cz_mask, seed->d_input, seed->scale);
     if (rc) return rc;
     // symmetric initial-CZ adjacency of the fused slots, and the parity of edges inside each subset
     const int K = desc->n_fused;
@@ -717,6 +717,9 @@ int mbqc_stream_steps_seeded(void* d_state, const mbqc_stream_desc* desc, const 
         for (int a = 0; a < seed->window && a < slot[j]; ++a)
             if ((seed->init_cz_mask[a] >> slot[j]) & 1ull) nb |= 1ull << a;
         sd.nbr[j] = nb;
+        sd.in_bit[j] = 0;
+        for (int q = 0; q < seed->n_inputs; ++q)
+            if (seed->input_slot[q] == slot[j]) sd.in_bit[j] = 1u << (seed->n_inputs - 1 - q);
     }
     sd.pair_parity = 0;
     for (uint32_t l = 0; l < (1u << K); ++l) {

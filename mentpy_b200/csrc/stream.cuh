@@ -38,6 +38,7 @@ struct SeedDev {
     //   sign(l) = sign(base) ^ XOR_{j in l} parity(base & nbr[j]) ^ bit l of pair_parity
     uint64_t nbr[MBQC_STREAM_MAX_FUSE];  // initial-CZ neighbours of fused slot j (both directions)
     uint32_t pair_parity;                // bit l: parity of the initial CZ edges inside subset l
+    uint32_t in_bit[MBQC_STREAM_MAX_FUSE];  // input-index bit fed by fused slot j (0: not an input)
 };
 
 __device__ __forceinline__ double2 seed_amplitude(const SeedDev& p, uint64_t g) {
@@ -99,11 +100,24 @@ __global__ void __launch_bounds__(256) stream_steps_kernel(double2* __restrict__
             for (int j = 0; j < K; ++j) pj |= ((uint32_t)__popcll(gfull & seed.nbr[j]) & 1u) << j;
             const uint32_t par0 = (uint32_t)__popcll(acc) & 1u;
             const double a = seed.scale * d.scale;
+            uint32_t src0 = 0;
+            if (seed.input)
+                for (int q = 0; q < seed.n_in; ++q) src0 |= (uint32_t)((gfull >> seed.in_slot[q]) & 1ull) << (seed.n_in - 1 - q);
 #pragma unroll
             for (int l = 0; l < N; ++l) {
                 const uint32_t sg = (par0 ^ ((uint32_t)__popc((uint32_t)l & pj) & 1u) ^ ((seed.pair_parity >> l) & 1u)) << 31;
-                re[l] = flip_sign(a, sg);
-                im[l] = 0.0;
+                if (seed.input) {
+                    uint32_t src = src0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        if (l & (1 << j)) src |= seed.in_bit[j];
+                    const double2 v = __ldg(seed.input + src);
+                    re[l] = flip_sign(v.x * a, sg);
+                    im[l] = flip_sign(v.y * a, sg);
+                } else {
+                    re[l] = flip_sign(a, sg);
+                    im[l] = 0.0;
+                }
             }
         }
 #pragma unroll

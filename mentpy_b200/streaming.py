@@ -233,7 +233,7 @@ class StreamExecutor:
         eng = self.engine
         # when the pattern starts with a local pass, the engine may generate the seed inside that
         # pass instead of writing it out first (one write + one read of the whole state saved)
-        first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass) and input_state is None
+        first_local = bool(sched.passes) and isinstance(sched.passes[0], LocalPass)
         import os
         import time
 
