@@ -333,9 +333,12 @@ def run_gpu_arm(args):
     e2e = None
     host_pool = min(pool, 4)
     if not args.skip_e2e:
+        # host-side inputs are produced on the host, directly in page-locked memory
+        hgen = torch.Generator()
+        hgen.manual_seed(SEED + 1000 * rank + 7)
         h_angles = [torch.empty((BATCH, T), dtype=torch.float64).pin_memory() for _ in range(host_pool)]
-        for j, h in enumerate(h_angles):
-            h.copy_(angles[j].cpu())
+        for h in h_angles:
+            h.uniform_(0.0, 2 * np.pi, generator=hgen)
         e2e_steps = max(3, min(args.steps, 50))
         for i in range(2):
             ps.run_batch(h_angles[i % host_pool], copy=False)
