@@ -215,6 +215,24 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def pin_to_gpu_numa_node(index):
+    """Bind this rank (and the page-locked buffers it allocates afterwards) to the CPU cores NVML
+    reports as local to its GPU: the host<->device legs then stay on the GPU's own PCIe root."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -230,6 +248,7 @@ def run_gpu_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -360,6 +379,10 @@ def run_gpu_arm(args):
         value = world * BATCH * args.steps / (ms * 1e-3)
         achieved = BATCH * ALGO_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9
         cores = os.cpu_count() or 1
+        try:
+            os.sched_setaffinity(0, range(cores))  # the CPU leg uses every host core again
+        except Exception:
+            pass
         cpu_rate, cpu_s = (None, 0.0) if args.skip_cpu else cpu_port_rate(evals_per_core=4096, cores=cores)
         line = {
             "metric": "pattern_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
