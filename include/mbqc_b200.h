@@ -212,6 +212,15 @@ int mbqc_ipc_export(const void* d_ptr, void* handle64);
 int mbqc_ipc_import(const void* handle64, void** d_ptr);
 int mbqc_ipc_close(void* d_ptr);
 
+/* ---- calculator helpers (mentpy/calculator/state_ops.py), single state, qubit 0 = MSB ------------
+ * pure: SUM over the traced qubits then renormalise (:42-74 -- the reference's pure-state "partial
+ * trace"); mixed: true partial trace (:77-119); pure2density: |psi><psi| (:16-39). n_qubits <= 14. */
+int mbqc_partial_trace_pure(const void* d_psi, int32_t n_qubits, const int32_t* traced, int32_t n_traced,
+                            void* d_out, void* stream);
+int mbqc_partial_trace_mixed(const void* d_rho, int32_t n_qubits, const int32_t* traced, int32_t n_traced,
+                             void* d_out, void* stream);
+int mbqc_pure2density(const void* d_psi, int32_t n_qubits, void* d_out, void* stream);
+
 /* plan introspection (used by the host mirror and the tests) */
 int32_t mbqc_plan_window(const mbqc_plan* plan);
 int32_t mbqc_plan_num_steps(const mbqc_plan* plan);

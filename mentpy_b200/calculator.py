@@ -1,0 +1,76 @@
+"""State helpers with the reference's calculator API (mentpy/calculator/state_ops.py:16-156),
+evaluated by CUDA kernels (csrc/calc.cuh).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor
+out.  Note the reference's pure-state "partial trace" is a SUM over the traced qubits followed by
+a renormalisation (state_ops.py:66-73), not a projection -- reproduced as is."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["partial_trace", "pure2density", "partial_trace_pure_state", "partial_trace_mixed_state"]
+
+
+def _to_device(data):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("mentpy_b200 needs a CUDA device: there is no CPU fallback.")
+    if isinstance(data, torch.Tensor):
+        return data.to(device="cuda", dtype=torch.complex128).contiguous(), False
+    return torch.from_numpy(np.ascontiguousarray(data, dtype=np.complex128)).cuda(), True
+
+
+def _finish(t, on_host):
+    return t.cpu().numpy() if on_host else t
+
+
+def _n_qubits(dim):
+    n = int(round(np.log2(dim)))
+    if 2**n != dim:
+        raise ValueError("Invalid input shape for quantum state.")
+    return n
+
+
+def pure2density(psi):
+    import torch
+
+    d, on_host = _to_device(psi)
+    n = _n_qubits(d.shape[0])
+    out = torch.empty((2**n, 2**n), dtype=torch.complex128, device=d.device)
+    _lib.check(_lib.load().mbqc_pure2density(d.data_ptr(), n, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return _finish(out, on_host)
+
+
+def partial_trace_pure_state(psi, indices):
+    import torch
+
+    d, on_host = _to_device(psi)
+    n = _n_qubits(d.shape[0])
+    idx = (C.c_int32 * max(len(indices), 1))(*[int(i) for i in indices])
+    out = torch.empty(2 ** (n - len(set(indices))), dtype=torch.complex128, device=d.device)
+    _lib.check(_lib.load().mbqc_partial_trace_pure(d.data_ptr(), n, idx, len(indices), out.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream))
+    return _finish(out, on_host)
+
+
+def partial_trace_mixed_state(rho, indices):
+    import torch
+
+    d, on_host = _to_device(rho)
+    n = _n_qubits(d.shape[0])
+    idx = (C.c_int32 * max(len(indices), 1))(*[int(i) for i in indices])
+    k = n - len(set(indices))
+    out = torch.empty((2**k, 2**k), dtype=torch.complex128, device=d.device)
+    _lib.check(_lib.load().mbqc_partial_trace_mixed(d.data_ptr(), n, idx, len(indices), out.data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+    return _finish(out, on_host)
+
+
+def partial_trace(data, indices):
+    shape = tuple(data.shape)
+    if len(shape) == 1:
+        return partial_trace_pure_state(data, indices)
+    if len(shape) == 2:
+        return partial_trace_mixed_state(data, indices)
+    raise ValueError("Invalid input shape for quantum state.")

@@ -14,6 +14,7 @@
 #include "sv_reg.cuh"
 #include "sv_reg_f32.cuh"
 #include "stream.cuh"
+#include "calc.cuh"
 #include <vector>
 
 using namespace mbqc;
@@ -804,6 +805,52 @@ int mbqc_ipc_import(const void* handle64, void** d_ptr) {
 int mbqc_ipc_close(void* d_ptr) {
     if (d_ptr) CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
     return MBQC_OK;
+}
+
+}  // extern "C"
+
+
+// ---- calculator helpers ------------------------------------------------------------------------
+extern "C" {
+
+static int split_masks(int n, const int32_t* traced, int n_traced, uint32_t* keep, uint32_t* trace) {
+    if (n < 1 || n > 14) return fail(MBQC_E_ARG, "n_qubits %d outside [1,14]", n);
+    uint32_t t = 0;
+    for (int i = 0; i < n_traced; ++i) {
+        if (traced[i] < 0 || traced[i] >= n) return fail(MBQC_E_ARG, "traced qubit %d outside the state", traced[i]);
+        t |= 1u << (n - 1 - traced[i]);
+    }
+    *trace = t;
+    *keep = ((1u << n) - 1u) & ~t;
+    return MBQC_OK;
+}
+
+int mbqc_partial_trace_pure(const void* d_psi, int32_t n_qubits, const int32_t* traced, int32_t n_traced,
+                            void* d_out, void* stream) {
+    if (!d_psi || !d_out || (n_traced && !traced)) return fail(MBQC_E_ARG, "NULL argument");
+    uint32_t keep, trace;
+    int rc = split_masks(n_qubits, traced, n_traced, &keep, &trace);
+    if (rc) return rc;
+    trace_pure_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((const double2*)d_psi, (double2*)d_out, n_qubits, keep, trace);
+    return after_launch("trace_pure_kernel");
+}
+
+int mbqc_partial_trace_mixed(const void* d_rho, int32_t n_qubits, const int32_t* traced, int32_t n_traced,
+                             void* d_out, void* stream) {
+    if (!d_rho || !d_out || (n_traced && !traced)) return fail(MBQC_E_ARG, "NULL argument");
+    uint32_t keep, trace;
+    int rc = split_masks(n_qubits, traced, n_traced, &keep, &trace);
+    if (rc) return rc;
+    const uint64_t total = 1ull << (2 * __builtin_popcount(keep));
+    trace_mixed_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const double2*)d_rho, (double2*)d_out, n_qubits, keep, trace);
+    return after_launch("trace_mixed_kernel");
+}
+
+int mbqc_pure2density(const void* d_psi, int32_t n_qubits, void* d_out, void* stream) {
+    if (!d_psi || !d_out) return fail(MBQC_E_ARG, "NULL argument");
+    if (n_qubits < 0 || n_qubits > 14) return fail(MBQC_E_ARG, "n_qubits %d outside [0,14]", n_qubits);
+    pure2density_kernel<<<stream_grid(1ull << (2 * n_qubits), 256), 256, 0, (cudaStream_t)stream>>>((const double2*)d_psi, (double2*)d_out, n_qubits);
+    return after_launch("pure2density_kernel");
 }
 
 }  // extern "C"

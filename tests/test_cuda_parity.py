@@ -512,3 +512,40 @@ def test_complex64_mode():
                             window_size=8).run_batch(np.zeros((1, 11)))
     with pytest.raises(ValueError):
         mb.PatternSimulator(gs, backend="cuda-sv", dtype="float16")
+
+
+def test_calculator_helpers_match_reference():
+    """mentpy tests/test_calculator.py:12-54 restated + golden vectors from the reference
+    (tests/golden/helpers.json) for the CUDA calculator kernels."""
+    h = load_golden("helpers.json")
+    calc = mb.calculator
+    psi = from_cplx(h["sum_trace_pure"]["psi"])
+    assert np.allclose(calc.partial_trace(psi, [0]), from_cplx(h["sum_trace_pure"]["idx0"]), atol=1e-13)
+    assert np.allclose(calc.partial_trace(psi, [1]), from_cplx(h["sum_trace_pure"]["idx1"]), atol=1e-13)
+    rho = calc.pure2density(psi)
+    assert np.allclose(rho, np.outer(psi, psi.conj()), atol=1e-15)
+    assert np.allclose(calc.partial_trace(rho, [0]), from_cplx(h["trace_mixed"]["idx0"]), atol=1e-13)
+    assert np.allclose(calc.partial_trace(rho, [2]), from_cplx(h["trace_mixed"]["idx2"]), atol=1e-13)
+    # reference unit tests
+    assert np.allclose(calc.pure2density(np.array([1, 0])), [[1, 0], [0, 0]])
+    plus = np.array([1, 1]) / np.sqrt(2)
+    assert np.allclose(calc.pure2density(plus), [[0.5, 0.5], [0.5, 0.5]])
+    mixed = np.array([[0.5, 0], [0, 0.5]])
+    sigma = np.outer(plus, plus)
+    prod = np.kron(mixed, sigma)
+    assert np.allclose(calc.partial_trace(mixed, [0]), 1)
+    assert np.allclose(calc.partial_trace(prod, [0]), sigma) and np.allclose(calc.partial_trace(prod, [1]), mixed)
+    assert np.allclose(calc.partial_trace(plus, [0]), 1)
+    pp = np.kron(plus, np.array([1.0, 0.0]))
+    assert np.allclose(calc.partial_trace(pp, [0]), [1, 0]) and np.allclose(calc.partial_trace(pp, [1]), plus)
+    # multi-qubit traces on a 5-qubit state against numpy
+    st = mb.utils.generate_haar_random_states(5, 1, random_state=3)[0]
+    t = st.reshape([2] * 5).transpose(0, 2, 4, 1, 3).reshape(8, 4).sum(axis=1)
+    assert np.allclose(calc.partial_trace(st, [1, 3]), t / np.linalg.norm(t), atol=1e-13)
+    r5 = np.outer(st, st.conj()).reshape([2] * 10)
+    want = np.einsum("abcdeAbCdE->aceACE", r5).reshape(8, 8)
+    assert np.allclose(calc.partial_trace(np.outer(st, st.conj()), [1, 3]), want, atol=1e-13)
+    with pytest.raises(ValueError):
+        calc.partial_trace(np.zeros((2, 2, 2)), [0])
+    with pytest.raises(ValueError):
+        calc.partial_trace(psi, [7])
