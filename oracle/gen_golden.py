@@ -48,6 +48,14 @@ def template_specs():
     specs.append(("muta", [2, 2], {"one_column": True}))
     specs.append(("muta", [3, 1], {"one_column": True}))
     specs.append(("muta", [3, 1], {}))
+    lin = lambda n: ["linear_cluster", [n], {}]
+    grid = lambda r, c: ["grid_cluster", [r, c], {}]
+    specs.append(("vstack", [lin(3), lin(4)], {}))
+    specs.append(("vstack", [grid(2, 3), lin(3), lin(2)], {}))
+    specs.append(("hstack", [grid(2, 3), grid(2, 2)], {}))
+    specs.append(("hstack", [lin(3), lin(2), lin(4)], {}))
+    specs.append(("merge", [grid(2, 3), lin(4), [[2, 0]]], {}))
+    specs.append(("merge", [grid(2, 3), grid(2, 2), [[5, 0], [2, 2]]], {}))
     seen, out = set(), []
     for s in specs:
         key = json.dumps(s)
@@ -59,6 +67,10 @@ def template_specs():
 
 def build(mp, spec):
     name, args, kwargs = spec
+    if name in ("vstack", "hstack"):   # composite: args = list of sub-specs
+        return getattr(mp, name)([build(mp, tuple(a)) for a in args])
+    if name == "merge":               # args = [spec_a, spec_b, along]
+        return mp.merge(build(mp, tuple(args[0])), build(mp, tuple(args[1])), along=[tuple(x) for x in args[2]])
     return getattr(mp.templates, name)(*args, **kwargs)
 
 

@@ -13,10 +13,18 @@ def _id(r):
     return f"{r['spec'][0]}{r['spec'][1]}{r['spec'][2] or ''}"
 
 
+def _build(spec):
+    name, args, kwargs = spec
+    if name in ("vstack", "hstack"):
+        return getattr(mb, name)([_build(a) for a in args])
+    if name == "merge":
+        return mb.merge(_build(args[0]), _build(args[1]), along=[tuple(x) for x in args[2]])
+    return getattr(mb.templates, name)(*args, **kwargs)
+
+
 @pytest.mark.parametrize("rec", RECORDS, ids=[_id(r) for r in RECORDS])
 def test_structure_tables(rec):
-    name, args, kwargs = rec["spec"]
-    gs = getattr(mb.templates, name)(*args, **kwargs)
+    gs = _build(rec["spec"])
     pat = rec["pattern"]
     assert list(gs.graph.nodes()) == rec["nodes"]
     assert sorted(tuple(sorted(e)) for e in gs.graph.edges()) == sorted(tuple(sorted(e)) for e in pat["edges"])
