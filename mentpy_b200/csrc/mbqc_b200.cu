@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "dm_batch.cuh"
+#include "dm_reg.cuh"
 #include "grad_batch.cuh"
 #include "sv_batch.cuh"
 #include "sv_reg.cuh"
@@ -515,6 +516,21 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
     p.out = (double2*)d_out;
     p.outcomes = d_outcomes;
     p.status = d_status;
+    // w <= 4: one lane per row of rho, registers + shuffles; w = 5, 6: rho in shared memory
+    const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
+    if (w <= 4 && !(force && !strcmp(force, "smem"))) {
+        const int n = 1 << w, spb = 4 * (32 / n);
+        const size_t smem = (size_t)spb * n * n * sizeof(double2);
+        const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (w) {
+            case 1: dm_reg_kernel<1><<<blocks, 128, smem, st>>>(p); break;
+            case 2: dm_reg_kernel<2><<<blocks, 128, smem, st>>>(p); break;
+            case 3: dm_reg_kernel<3><<<blocks, 128, smem, st>>>(p); break;
+            default: dm_reg_kernel<4><<<blocks, 128, smem, st>>>(p); break;
+        }
+        return after_launch("dm_reg_kernel");
+    }
     const unsigned ngroups = 1u << (2 * w - 2);
     int tps_log2 = ilog2_ceil((ngroups + 1) / 2);  // two 4-groups per thread
     if (tps_log2 > 8) tps_log2 = 8;

@@ -549,3 +549,32 @@ def test_calculator_helpers_match_reference():
         calc.partial_trace(np.zeros((2, 2, 2)), [0])
     with pytest.raises(ValueError):
         calc.partial_trace(psi, [7])
+
+
+def test_dm_kernels_agree(monkeypatch):
+    """The register/shuffle DM kernel (w <= 4) and the shared-memory DM kernel give the same
+    states and outcome records (incl. noise, XZ/YZ planes, Haar inputs, outcome-1 branch)."""
+    from scipy.stats import unitary_group
+
+    rng = np.random.default_rng(51)
+    for name, args, w in (("grid_cluster", [3, 8], None), ("grid_cluster", [2, 5], 4), ("linear_cluster", [6], 3),
+                          ("linear_cluster", [5], None), ("many_wires", [[3, 3]], 2)):
+        gs = getattr(mb.templates, name)(*args)
+        if name == "grid_cluster":
+            gs[1] = mb.Ment(0.7, "XZ")
+            gs[2] = mb.Ment("YZ")
+        T, n_in = len(gs.trainable_nodes), len(gs.input_nodes)
+        ang = rng.uniform(0, 2 * np.pi, (19, T))
+        ang[0, 0] = np.pi                       # pushes the first measurement towards prob0 = 0 for |+> inputs
+        ins = np.stack([unitary_group.rvs(2**n_in, random_state=s)[:, 0] for s in range(19)])
+        kw = {} if w is None else {"window_size": w}
+        for noise in ({}, {"circuit_noise": "amplitude_damping", "p": 0.15}):
+            res = {}
+            for kern in ("reg", "smem"):
+                monkeypatch.setenv("MBQC_DM_KERNEL", kern)
+                ps = mb.PatternSimulator(gs, backend="cuda-dm", **kw, **noise)
+                res[kern] = ps.run_batch(ang, input_states=ins, return_outcomes=True)
+                res[kern + "_plus"] = ps.run_batch(ang, return_outcomes=True)
+            for suffix in ("", "_plus"):
+                assert np.allclose(res["reg" + suffix][0], res["smem" + suffix][0], atol=1e-12)
+                assert np.array_equal(res["reg" + suffix][1], res["smem" + suffix][1])
