@@ -57,8 +57,8 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
 #pragma unroll
         for (int c0 = 0; c0 < N; ++c0) {
             if (c0 & (1 << S)) continue;
-            const int cd = a ? (c0 | (1 << S)) : c0;
-            double fr = re[cd], fi = im[cd];
+            const int c1 = c0 | (1 << S);
+            double fr = a ? re[c1] : re[c0], fi = a ? im[c1] : im[c0];
             fr += __shfl_xor_sync(0xffffffffu, fr, 1 << S);
             fi += __shfl_xor_sync(0xffffffffu, fi, 1 << S);
             if (a == 0 && (uint32_t)c0 == r0) trf += fr;
