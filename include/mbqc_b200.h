@@ -139,6 +139,21 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
                         const void* d_target, double shift, double* d_grad, double* d_cost,
                         int32_t* d_status, void* stream);
 
+/* Data-set averaged cost and its gradient in one call -- the S x 2T pattern evaluations of one
+ * optimiser step of the reference's training loop (docs/tutorials/intro-to-mbqml.rst:35-86:
+ * cost(x) = mean_s [1 - |<t_s|psi(x; in_s)>|^2], differentiated by gradients/_parameter_shift.py:9-25):
+ *     d_cost[p]    = mean_s cost_s(x_p)
+ *     d_grad[p][i] = mean_s (cost_s(x_p + s e_i) - cost_s(x_p - s e_i)) / (2 s)
+ * d_angles [P][stride]; d_inputs [S][2^|I|] complex128 or NULL (|+> inputs); d_targets [S][2^k];
+ * d_grad [P][T]; d_cost [P] / d_status [P] may be NULL.  d_workspace: caller-owned device buffer of
+ * mbqc_psr_grad_dataset_workspace_bytes(plan, P, S) bytes (per-sample gradients before the mean;
+ * the reduction order is fixed, so results are reproducible run to run). */
+int64_t mbqc_psr_grad_dataset_workspace_bytes(const mbqc_plan* plan, int64_t n_vectors, int64_t n_data);
+int mbqc_psr_grad_dataset(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                          const void* d_inputs, const void* d_targets, int64_t n_vectors, int64_t n_data,
+                          double shift, double* d_grad, double* d_cost, int32_t* d_status,
+                          void* d_workspace, void* stream);
+
 /* ---- streaming regime: one large window resident in HBM, one angle set -------------------------
  * Replaces NumpySimulatorSV.reset / measure / run for windows the reference cannot hold (it
  * materialises 2^w x 2^w operators: np_simulator_sv.py:103-128, :164-225, :286-297).  The state is

@@ -65,6 +65,10 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mbqc_psr_grad_dataset_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64]),
+    "mbqc_psr_grad_dataset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_stream_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p, C.c_double, C.c_void_p]),
     "mbqc_stream_steps": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_void_p]),

@@ -1,4 +1,4 @@
-// Register-resident batched density-matrix kernel (window w <= 4): one LANE per row of rho.
+// Register-resident batched density-matrix kernel (window w <= 5): one LANE per row of rho.
 //
 // A sample is handled by 2^w lanes of a warp (2 samples per warp at w = 4); lane r keeps row r of
 // rho (2^w complex numbers) in registers.  For the measurement of slot s the column bit is a
@@ -6,11 +6,12 @@
 //
 //     u_a    = q_{a0} rho_{a0} + q_{a1} rho_{a1}        per lane, a = its row bit     (registers)
 //     sigma  = u_0 + u_1                                 exchange with lane ^ (1 << s) (shuffles)
-//     prob   = sum of Re sigma on the diagonal groups    2^w-lane shuffle reduction
-//     rho'_{ab} = sigma / (2 prob) * sign(r,a) sign(c,b) back into the same registers
+//     2 tr   = sum over lanes of Re sigma[r][r]          2^w-lane shuffle reduction
+//     rho'_{ab} = sigma * sign(r,a) sign(c,b)            back into the same registers
 //
-// No shared-memory traffic, no barriers and no index arithmetic inside the step loop: ~1/3 of the
-// instructions of dm_smem_kernel (which stays for w = 5, 6).  Same arithmetic and quirks
+// rho stays unnormalised between steps (trace carried as a scalar, reset every 2^w steps), so a
+// step has no division.  No shared-memory traffic, no barriers and no index arithmetic inside the
+// step loop: ~1/4 of the instructions of dm_smem_kernel (which stays for w = 6).  Same arithmetic and quirks
 // (np_simulator_dm.py:151-346: outcome 1 iff prob0 < 1e-4, per-step normalisation, NaN status),
 // optional channel folded into the projector coefficients, channel on the output qubits and the
 // output gather done once at the end through a small shared-memory stage.
@@ -19,10 +20,32 @@
 
 namespace mbqc {
 
+// Value of v[pair(r)] for a lane-varying row r: binary select tree over the column bits != S
+// (pair indices enumerate the columns with bit S clear in increasing order).
+template <int W, int S>
+__device__ __forceinline__ double select_diag(const double (&v)[1 << (W - 1)], uint32_t r) {
+    constexpr int NP = 1 << (W - 1);
+    double sel[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) sel[i] = v[i];
+    int n = NP;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        if (j == S) continue;
+        const bool hi = (r >> j) & 1u;
+        n >>= 1;
+#pragma unroll
+        for (int i = 0; i < n; ++i) sel[i] = hi ? sel[2 * i + 1] : sel[2 * i];
+    }
+    return sel[0];
+}
+
+// One measurement of slot S.  rho is kept UNNORMALISED (trace `trc`, uniform over the sample's
+// lanes): the new blocks are +-sigma, so trace' = 2 tr(sigma) and no division is needed per step;
+// prob0 = tr(sigma0) / trc decides the outcome exactly as the reference's normalised state does.
 template <int W, int S>
 __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[1 << W], const MeasCoef& q,
-                                             uint32_t r, uint64_t nbr_mask, int lps_base, bool append,
-                                             int& outcome, int& bad) {
+                                             uint32_t r, uint32_t colpar, double& trc, int& outcome, int& bad) {
     constexpr int N = 1 << W;
     constexpr int NP = N >> 1;
     const uint32_t a = (r >> S) & 1u;
@@ -30,8 +53,6 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
     const double ar = a ? q.q01r : q.q00, ai = a ? -q.q01i : 0.0;
     const double br = a ? q.q11 : q.q01r, bi = a ? 0.0 : q.q01i;
     double sr[NP], si[NP];
-    const uint32_t r0 = r & ~(1u << S);
-    double tr0 = 0.0;
     int p = 0;
 #pragma unroll
     for (int c0 = 0; c0 < N; ++c0) {
@@ -43,52 +64,56 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
         ui += __shfl_xor_sync(0xffffffffu, ui, 1 << S);
         sr[p] = ur;
         si[p] = ui;
-        if (a == 0 && (uint32_t)c0 == r0) tr0 += ur;  // diagonal group, counted once
         ++p;
     }
+    // both lanes of a row pair hold the same sigma, so the all-lane sum is 2 tr(sigma0) = trace'
+    double t2 = select_diag<W, S>(sr, r);
 #pragma unroll
-    for (int o = (1 << W) >> 1; o > 0; o >>= 1) tr0 += __shfl_xor_sync(0xffffffffu, tr0, o);
-    outcome = (tr0 < 1e-4) ? 1 : 0;  // np_simulator_dm.py:335-338
-    double prob = tr0;
+    for (int o = N >> 1; o > 0; o >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+    outcome = (0.5 * t2 < 1e-4 * trc) ? 1 : 0;  // prob0 < 1e-4, np_simulator_dm.py:335-338
     if (__any_sync(0xffffffffu, outcome)) {
         // rare: sigma1 = tr_s(rho) - sigma0, tr_s(rho) = rho_00 + rho_11 (own diagonal block + partner's)
-        double trf = 0.0;
+        double fr[NP], fi[NP];
         p = 0;
 #pragma unroll
         for (int c0 = 0; c0 < N; ++c0) {
             if (c0 & (1 << S)) continue;
             const int c1 = c0 | (1 << S);
-            double fr = a ? re[c1] : re[c0], fi = a ? im[c1] : im[c0];
-            fr += __shfl_xor_sync(0xffffffffu, fr, 1 << S);
-            fi += __shfl_xor_sync(0xffffffffu, fi, 1 << S);
-            if (a == 0 && (uint32_t)c0 == r0) trf += fr;
-            if (outcome) {
-                sr[p] = fr - sr[p];
-                si[p] = fi - si[p];
-            }
+            double xr = a ? re[c1] : re[c0], xi = a ? im[c1] : im[c0];
+            xr += __shfl_xor_sync(0xffffffffu, xr, 1 << S);
+            xi += __shfl_xor_sync(0xffffffffu, xi, 1 << S);
+            fr[p] = xr;
+            fi[p] = xi;
             ++p;
         }
+        double f2 = select_diag<W, S>(fr, r);
 #pragma unroll
-        for (int o = (1 << W) >> 1; o > 0; o >>= 1) trf += __shfl_xor_sync(0xffffffffu, trf, o);
-        if (outcome) prob = trf - tr0;
+        for (int o = N >> 1; o > 0; o >>= 1) f2 += __shfl_xor_sync(0xffffffffu, f2, o);
+        if (outcome) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                sr[i] = fr[i] - sr[i];
+                si[i] = fi[i] - si[i];
+            }
+            t2 = f2 - t2;
+        }
     }
-    if (!(prob > 0.0) || !isfinite(prob)) bad = 1;
-    const double sc = 0.5 / prob;
-    const uint32_t pr = (a & (append ? parity64((uint64_t)r0 & nbr_mask) : 0u)) << 31;
+    if (!(t2 > 0.0) || !isfinite(t2)) bad = 1;
+    trc = t2;
+    // CZ signs with the slot's new |+>: bit c of colpar = parity(c & nbr_mask) (0 for tail steps)
+    const uint32_t pr = (a & (colpar >> r)) << 31;
     p = 0;
 #pragma unroll
     for (int c0 = 0; c0 < N; ++c0) {
         if (c0 & (1 << S)) continue;
         const int c1 = c0 | (1 << S);
-        const double vr = sr[p] * sc, vi = si[p] * sc;
-        const uint32_t pc = append ? (parity64((uint64_t)c0 & nbr_mask) << 31) : 0u;
-        re[c0] = flip_sign(vr, pr);
-        im[c0] = flip_sign(vi, pr);
-        re[c1] = flip_sign(vr, pr ^ pc);
-        im[c1] = flip_sign(vi, pr ^ pc);
+        const uint32_t pc = pr ^ ((colpar << (31 - c0)) & 0x80000000u);
+        re[c0] = flip_sign(sr[p], pr);
+        im[c0] = flip_sign(si[p], pr);
+        re[c1] = flip_sign(sr[p], pc);
+        im[c1] = flip_sign(si[p], pc);
         ++p;
     }
-    (void)lps_base;
 }
 
 template <int W>
@@ -136,9 +161,21 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
     const double* row = p.angles + be * p.stride;
     int bad = 0, took1 = 0;
     double c_mine = 1.0, s_mine = 0.0;
+    double trc = psi.x * psi.x + psi.y * psi.y;  // trace of the (unnormalised) rho
+#pragma unroll
+    for (int o = N >> 1; o > 0; o >>= 1) trc += __shfl_xor_sync(0xffffffffu, trc, o);
     for (int m = 0; m < t.n_steps; ++m) {
         const int within = m % N;
         if (within == 0) {  // lane j of the sample evaluates (cos, sin) of measurement m + j
+            if (m) {  // bring the trace back to 1 (it moves by 2 prob per step)
+                const double sc = 1.0 / trc;
+#pragma unroll
+                for (int c = 0; c < N; ++c) {
+                    re[c] *= sc;
+                    im[c] *= sc;
+                }
+                trc = 1.0;
+            }
             const int mm = m + (int)r;
             c_mine = 1.0;
             s_mine = 0.0;
@@ -153,13 +190,16 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
         const double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
         const StepDev st = p.steps[m];
         const MeasCoef q = meas_coef(st.plane, c, s, t);
-        const bool append = (st.flags & MBQC_STEP_APPEND) != 0;
+        // column-parity table of this step's CZ mask, one bit per lane of the sample (0 for tail steps)
+        const bool odd = (st.flags & MBQC_STEP_APPEND) && parity64((uint64_t)r & st.nbr_mask);
+        const uint32_t colpar = __ballot_sync(0xffffffffu, odd) >> lane_base;
         int outcome = 0;
         switch (st.slot) {
-            case 0: dm_reg_stage<W, 0>(re, im, q, r, st.nbr_mask, lane_base, append, outcome, bad); break;
-            case 1: if constexpr (W > 1) dm_reg_stage<W, 1>(re, im, q, r, st.nbr_mask, lane_base, append, outcome, bad); break;
-            case 2: if constexpr (W > 2) dm_reg_stage<W, 2>(re, im, q, r, st.nbr_mask, lane_base, append, outcome, bad); break;
-            case 3: if constexpr (W > 3) dm_reg_stage<W, 3>(re, im, q, r, st.nbr_mask, lane_base, append, outcome, bad); break;
+            case 0: dm_reg_stage<W, 0>(re, im, q, r, colpar, trc, outcome, bad); break;
+            case 1: if constexpr (W > 1) dm_reg_stage<W, 1>(re, im, q, r, colpar, trc, outcome, bad); break;
+            case 2: if constexpr (W > 2) dm_reg_stage<W, 2>(re, im, q, r, colpar, trc, outcome, bad); break;
+            case 3: if constexpr (W > 3) dm_reg_stage<W, 3>(re, im, q, r, colpar, trc, outcome, bad); break;
+            case 4: if constexpr (W > 4) dm_reg_stage<W, 4>(re, im, q, r, colpar, trc, outcome, bad); break;
             default: break;
         }
         took1 |= outcome;

@@ -18,12 +18,13 @@ __device__ __forceinline__ double sv_reg_cost(const SvBatchParams& p, const RegS
     constexpr int N = 1 << W;
     double re[N], im[N], zr, zi;
     const double n2 = sv_reg_evolve<W, true, true>(p, sm, periodic, b, ang, re, im, zr, zi);
+    const double2* target = p.target + (p.data_count > 0 ? (b << p.tab.n_out) : 0);
     double ar = 0.0, ai = 0.0;  // <t|psi>
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const int d = p.tab.out_dst[i];
         if (d >= 0) {
-            const double2 tg = __ldg(p.target + d);
+            const double2 tg = __ldg(target + d);
             ar = fma(tg.x, re[i], fma(tg.y, im[i], ar));
             ai = fma(tg.x, im[i], fma(-tg.y, re[i], ai));
         }
@@ -44,9 +45,11 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
     const int bl = threadIdx.x / T;
     const int i = threadIdx.x - bl * T;
     const bool live = bl < samples;
+    int64_t arow = 0, item = 0;  // angle row; data item (input / target state) of this sample
     if (live) {  // one angle per thread: a single round of loads for the whole CTA
+        sample_index(p, b0 + bl, arow, item);
         double sn, cs;
-        sincos_cw(__ldg(p.angles + (b0 + bl) * p.stride + i), sn, cs);  // one angle per thread: no table needed
+        sincos_cw(__ldg(p.angles + arow * p.stride + i), sn, cs);  // one angle per thread: no table needed
         l.cs[threadIdx.x] = make_double2(cs, sn);
     }
     cp_async_wait_all();
@@ -58,11 +61,11 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
     double ss, cs;
     sincos(p.shift, &ss, &cs);
     const double2* row = l.cs + bl * T;
-    const double cp = sv_reg_cost<W>(p, sm, periodic, b, AngleStaged{row, 1, T, l.fixed, i, cs, ss});
-    const double cm = sv_reg_cost<W>(p, sm, periodic, b, AngleStaged{row, 1, T, l.fixed, i, cs, -ss});
+    const double cp = sv_reg_cost<W>(p, sm, periodic, item, AngleStaged{row, 1, T, l.fixed, i, cs, ss});
+    const double cm = sv_reg_cost<W>(p, sm, periodic, item, AngleStaged{row, 1, T, l.fixed, i, cs, -ss});
     p.grad[b * T + i] = (cp - cm) / (2.0 * p.shift);
     if (i == 0) {
-        if (p.cost) p.cost[b] = sv_reg_cost<W>(p, sm, periodic, b, AngleStaged{row, 1, T, l.fixed, -1, 1.0, 0.0});
+        if (p.cost) p.cost[b] = sv_reg_cost<W>(p, sm, periodic, item, AngleStaged{row, 1, T, l.fixed, -1, 1.0, 0.0});
         if (p.status) p.status[b] = (cp == cp && cm == cm) ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM;
     }
 }
@@ -76,14 +79,14 @@ __global__ void __launch_bounds__(128) sv_reg_grad_kernel(const __grid_constant_
 // with no phase tracking (the cost is phase invariant) and the unshifted cost for free from the
 // final prefix.  Needs B >= ~100k angle vectors to fill the GPU (thread per vector).
 template <int W>
-__device__ __forceinline__ double fidelity_cost(const SvBatchParams& p, const double (&re)[1 << W],
-                                                const double (&im)[1 << W]) {
+__device__ __forceinline__ double fidelity_cost(const SvBatchParams& p, const double2* __restrict__ target,
+                                                const double (&re)[1 << W], const double (&im)[1 << W]) {
     double ar = 0.0, ai = 0.0, n2 = 0.0;
 #pragma unroll
     for (int i = 0; i < (1 << W); ++i) {
         const int d = p.tab.out_dst[i];
         if (d >= 0) {
-            const double2 tg = __ldg(p.target + d);
+            const double2 tg = __ldg(target + d);
             ar = fma(tg.x, re[i], fma(tg.y, im[i], ar));
             ai = fma(tg.x, im[i], fma(-tg.y, re[i], ai));
             n2 = fma(re[i], re[i], fma(im[i], im[i], n2));
@@ -117,10 +120,15 @@ __global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_co
     const int64_t b = (int64_t)blockIdx.x * kRegThreads + threadIdx.x;
     const bool live = b < p.batch;
     stage_reg_tables(pp, l);
-    if (live) fetch_own_row(p.angles + b * p.stride, l.cs + threadIdx.x, T, kRegThreads);
+    int64_t arow = 0, item = 0;
+    if (live) {
+        sample_index(p, b, arow, item);
+        fetch_own_row(p.angles + arow * p.stride, l.cs + threadIdx.x, T, kRegThreads);
+    }
     cp_async_wait_all();
     __syncthreads();
     if (!live) return;
+    const double2* target = p.target + (p.data_count > 0 ? (item << t.n_out) : 0);
     double2* cs = l.cs + threadIdx.x;
     convert_own_row(cs, T, kRegThreads, l.trig);
     double2* pf = prefix + threadIdx.x;
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_co
     sincos(p.shift, &sh_s, &sh_c);
     // seed -> prefix
     {
-        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (b << t.n_in) : 0);
+        const double2* in = p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (item << t.n_in) : 0);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t sb = (t.init_sign << (31 - i)) & 0x80000000u;
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_co
                     reg_step_any<W>(re, im, (int)(l.cols[m2] >> 16), c2, s2, l.signs + m2 * pp.reg.sign_pitch);
                     if (((m2 - m) & 15) == 15) rescale_state<W>(re, im);
                 }
-                cost[sgn] = fidelity_cost<W>(p, re, im);
+                cost[sgn] = fidelity_cost<W>(p, target, re, im);
             }
             p.grad[b * T + col] = (cost[0] - cost[1]) / (2.0 * p.shift);
             bad |= !(cost[0] == cost[0]) || !(cost[1] == cost[1]);
@@ -195,9 +203,58 @@ __global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < N; ++i) pf[i * kRegThreads] = make_double2(re[i], im[i]);
     }
-    const double c0 = fidelity_cost<W>(p, re, im);
+    const double c0 = fidelity_cost<W>(p, target, re, im);
     if (p.cost) p.cost[b] = c0;
     if (p.status) p.status[b] = (bad || !(c0 == c0)) ? MBQC_STATUS_BAD_NORM : MBQC_STATUS_OK;
+}
+
+// ---- data-set average ----------------------------------------------------------------------------
+// grad[p][i] = mean_s ws_grad[p*S + s][i], cost[p] = mean_s ws_cost[p*S + s], status[p] = OR_s.
+// One CTA per parameter vector p; thread (lane, col) sums a strided subset of the data items in a
+// fixed order (deterministic result), lanes are combined through shared memory.
+constexpr int kReduceThreads = 256;
+
+__global__ void __launch_bounds__(kReduceThreads) grad_dataset_reduce_kernel(
+    const double* __restrict__ ws_grad, const double* __restrict__ ws_cost, const int32_t* __restrict__ ws_status,
+    int64_t S, int T, double* __restrict__ grad, double* __restrict__ cost, int32_t* __restrict__ status) {
+    __shared__ double part[kReduceThreads];
+    __shared__ int32_t st_any;
+    const int64_t p = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int Tc = T < kReduceThreads ? T : kReduceThreads;  // columns handled per sweep
+    const int L = kReduceThreads / Tc;                        // lanes per column
+    const int lane = tid / Tc, c0 = tid - lane * Tc;
+    const double inv = 1.0 / (double)S;
+    if (tid == 0) st_any = 0;
+    for (int base = 0; base < T; base += Tc) {
+        const int col = base + c0;
+        double sum = 0.0;
+        if (lane < L && col < T) {
+            const double* src = ws_grad + p * S * T + col;
+            for (int64_t s = lane; s < S; s += L) sum += src[s * T];
+        }
+        part[tid] = sum;
+        __syncthreads();
+        if (lane == 0 && col < T) {
+            for (int j = 1; j < L; ++j) sum += part[j * Tc + c0];
+            grad[p * T + col] = sum * inv;
+        }
+        __syncthreads();
+    }
+    double csum = 0.0;
+    int32_t sany = 0;
+    for (int64_t s = tid; s < S; s += kReduceThreads) {
+        csum += ws_cost[p * S + s];
+        sany |= ws_status[p * S + s];
+    }
+    part[tid] = csum;
+    if (sany) atomicOr(&st_any, sany);
+    __syncthreads();
+    if (tid == 0) {
+        for (int j = 1; j < kReduceThreads; ++j) csum += part[j];
+        if (cost) cost[p] = csum * inv;
+        if (status) status[p] = st_any;
+    }
 }
 
 }  // namespace mbqc

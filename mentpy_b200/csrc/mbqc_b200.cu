@@ -516,9 +516,9 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
     p.out = (double2*)d_out;
     p.outcomes = d_outcomes;
     p.status = d_status;
-    // w <= 4: one lane per row of rho, registers + shuffles; w = 5, 6: rho in shared memory
+    // w <= 5: one lane per row of rho, registers + shuffles; w = 6: rho in shared memory
     const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
-    if (w <= 4 && !(force && !strcmp(force, "smem"))) {
+    if (w <= 5 && !(force && !strcmp(force, "smem"))) {
         const int n = 1 << w, spb = 4 * (32 / n);
         const size_t smem = (size_t)spb * n * n * sizeof(double2);
         const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
@@ -527,7 +527,11 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
             case 1: dm_reg_kernel<1><<<blocks, 128, smem, st>>>(p); break;
             case 2: dm_reg_kernel<2><<<blocks, 128, smem, st>>>(p); break;
             case 3: dm_reg_kernel<3><<<blocks, 128, smem, st>>>(p); break;
-            default: dm_reg_kernel<4><<<blocks, 128, smem, st>>>(p); break;
+            case 4: dm_reg_kernel<4><<<blocks, 128, smem, st>>>(p); break;
+            default:
+                CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dm_reg_kernel<5><<<blocks, 128, smem, st>>>(p);
+                break;
         }
         return after_launch("dm_reg_kernel");
     }
@@ -546,31 +550,17 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
     return after_launch("dm_smem_kernel");
 }
 
-int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
-                        const void* d_inputs, int32_t input_mode, int64_t batch,
-                        const void* d_target, double shift, double* d_grad, double* d_cost,
-                        int32_t* d_status, void* stream) {
-    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_grad);
-    if (rc) return rc;
-    if (!d_target) return fail(MBQC_E_ARG, "d_target is NULL");
-    if (!(shift != 0.0)) return fail(MBQC_E_ARG, "shift must be non-zero");
+}  // extern "C"
+
+namespace {
+// Shared by the per-sample and the data-set entry points: p.batch samples, p.grad [batch][T].
+int launch_psr_grad(const mbqc_plan* plan, const SvBatchParams& p, cudaStream_t st) {
+    int rc = MBQC_OK;
     const int w = plan->tab.window;
-    if (w > MBQC_MAX_WINDOW_REG)
-        return fail(MBQC_E_UNSUPPORTED, "fused gradient covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
-    for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
-            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
-    if (batch == 0 || plan->tab.n_angles == 0) return MBQC_OK;
-    SvBatchParams p;
-    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, nullptr, d_status);
-    p.target = (const double2*)d_target;
-    p.shift = shift;
-    p.grad = d_grad;
-    p.cost = d_cost;
+    const int64_t batch = p.batch;
     const int T = plan->tab.n_angles;
     SvRegParams rp;
     fill_reg_params(rp, p, plan);
-    cudaStream_t st = (cudaStream_t)stream;
     const size_t tables = reg_smem_tables_bytes(plan->tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
     // Large batches: one thread per angle vector with prefix sharing (about half the measurements).
     // Small batches (or tiles that do not fit shared memory): one thread per (vector, parameter).
@@ -615,6 +605,74 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     }
     if (rc) return rc;
     return after_launch("sv_reg_grad_kernel");
+}
+
+int check_grad_plan(const mbqc_plan* plan, const void* d_target, double shift) {
+    if (!d_target) return fail(MBQC_E_ARG, "d_target is NULL");
+    if (!(shift != 0.0)) return fail(MBQC_E_ARG, "shift must be non-zero");
+    const int w = plan->tab.window;
+    if (w > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "fused gradient covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
+    return MBQC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                        const void* d_inputs, int32_t input_mode, int64_t batch,
+                        const void* d_target, double shift, double* d_grad, double* d_cost,
+                        int32_t* d_status, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_grad);
+    if (rc) return rc;
+    if ((rc = check_grad_plan(plan, d_target, shift))) return rc;
+    if (batch == 0 || plan->tab.n_angles == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, nullptr, d_status);
+    p.target = (const double2*)d_target;
+    p.shift = shift;
+    p.grad = d_grad;
+    p.cost = d_cost;
+    return launch_psr_grad(plan, p, (cudaStream_t)stream);
+}
+
+int64_t mbqc_psr_grad_dataset_workspace_bytes(const mbqc_plan* plan, int64_t n_vectors, int64_t n_data) {
+    if (!plan || n_vectors < 0 || n_data < 0) return -1;
+    const int64_t n = n_vectors * n_data;
+    return ((n * ((int64_t)plan->tab.n_angles * 8 + 8 + 4) + 255) / 256) * 256;
+}
+
+int mbqc_psr_grad_dataset(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                          const void* d_inputs, const void* d_targets, int64_t n_vectors, int64_t n_data,
+                          double shift, double* d_grad, double* d_cost, int32_t* d_status,
+                          void* d_workspace, void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, d_inputs ? MBQC_INPUT_BATCH : MBQC_INPUT_PLUS,
+                              n_vectors, d_grad);
+    if (rc) return rc;
+    if ((rc = check_grad_plan(plan, d_targets, shift))) return rc;
+    if (n_data <= 0) return fail(MBQC_E_ARG, "n_data must be positive (got %lld)", (long long)n_data);
+    if (!d_workspace) return fail(MBQC_E_ARG, "d_workspace is NULL");
+    const int T = plan->tab.n_angles;
+    if (n_vectors == 0 || T == 0) return MBQC_OK;
+    const int64_t n = n_vectors * n_data;
+    double* ws_grad = (double*)d_workspace;
+    double* ws_cost = ws_grad + n * T;
+    int32_t* ws_status = (int32_t*)(ws_cost + n);
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, d_inputs ? MBQC_INPUT_BATCH : MBQC_INPUT_PLUS, n,
+                   nullptr, ws_status);
+    p.target = (const double2*)d_targets;
+    p.shift = shift;
+    p.grad = ws_grad;
+    p.cost = ws_cost;
+    p.data_count = n_data;
+    if ((rc = launch_psr_grad(plan, p, (cudaStream_t)stream))) return rc;
+    grad_dataset_reduce_kernel<<<(unsigned)n_vectors, kReduceThreads, 0, (cudaStream_t)stream>>>(
+        ws_grad, ws_cost, ws_status, n_data, T, d_grad, d_cost, d_status);
+    return after_launch("grad_dataset_reduce_kernel");
 }
 
 }  // extern "C"

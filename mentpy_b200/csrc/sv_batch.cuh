@@ -28,7 +28,20 @@ struct SvBatchParams {
     double shift;
     double* __restrict__ grad;
     double* __restrict__ cost;
+    // data-set mode of the gradient kernels (data_count = S > 0): sample b = p * S + s uses angle
+    // row p, input state s and target state s; 0 = every sample has its own row / input, one target
+    int64_t data_count;
 };
+
+// (angle row, data item) of sample b
+__device__ __forceinline__ void sample_index(const SvBatchParams& p, int64_t b, int64_t& row, int64_t& item) {
+    row = b;
+    item = b;
+    if (p.data_count > 0) {
+        row = b / p.data_count;
+        item = b - row * p.data_count;
+    }
+}
 
 // ---- shared-memory variant for 6 <= w <= 12 -----------------------------------------------------
 // A group of TPS = 2^tps_log2 threads cooperates on one sample; SPB samples per CTA.

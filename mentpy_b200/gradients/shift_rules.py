@@ -8,6 +8,8 @@ factor); that formula is kept verbatim.
 Acceleration hooks (additive):
   * a cost object exposing `batch(X) -> costs` (X is [n, T]) gets all its shifted evaluations in
     ONE call instead of 2T (or 4T^2) sequential ones -- see `BatchedCost` users in optimizers;
+  * a cost object exposing `shift_gradient(x, shift)` (BatchedFidelityCost on a CUDA SV backend)
+    gets the whole central difference from the fused data-set kernel (mbqc_psr_grad_dataset);
   * `psr_gradient_batched` runs B gradients of the fidelity cost 1 - |<t|psi(x)>|^2 entirely in
     the fused CUDA kernel (mbqc_psr_grad_batch), never materialising shifted angle vectors.
 """
@@ -24,6 +26,8 @@ def _evaluate_many(cost, points):
 
 
 def psr_gradient(cost, x, shift=1.5):
+    if hasattr(cost, "shift_gradient"):  # fused kernel: all 2T x S evaluations in one launch
+        return np.asarray(cost.shift_gradient(x, shift), dtype=float)
     x = np.asarray(x, dtype=float)
     n = len(x)
     eye = np.eye(n)
@@ -51,6 +55,8 @@ def fd_gradient(f, x, h=1e-5, type="central"):
     n = len(x)
     eye = np.eye(n)
     if type == "central":
+        if hasattr(f, "shift_gradient"):
+            return np.asarray(f.shift_gradient(x, h), dtype=float)
         v = _evaluate_many(f, np.concatenate([x + h * eye, x - h * eye]))
         return (v[:n] - v[n:]) / (2 * h)
     if type == "forward":
@@ -130,5 +136,58 @@ def psr_gradient_batched(simulator, angles, target, shift=1.5, input_states=None
             g = grad.cpu().numpy()
             sim._check_status(status)
             return (g, cost.cpu().numpy()) if return_cost else g
+        sim.last_status = status
+        return (grad, cost) if return_cost else grad
+
+
+def psr_gradient_dataset(simulator, angles, targets, input_states=None, shift=1.5, return_cost=False):
+    """Gradient of the data-set averaged cost  mean_s [1 - |<t_s|psi_out(x; in_s)>|^2]  for P angle
+    vectors in one fused launch (mbqc_psr_grad_dataset): the S x 2T `ps.reset(); ps(x)` calls that
+    one optimiser step of docs/tutorials/intro-to-mbqml.rst:35-86 makes per parameter vector.
+
+    angles [P,T] (or [T]) numpy / torch CUDA; targets [S,2^k]; input_states [S,2^|I|] or None
+    (|+> inputs, S = len(targets)).  Returns grad [P,T] (and cost [P]), numpy in -> numpy out."""
+    import torch
+
+    from .. import _lib
+
+    sim = getattr(simulator, "simulator", simulator)
+    dev = sim._dev()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        squeeze = (angles.dim() if isinstance(angles, torch.Tensor) else np.ndim(angles)) == 1
+        a, on_host = sim._stage_angles(angles, dev)
+        P, T = a.shape
+        dplan = sim._full_plan()
+
+        def stage(x, width, what):
+            t = x.to(device=dev, dtype=torch.complex128) if isinstance(x, torch.Tensor) \
+                else torch.as_tensor(np.ascontiguousarray(np.atleast_2d(x), dtype=np.complex128)).to(dev)
+            t = t.reshape(-1, t.shape[-1]).contiguous()
+            if t.shape[1] != width:
+                raise ValueError(f"{what} must have {width} amplitudes per state (got {t.shape[1]})")
+            return t
+
+        tg = stage(targets, 2 ** dplan.n_out, "targets")
+        S = tg.shape[0]
+        inp = None if input_states is None else stage(input_states, 2 ** dplan.n_in, "input_states")
+        if inp is not None and inp.shape[0] != S:
+            raise ValueError("need one target state per input state")
+        grad = torch.empty((P, T), dtype=torch.float64, device=dev)
+        cost = torch.empty(P, dtype=torch.float64, device=dev)
+        status = torch.empty(P, dtype=torch.int32, device=dev)
+        nbytes = lib.mbqc_psr_grad_dataset_workspace_bytes(dplan.handle, P, S)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mbqc_psr_grad_dataset(dplan.handle, a.data_ptr(), (a.stride(0) if P > 1 else max(T, 1)),
+                                             None if inp is None else inp.data_ptr(), tg.data_ptr(), P, S,
+                                             C.c_double(shift), grad.data_ptr(), cost.data_ptr(),
+                                             status.data_ptr(), ws.data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+        if squeeze:
+            grad, cost = grad[0], cost[0]
+        if on_host:
+            sim._check_status(status)
+            g, c = grad.cpu().numpy(), cost.cpu().numpy()
+            return (g, c) if return_cost else g
         sim.last_status = status
         return (grad, cost) if return_cost else grad

@@ -194,3 +194,22 @@ class BatchedFidelityCost:
 
     def __call__(self, x):
         return float(self.batch(np.asarray(x)[None, :])[0])
+
+    def _fused_ok(self):
+        from .. import _lib
+
+        plan = getattr(self.sim, "plan", None)
+        return hasattr(self.sim, "_full_plan") and plan is not None and not getattr(plan, "mixed", False) \
+            and plan.window <= _lib.MAX_WINDOW_REG and getattr(self.sim, "dtype", "complex128") == "complex128"
+
+    def shift_gradient(self, x, shift=1.5):
+        """(cost(x + s e_i) - cost(x - s e_i)) / (2 s) for every i -- the reference's psr / central
+        fd formula -- from the fused data-set kernel; falls back to `batch` on other backends."""
+        if not self._fused_ok():
+            x = np.asarray(x, dtype=float)
+            eye = np.eye(len(x))
+            v = self.batch(np.concatenate([x + shift * eye, x - shift * eye]))
+            return (v[: len(x)] - v[len(x):]) / (2 * shift)
+        from ..gradients import psr_gradient_dataset
+
+        return psr_gradient_dataset(self.sim, x, self.targets, self.inputs, shift=shift)

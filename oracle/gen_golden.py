@@ -239,8 +239,36 @@ def main():
     random.seed(7)
     rcd = mp.optimizers.RCDOptimizer(step_size=0.3, adaptive=True)
     opt_rec["rcd_seed7_6"] = rcd.optimize(cost_s, xs.copy(), num_iters=6).tolist()
+    # data-set averaged training cost of docs/tutorials/intro-to-mbqml.rst:16-86 (same pattern:
+    # muta(2, 1, one_column=True) with nodes 3 and 8 measured in X; numpy-sv instead of the absent
+    # PennyLane backend; fidelity <t|rho|t> restated because calculator.fidelity is PennyLane's)
+    gs_d = mp.templates.muta(2, 1, one_column=True)
+    gs_d[3] = mp.Ment("X")
+    gs_d[8] = mp.Ment("X")
+    ps_d = mp.PatternSimulator(gs_d, backend="numpy-sv")
+    from scipy.stats import unitary_group
+
+    u1 = unitary_group.rvs(2, random_state=77)
+    gate = np.kron(u1 / np.sqrt(np.linalg.det(u1)), np.eye(2))
+    xs_d = [haar_state(2, 100 + i) for i in range(6)]
+    ys_d = [gate @ v for v in xs_d]
+
+    def cost_d(thetas):
+        acc = 0.0
+        for vin, vt in zip(xs_d, ys_d):
+            ps_d.reset(input_state=vin)
+            rho = ps_d(thetas)
+            acc += 1 - float(np.real(vt.conj() @ rho @ vt))
+        return acc / len(xs_d)
+
+    xd = np.random.default_rng(6).uniform(0, 2 * np.pi, len(gs_d.trainable_nodes))
+    data_rec = {"spec": ("muta", [2, 1], {"one_column": True}), "x_nodes": [3, 8], "x": xd.tolist(),
+                "inputs": cplx(np.array(xs_d)), "targets": cplx(np.array(ys_d)), "cost": cost_d(xd),
+                "psr": mp.gradients.get_gradient(cost_d, xd).tolist(),
+                "fd": mp.gradients.get_gradient(cost_d, xd, method="fd").tolist(),
+                "adam_4": mp.optimizers.AdamOptimizer(step_size=0.08).optimize(cost_d, xd.copy(), num_iters=4).tolist()}
     with open(os.path.join(GOLDEN, "gradients.json"), "w") as f:
-        json.dump({"generator": "oracle/gen_golden.py", "c4": rec, "small": opt_rec}, f)
+        json.dump({"generator": "oracle/gen_golden.py", "c4": rec, "small": opt_rec, "dataset": data_rec}, f)
 
     # 4. helper known answers (calculator / Ment)
     helpers = {}

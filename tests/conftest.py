@@ -48,3 +48,15 @@ def golden_sim_cases():
 @pytest.fixture(scope="session")
 def golden_structures():
     return load_golden("structures.json")["records"]
+
+
+def build_spec(spec):
+    """Circuit for a golden `spec` = (template | "vstack" | "hstack" | "merge", args, kwargs)."""
+    import mentpy_b200 as mb
+
+    name, args, kwargs = spec
+    if name in ("vstack", "hstack"):
+        return getattr(mb, name)([build_spec(a) for a in args])
+    if name == "merge":
+        return mb.merge(build_spec(args[0]), build_spec(args[1]), along=[tuple(x) for x in args[2]])
+    return getattr(mb.templates, name)(*args, **kwargs)

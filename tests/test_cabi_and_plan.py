@@ -9,7 +9,7 @@ import pytest
 import mentpy_b200 as mb
 from mentpy_b200 import _lib
 from mentpy_b200.plan import kraus_set, lower, noise_from_kraus, window_is_valid
-from conftest import ROOT, load_golden
+from conftest import ROOT, build_spec, load_golden
 from oracle.pattern_data import PatternData
 
 
@@ -51,8 +51,7 @@ def test_lowering_matches_reference_window_bookkeeping():
     """Replay the slot plan on the host and compare with the reference's shifting window
     (np_simulator_sv.py:130-142, :207-223) recorded in the golden patterns."""
     for rec in load_golden("structures.json")["records"]:
-        name, args, kwargs = rec["spec"]
-        gs = getattr(mb.templates, name)(*args, **kwargs)
+        gs = build_spec(rec["spec"])
         pat = PatternData.from_json(rec["pattern"])
         n_meas = len(pat.measurement_order) - len(pat.output_nodes)
         for w in {len(pat.input_nodes) + 1, min(len(pat.input_nodes) + 3, n_meas)}:

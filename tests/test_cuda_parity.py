@@ -552,12 +552,12 @@ def test_calculator_helpers_match_reference():
 
 
 def test_dm_kernels_agree(monkeypatch):
-    """The register/shuffle DM kernel (w <= 4) and the shared-memory DM kernel give the same
+    """The register/shuffle DM kernel (w <= 5) and the shared-memory DM kernel give the same
     states and outcome records (incl. noise, XZ/YZ planes, Haar inputs, outcome-1 branch)."""
     from scipy.stats import unitary_group
 
     rng = np.random.default_rng(51)
-    for name, args, w in (("grid_cluster", [3, 8], None), ("grid_cluster", [2, 5], 4), ("linear_cluster", [6], 3),
+    for name, args, w in (("grid_cluster", [3, 8], None), ("grid_cluster", [2, 5], 4), ("grid_cluster", [4, 4], None), ("linear_cluster", [6], 3),
                           ("linear_cluster", [5], None), ("many_wires", [[3, 3]], 2)):
         gs = getattr(mb.templates, name)(*args)
         if name == "grid_cluster":

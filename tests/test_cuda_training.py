@@ -80,3 +80,72 @@ def test_device_resident_adam_and_sgd_match_reference_trajectories():
     _, c0 = mb.optimizers.adam_optimize_batched(ps, X0, tgt, num_iters=0, return_cost=True)
     _, c1 = mb.optimizers.adam_optimize_batched(ps, X0, tgt, num_iters=40, return_cost=True)
     assert c1.mean() < c0.mean() - 0.1
+
+
+def _dataset_circuit(d):
+    name, args, kwargs = d["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    for v in d["x_nodes"]:
+        gs[v] = mb.Ment("X")
+    return gs
+
+
+def test_fused_dataset_gradient_matches_reference(monkeypatch):
+    """mbqc_psr_grad_dataset (both gradient kernels) against the reference's recorded cost, psr and
+    fd gradients and Adam trajectory for the tutorial's data-set averaged infidelity."""
+    d = G["dataset"]
+    gs = _dataset_circuit(d)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    ins, tgts, x = from_cplx(d["inputs"]), from_cplx(d["targets"]), np.asarray(d["x"])
+    for kern in ("pairs", "prefix"):
+        monkeypatch.setenv("MBQC_GRAD_KERNEL", kern)
+        g, c = mb.gradients.psr_gradient_dataset(ps, x, tgts, ins, return_cost=True)
+        assert g.shape == x.shape and abs(float(c) - d["cost"]) < 1e-12
+        assert np.allclose(g, d["psr"], atol=1e-11, rtol=0)
+        gfd = mb.gradients.psr_gradient_dataset(ps, x, tgts, ins, shift=1e-5)
+        assert np.allclose(gfd, d["fd"], atol=1e-6, rtol=0)
+    monkeypatch.delenv("MBQC_GRAD_KERNEL")
+    cost = mb.optimizers.BatchedFidelityCost(ps, tgts, input_states=ins)
+    assert abs(cost(x) - d["cost"]) < 1e-12
+    assert np.allclose(mb.gradients.get_gradient(cost, x), d["psr"], atol=1e-11, rtol=0)          # fused hook
+    assert np.allclose(mb.gradients.get_gradient(cost, x, method="fd"), d["fd"], atol=1e-6, rtol=0)
+    got = mb.optimizers.AdamOptimizer(step_size=0.08).optimize(cost, x.copy(), num_iters=4)
+    assert np.allclose(got, d["adam_4"], atol=1e-9, rtol=0)
+    # device-resident loop, several parameter vectors at once; row 0 is the golden start
+    X0 = np.vstack([x, np.random.default_rng(2).uniform(0, 2 * np.pi, (40, len(x)))])
+    out, cst = mb.optimizers.adam_optimize_batched(ps, X0, tgts, num_iters=4, step_size=0.08, input_states=ins,
+                                                   dataset=True, return_cost=True)
+    assert np.allclose(out[0], d["adam_4"], atol=1e-9, rtol=0)
+    assert abs(cst[0] - cost(np.asarray(d["adam_4"]))) < 1e-9
+
+
+def test_fused_dataset_gradient_properties():
+    """P vectors x S items in one launch == per-vector calls == mean of per-sample gradients;
+    |+> inputs when input_states is None; argument errors."""
+    from scipy.stats import unitary_group
+
+    gs = mb.templates.grid_cluster(3, 4)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    T, rng = len(gs.trainable_nodes), np.random.default_rng(9)
+    P, S = 37, 300   # P * S > 32768 / 3: exercise both kernel choices below
+    X = rng.uniform(0, 2 * np.pi, (P, T))
+    ins = np.stack([unitary_group.rvs(8, random_state=s)[:, 0] for s in range(S)])
+    tgts = np.stack([unitary_group.rvs(8, random_state=1000 + s)[:, 0] for s in range(S)])
+    g, c = mb.gradients.psr_gradient_dataset(ps, X, tgts, ins, return_cost=True)
+    assert g.shape == (P, T) and c.shape == (P,)
+    for p in (0, 17, 36):
+        gp, cp = mb.gradients.psr_gradient_dataset(ps, X[p], tgts, ins, return_cost=True)
+        assert np.allclose(gp, g[p], atol=1e-13) and abs(cp - c[p]) < 1e-13
+        per = np.stack([mb.gradients.psr_gradient_batched(ps, X[p][None], tgts[s], input_states=ins[s][None])[0]
+                        for s in range(0, S, 50)])
+        sub = mb.gradients.psr_gradient_dataset(ps, X[p], tgts[::50], ins[::50])
+        assert np.allclose(per.mean(axis=0), sub, atol=1e-13)
+    big = mb.gradients.psr_gradient_dataset(ps, np.repeat(X, 4, axis=0), tgts, ins)  # 44,400 samples: prefix kernel
+    assert np.allclose(big[::4], g, atol=1e-12)
+    plus = mb.gradients.psr_gradient_dataset(ps, X[:3], tgts[:5])
+    want = np.mean([mb.gradients.psr_gradient_batched(ps, X[:3], tgts[s]) for s in range(5)], axis=0)
+    assert np.allclose(plus, want, atol=1e-13)
+    with pytest.raises(ValueError):
+        mb.gradients.psr_gradient_dataset(ps, X, tgts, ins[:-1])
+    with pytest.raises(ValueError):
+        mb.gradients.psr_gradient_dataset(ps, X, tgts[:, :4], None)

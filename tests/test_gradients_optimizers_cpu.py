@@ -71,3 +71,37 @@ def test_optimizers_match_reference_trajectories():
     assert len(norms) == 2 and x.shape == x0.shape
     var = mb.optimizers.compute_gradient_variance(cost, x0, mb.gradients.get_gradient, num_samples=2)
     assert np.allclose(var, 0)
+
+
+def _dataset_circuit(d):
+    name, args, kwargs = d["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    for v in d["x_nodes"]:
+        gs[v] = mb.Ment("X")
+    return gs
+
+
+def test_dataset_averaged_cost_matches_reference():
+    """The tutorial's data-set averaged infidelity (docs/tutorials/intro-to-mbqml.rst:35-54) and its
+    psr / fd gradients + 4 Adam steps, oracle-evaluated, against the reference's recorded values."""
+    d = G["dataset"]
+    pat = PatternData.from_circuit(_dataset_circuit(d))
+    ins, tgts = from_cplx(d["inputs"]), from_cplx(d["targets"])
+    S = len(ins)
+
+    class Cost:
+        def batch(self, X):
+            X = np.atleast_2d(X)
+            psi = matrix_free.run_sv_batch(pat, np.repeat(X, S, axis=0), input_states=np.tile(ins, (len(X), 1)))
+            fid = np.abs(np.einsum("nsk,sk->ns", psi.reshape(len(X), S, -1), tgts.conj())) ** 2
+            return 1 - fid.mean(axis=1)
+
+        def __call__(self, x):
+            return float(self.batch(np.asarray(x)[None])[0])
+
+    cost, x = Cost(), np.asarray(d["x"])
+    assert abs(cost(x) - d["cost"]) < 1e-12
+    assert np.allclose(mb.gradients.get_gradient(cost, x), d["psr"], atol=1e-11, rtol=0)
+    assert np.allclose(mb.gradients.get_gradient(cost, x, method="fd"), d["fd"], atol=1e-6, rtol=0)
+    got = mb.optimizers.AdamOptimizer(step_size=0.08).optimize(cost, x.copy(), num_iters=4)
+    assert np.allclose(got, d["adam_4"], atol=1e-9, rtol=0)

@@ -4,7 +4,7 @@ trainable order) must be bit-exact with tables dumped from the unmodified refere
 import pytest
 
 import mentpy_b200 as mb
-from conftest import load_golden
+from conftest import build_spec, load_golden
 
 RECORDS = load_golden("structures.json")["records"]
 
@@ -13,13 +13,7 @@ def _id(r):
     return f"{r['spec'][0]}{r['spec'][1]}{r['spec'][2] or ''}"
 
 
-def _build(spec):
-    name, args, kwargs = spec
-    if name in ("vstack", "hstack"):
-        return getattr(mb, name)([_build(a) for a in args])
-    if name == "merge":
-        return mb.merge(_build(args[0]), _build(args[1]), along=[tuple(x) for x in args[2]])
-    return getattr(mb.templates, name)(*args, **kwargs)
+_build = build_spec
 
 
 @pytest.mark.parametrize("rec", RECORDS, ids=[_id(r) for r in RECORDS])
