@@ -291,6 +291,7 @@ class DevicePlan:
                                         C.byref(handle)))
         self.handle = handle
         self.n_out = len(out_slot)
+        self.n_in = len(plan.input_slot)
         self.n_steps = len(steps)
         self._lib = lib
 
