@@ -81,6 +81,19 @@ typedef struct mbqc_noise {
     double coh_d;
 } mbqc_noise;
 
+/* Flow corrections of one measurement step for sampled runs (force0 = False; the reference raises
+ * NotImplementedError, np_simulator_sv.py:50-51; rule: pennylane_simulator.py:145-153).  The
+ * kernels keep the last 32 outcomes of a sample in a shift register (bit d = outcome of step
+ * m-1-d): xdep / zdep select the outcomes that put a pending X / Z on the qubit measured at this
+ * step (its XY angle becomes (-1)^a theta + b pi); outx / outz name the output qubits (bit q =
+ * q-th output) whose X / Z byproduct toggles when THIS step's outcome is 1. */
+typedef struct mbqc_feedforward {
+    uint32_t xdep, zdep, outx, outz;
+} mbqc_feedforward;
+
+#define MBQC_OUTCOMES_SAMPLE 0 /* draw outcomes from the Born rule (Philox4x32-10, stateless) */
+#define MBQC_OUTCOMES_FORCED 1 /* read the outcome record from d_outcomes */
+
 typedef struct mbqc_plan mbqc_plan;
 
 /* Lowered pattern.  Replaces the per-run bookkeeping of NumpySimulatorSV.__init__/reset
@@ -129,6 +142,30 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
 int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
                       int8_t* d_outcomes, int32_t* d_status, void* stream);
+
+/* Attach the feed-forward table (n_steps records) to a plan.  Call once, right after
+ * mbqc_plan_create and before the plan is shared between threads. */
+int mbqc_plan_set_feedforward(mbqc_plan* plan, const mbqc_feedforward* ff, int32_t n_steps);
+
+/* Sampled twins of mbqc_run_batch_sv / _dm (window <= 5, XY-plane steps): every measurement takes
+ * outcome 0 with its Born probability -- uniform draw = Philox4x32-10 with key `seed` and counter
+ * (sample_offset + b, step), so a sample's record does not depend on how the batch is split -- or
+ * the outcome given in d_outcomes (MBQC_OUTCOMES_FORCED); later angles adapt through the plan's
+ * feed-forward table; with correct != 0 the byproduct X^a Z^b is applied to the output register,
+ * after which a noiseless sample equals the deterministic (force0) state up to a global phase.
+ * d_out: [B][2^k] (sv) / [B][2^k][2^k] (dm) complex128.  Optional outputs (NULL to skip):
+ * d_outcomes [B][n_steps] int8 (input when forced), d_byproducts [B] (x bits | z bits << 16),
+ * d_prob [B] probability of the record, d_status [B]. */
+int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, int32_t outcome_mode, int32_t correct, void* d_out,
+                              int8_t* d_outcomes, uint32_t* d_byproducts, double* d_prob, int32_t* d_status,
+                              void* stream);
+int mbqc_run_batch_dm_sampled(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, int32_t outcome_mode, int32_t correct, void* d_out,
+                              int8_t* d_outcomes, uint32_t* d_byproducts, double* d_prob, int32_t* d_status,
+                              void* stream);
 
 /* Batched parameter-shift / central-difference gradient of cost(x) = 1 - |<target|psi(x)>|^2:
  * grad[b][i] = (cost(x_b + s e_i) - cost(x_b - s e_i)) / (2 s)

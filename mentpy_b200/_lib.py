@@ -14,6 +14,7 @@ PLANE_XY, PLANE_XZ, PLANE_YZ = 0, 1, 2
 STEP_APPEND = 1
 STATUS_BAD_NORM, STATUS_OUTCOME1 = 1, 2
 OUT_SV, OUT_DM = 0, 1
+OUTCOMES_SAMPLE, OUTCOMES_FORCED = 0, 1
 INPUT_PLUS, INPUT_SHARED, INPUT_BATCH = 0, 1, 2
 MAX_WINDOW_REG, MAX_WINDOW_SMEM_SV, MAX_WINDOW_SMEM_DM, MAX_WINDOW = 5, 12, 6, 40
 MAX_IO = 16
@@ -23,6 +24,10 @@ class Step(C.Structure):
     _fields_ = [("slot", C.c_int32), ("angle_idx", C.c_int32), ("plane", C.c_int32),
                 ("flags", C.c_uint32), ("fixed_cos", C.c_double), ("fixed_sin", C.c_double),
                 ("nbr_mask", C.c_uint64)]
+
+
+class FeedForwardC(C.Structure):
+    _fields_ = [("xdep", C.c_uint32), ("zdep", C.c_uint32), ("outx", C.c_uint32), ("outz", C.c_uint32)]
 
 
 STREAM_MAX_FUSE, STREAM_MAX_RANGES = 5, 16
@@ -65,6 +70,13 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mbqc_plan_set_feedforward": (C.c_int, [C.c_void_p, C.POINTER(FeedForwardC), C.c_int32]),
+    "mbqc_run_batch_sv_sampled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                            C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mbqc_run_batch_dm_sampled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
+                                            C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_psr_grad_dataset_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64]),
     "mbqc_psr_grad_dataset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,

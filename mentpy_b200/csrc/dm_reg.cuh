@@ -17,6 +17,7 @@
 // output gather done once at the end through a small shared-memory stage.
 #pragma once
 #include "dm_batch.cuh"
+#include "sample.cuh"
 
 namespace mbqc {
 
@@ -43,9 +44,15 @@ __device__ __forceinline__ double select_diag(const double (&v)[1 << (W - 1)], u
 // One measurement of slot S.  rho is kept UNNORMALISED (trace `trc`, uniform over the sample's
 // lanes): the new blocks are +-sigma, so trace' = 2 tr(sigma) and no division is needed per step;
 // prob0 = tr(sigma0) / trc decides the outcome exactly as the reference's normalised state does.
+// rule: kDmRuleThreshold = the reference's deterministic rule; kDmRuleSample: outcome 0 with
+// probability prob0 (u = uniform draw); kDmRuleForced: outcome = (u != 0).  pstep receives the
+// probability of the outcome taken.
+constexpr int kDmRuleThreshold = 0, kDmRuleSample = 1, kDmRuleForced = 2;
+
 template <int W, int S>
 __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[1 << W], const MeasCoef& q,
-                                             uint32_t r, uint32_t colpar, double& trc, int& outcome, int& bad) {
+                                             uint32_t r, uint32_t colpar, double& trc, int& outcome, int& bad,
+                                             int rule = kDmRuleThreshold, double u = 0.0, double* pstep = nullptr) {
     constexpr int N = 1 << W;
     constexpr int NP = N >> 1;
     const uint32_t a = (r >> S) & 1u;
@@ -70,7 +77,12 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
     double t2 = select_diag<W, S>(sr, r);
 #pragma unroll
     for (int o = N >> 1; o > 0; o >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-    outcome = (0.5 * t2 < 1e-4 * trc) ? 1 : 0;  // prob0 < 1e-4, np_simulator_dm.py:335-338
+    if (rule == kDmRuleThreshold)
+        outcome = (0.5 * t2 < 1e-4 * trc) ? 1 : 0;  // prob0 < 1e-4, np_simulator_dm.py:335-338
+    else if (rule == kDmRuleSample)
+        outcome = (u * trc < 0.5 * t2) ? 0 : 1;
+    else
+        outcome = (u != 0.0) ? 1 : 0;
     if (__any_sync(0xffffffffu, outcome)) {
         // rare: sigma1 = tr_s(rho) - sigma0, tr_s(rho) = rho_00 + rho_11 (own diagonal block + partner's)
         double fr[NP], fi[NP];
@@ -99,6 +111,7 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
         }
     }
     if (!(t2 > 0.0) || !isfinite(t2)) bad = 1;
+    if (pstep) *pstep = 0.5 * t2 / trc;
     trc = t2;
     // CZ signs with the slot's new |+>: bit c of colpar = parity(c & nbr_mask) (0 for tail steps)
     const uint32_t pr = (a & (colpar >> r)) << 31;
@@ -116,8 +129,13 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
     }
 }
 
-template <int W>
-__global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmBatchParams p) {
+// SAMPLE = false: the reference's deterministic outcome rule (mbqc_run_batch_dm).  SAMPLE = true:
+// Born-rule sampling / forced records with flow corrections (mbqc_run_batch_dm_sampled, see
+// sample.cuh); with noise every sample is one branch of the noisy pattern, and the
+// probability-weighted mean of the corrected outputs is the PennyLane backend's result.
+template <int W, bool SAMPLE>
+__global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmBatchParams p,
+                                                     const __grid_constant__ SampleParams sp) {
     constexpr int N = 1 << W;           // lanes per sample = columns per lane
     constexpr int SPW = 32 / N;         // samples per warp
     constexpr int SPB = 4 * SPW;        // samples per CTA (4 warps)
@@ -160,6 +178,8 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
 
     const double* row = p.angles + be * p.stride;
     int bad = 0, took1 = 0;
+    uint32_t hist = 0, bx = 0, bz = 0;  // SAMPLE: last 32 outcomes, output byproduct bits
+    double pb = 1.0;                    // SAMPLE: probability of the outcome record
     double c_mine = 1.0, s_mine = 0.0;
     double trc = psi.x * psi.x + psi.y * psi.y;  // trace of the (unnormalised) rho
 #pragma unroll
@@ -186,24 +206,51 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
                 if (sx.angle_idx >= 0) sincos_cw(__ldg(row + sx.angle_idx), s_mine, c_mine);
             }
         }
-        const double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
-        const double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
+        double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
+        double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
         const StepDev st = p.steps[m];
+        FeedForwardDev ff = {0, 0, 0, 0};
+        int rule = kDmRuleThreshold;
+        double u = 0.0, pstep = 1.0;
+        if constexpr (SAMPLE) {  // theta' = (-1)^a theta + b pi
+            ff = sp.ff[m];
+            const uint32_t a = __popc(hist & ff.xdep) & 1u, z = __popc(hist & ff.zdep) & 1u;
+            c = flip_sign(c, z << 31);
+            s = flip_sign(s, (a ^ z) << 31);
+            if (sp.outcome_mode == MBQC_OUTCOMES_FORCED) {
+                rule = kDmRuleForced;
+                u = sp.outcomes[be * t.n_steps + m] ? 1.0 : 0.0;
+            } else {
+                rule = kDmRuleSample;
+                u = philox_uniform(sp.seed, sp.sample_offset + (uint64_t)be, (uint32_t)m);
+            }
+        }
         const MeasCoef q = meas_coef(st.plane, c, s, t);
         // column-parity table of this step's CZ mask, one bit per lane of the sample (0 for tail steps)
         const bool odd = (st.flags & MBQC_STEP_APPEND) && parity64((uint64_t)r & st.nbr_mask);
         const uint32_t colpar = __ballot_sync(0xffffffffu, odd) >> lane_base;
         int outcome = 0;
         switch (st.slot) {
-            case 0: dm_reg_stage<W, 0>(re, im, q, r, colpar, trc, outcome, bad); break;
-            case 1: if constexpr (W > 1) dm_reg_stage<W, 1>(re, im, q, r, colpar, trc, outcome, bad); break;
-            case 2: if constexpr (W > 2) dm_reg_stage<W, 2>(re, im, q, r, colpar, trc, outcome, bad); break;
-            case 3: if constexpr (W > 3) dm_reg_stage<W, 3>(re, im, q, r, colpar, trc, outcome, bad); break;
-            case 4: if constexpr (W > 4) dm_reg_stage<W, 4>(re, im, q, r, colpar, trc, outcome, bad); break;
+            case 0: dm_reg_stage<W, 0>(re, im, q, r, colpar, trc, outcome, bad, rule, u, &pstep); break;
+            case 1: if constexpr (W > 1) dm_reg_stage<W, 1>(re, im, q, r, colpar, trc, outcome, bad, rule, u, &pstep); break;
+            case 2: if constexpr (W > 2) dm_reg_stage<W, 2>(re, im, q, r, colpar, trc, outcome, bad, rule, u, &pstep); break;
+            case 3: if constexpr (W > 3) dm_reg_stage<W, 3>(re, im, q, r, colpar, trc, outcome, bad, rule, u, &pstep); break;
+            case 4: if constexpr (W > 4) dm_reg_stage<W, 4>(re, im, q, r, colpar, trc, outcome, bad, rule, u, &pstep); break;
             default: break;
         }
         took1 |= outcome;
-        if (live && p.outcomes && r == 0) p.outcomes[b * t.n_steps + m] = (int8_t)outcome;
+        if constexpr (SAMPLE) {
+            hist = (hist << 1) | (uint32_t)outcome;
+            if (outcome) {
+                bx ^= ff.outx;
+                bz ^= ff.outz;
+            }
+            pb *= pstep;
+            if (live && r == 0 && sp.outcomes && sp.outcome_mode != MBQC_OUTCOMES_FORCED)
+                sp.outcomes[b * t.n_steps + m] = (int8_t)outcome;
+        } else {
+            if (live && p.outcomes && r == 0) p.outcomes[b * t.n_steps + m] = (int8_t)outcome;
+        }
     }
 
     // ---- output phase through shared memory: rows -> stage, channel on output qubits, gather ----
@@ -244,11 +291,24 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
     if (p.status && r == 0) p.status[b] = (bad ? MBQC_STATUS_BAD_NORM : 0) | (took1 ? MBQC_STATUS_OUTCOME1 : 0);
     const double sc = 1.0 / tr;
     double2* o = p.out + (b << (2 * t.n_out));
+    uint32_t xm = 0, zm = 0;
+    if constexpr (SAMPLE) {
+        if (r == 0) {
+            if (sp.byproducts) sp.byproducts[b] = bx | (bz << 16);
+            if (sp.prob) sp.prob[b] = pb;
+        }
+        if (sp.correct) {  // rho' = X^x Z^z rho Z^z X^x on the output register
+            xm = byproduct_index_mask(bx, t.n_out);
+            zm = byproduct_index_mask(bz, t.n_out);
+        }
+    }
     for (uint32_t e = r; e < no * no; e += N) {
-        const uint32_t ri = (uint32_t)output_state_index(t, e >> t.n_out);
-        const uint32_t ci = (uint32_t)output_state_index(t, e & (no - 1));
+        const uint32_t dr = (e >> t.n_out) ^ xm, dc = (e & (no - 1)) ^ xm;
+        const uint32_t ri = (uint32_t)output_state_index(t, dr);
+        const uint32_t ci = (uint32_t)output_state_index(t, dc);
         const double2 v = rho[(ri << W) | ci];
-        o[e] = make_double2(v.x * sc, v.y * sc);
+        const uint32_t sg = (uint32_t)(__popc((dr ^ dc) & zm) & 1) << 31;
+        o[e] = make_double2(flip_sign(v.x * sc, sg), flip_sign(v.y * sc, sg));
     }
 }
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "dm_batch.cuh"
 #include "dm_reg.cuh"
+#include "sample.cuh"
 #include "grad_batch.cuh"
 #include "sv_batch.cuh"
 #include "sv_reg.cuh"
@@ -207,8 +208,34 @@ void mbqc_plan_destroy(mbqc_plan* plan) {
     if (!plan) return;
     if (plan->d_steps) cudaFree(plan->d_steps);
     if (plan->d_reg_blob) cudaFree(plan->d_reg_blob);
+    if (plan->d_ff) cudaFree(plan->d_ff);
     delete[] plan->h_steps;
     delete plan;
+}
+
+int mbqc_plan_set_feedforward(mbqc_plan* plan, const mbqc_feedforward* ff, int32_t n_steps) {
+    if (!plan) return fail(MBQC_E_ARG, "plan is NULL");
+    if (n_steps != plan->tab.n_steps) return fail(MBQC_E_ARG, "n_steps %d != plan steps %d", n_steps, plan->tab.n_steps);
+    if (n_steps > 0 && !ff) return fail(MBQC_E_ARG, "ff is NULL");
+    const int k = plan->tab.n_out;
+    for (int m = 0; m < n_steps; ++m) {
+        if ((k < 32 && ((ff[m].outx | ff[m].outz) >> k)) || k > 16)
+            return fail(MBQC_E_ARG, "step %d: byproduct mask names an output >= %d (max 16 outputs)", m, k);
+        if (m < 32 && (((uint64_t)ff[m].xdep | ff[m].zdep) >> m))
+            return fail(MBQC_E_ARG, "step %d depends on an outcome before the first measurement", m);
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    CUDA_TRY(cudaSetDevice(plan->device));
+    if (plan->d_ff) cudaFree(plan->d_ff);
+    plan->d_ff = nullptr;
+    static_assert(sizeof(mbqc_feedforward) == sizeof(mbqc::FeedForwardDev), "feed-forward record layout");
+    if (n_steps > 0) {
+        CUDA_TRY(cudaMalloc(&plan->d_ff, sizeof(mbqc_feedforward) * n_steps));
+        CUDA_TRY(cudaMemcpy(plan->d_ff, ff, sizeof(mbqc_feedforward) * n_steps, cudaMemcpyHostToDevice));
+    }
+    cudaSetDevice(prev);
+    return MBQC_OK;
 }
 
 int32_t mbqc_plan_window(const mbqc_plan* plan) { return plan ? plan->tab.window : -1; }
@@ -523,14 +550,16 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
         const size_t smem = (size_t)spb * n * n * sizeof(double2);
         const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
         cudaStream_t st = (cudaStream_t)stream;
+        SampleParams sp;
+        memset(&sp, 0, sizeof(sp));
         switch (w) {
-            case 1: dm_reg_kernel<1><<<blocks, 128, smem, st>>>(p); break;
-            case 2: dm_reg_kernel<2><<<blocks, 128, smem, st>>>(p); break;
-            case 3: dm_reg_kernel<3><<<blocks, 128, smem, st>>>(p); break;
-            case 4: dm_reg_kernel<4><<<blocks, 128, smem, st>>>(p); break;
+            case 1: dm_reg_kernel<1, false><<<blocks, 128, smem, st>>>(p, sp); break;
+            case 2: dm_reg_kernel<2, false><<<blocks, 128, smem, st>>>(p, sp); break;
+            case 3: dm_reg_kernel<3, false><<<blocks, 128, smem, st>>>(p, sp); break;
+            case 4: dm_reg_kernel<4, false><<<blocks, 128, smem, st>>>(p, sp); break;
             default:
-                CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dm_reg_kernel<5><<<blocks, 128, smem, st>>>(p);
+                CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dm_reg_kernel<5, false><<<blocks, 128, smem, st>>>(p, sp);
                 break;
         }
         return after_launch("dm_reg_kernel");
@@ -621,6 +650,115 @@ int check_grad_plan(const mbqc_plan* plan, const void* d_target, double shift) {
 }  // namespace
 
 extern "C" {
+
+// ---- sampled runs (force0 = False) -----------------------------------------------------------------
+static int fill_sample_params(SampleParams& sp, const mbqc_plan* plan, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, int32_t outcome_mode, int32_t correct, int8_t* d_outcomes,
+                              uint32_t* d_byproducts, double* d_prob) {
+    if (!plan->d_ff && plan->tab.n_steps > 0)
+        return fail(MBQC_E_ARG, "the plan has no feed-forward table (mbqc_plan_set_feedforward)");
+    if (outcome_mode != MBQC_OUTCOMES_SAMPLE && outcome_mode != MBQC_OUTCOMES_FORCED)
+        return fail(MBQC_E_ARG, "outcome_mode %d unknown", outcome_mode);
+    if (outcome_mode == MBQC_OUTCOMES_FORCED && !d_outcomes && batch > 0 && plan->tab.n_steps > 0)
+        return fail(MBQC_E_ARG, "forced outcomes need d_outcomes");
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_ARG, "step %d: byproduct corrections are implemented for the XY plane only", m);
+    memset(&sp, 0, sizeof(sp));
+    sp.ff = (const FeedForwardDev*)plan->d_ff;
+    sp.seed = seed;
+    sp.sample_offset = sample_offset;
+    sp.outcome_mode = outcome_mode;
+    sp.correct = correct;
+    sp.outcomes = d_outcomes;
+    sp.byproducts = d_byproducts;
+    sp.prob = d_prob;
+    return MBQC_OK;
+}
+
+int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, int32_t outcome_mode, int32_t correct, void* d_out,
+                              int8_t* d_outcomes, uint32_t* d_byproducts, double* d_prob, int32_t* d_status,
+                              void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
+    if (rc) return rc;
+    const int w = plan->tab.window;
+    if (w > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "sampled runs cover window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
+    SampleParams sp;
+    if ((rc = fill_sample_params(sp, plan, batch, seed, sample_offset, outcome_mode, correct, d_outcomes,
+                                 d_byproducts, d_prob)))
+        return rc;
+    if (batch == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
+    SvRegParams rp;
+    fill_reg_params(rp, p, plan);
+    const int T = plan->tab.n_angles;
+    const size_t smem = reg_smem_tables_bytes(plan->tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed) +
+                        (size_t)kRegThreads * (size_t)T * sizeof(double2);
+    if (smem > 200 * 1024) return fail(MBQC_E_UNSUPPORTED, "sampled runs stage at most %d angles per pattern (got %d)", (int)((200 * 1024) / (kRegThreads * 16)), T);
+    const unsigned blocks = (unsigned)((batch + kRegThreads - 1) / kRegThreads);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<blocks, kRegThreads, smem, st>>>(rp, sp);
+        return MBQC_OK;
+    };
+    switch (w) {
+        case 1: rc = go(sv_reg_sample_kernel<1>); break;
+        case 2: rc = go(sv_reg_sample_kernel<2>); break;
+        case 3: rc = go(sv_reg_sample_kernel<3>); break;
+        case 4: rc = go(sv_reg_sample_kernel<4>); break;
+        default: rc = go(sv_reg_sample_kernel<5>); break;
+    }
+    if (rc) return rc;
+    return after_launch("sv_reg_sample_kernel");
+}
+
+int mbqc_run_batch_dm_sampled(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, int32_t outcome_mode, int32_t correct, void* d_out,
+                              int8_t* d_outcomes, uint32_t* d_byproducts, double* d_prob, int32_t* d_status,
+                              void* stream) {
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
+    if (rc) return rc;
+    const int w = plan->tab.window;
+    if (w > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "sampled runs cover window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
+    SampleParams sp;
+    if ((rc = fill_sample_params(sp, plan, batch, seed, sample_offset, outcome_mode, correct, d_outcomes,
+                                 d_byproducts, d_prob)))
+        return rc;
+    if (batch == 0) return MBQC_OK;
+    DmBatchParams p;
+    memset(&p, 0, sizeof(p));
+    p.tab = plan->tab;
+    p.steps = plan->d_steps;
+    p.angles = d_angles;
+    p.stride = angle_stride;
+    p.inputs = (const double2*)d_inputs;
+    p.input_mode = input_mode;
+    p.batch = batch;
+    p.out = (double2*)d_out;
+    p.status = d_status;
+    const int n = 1 << w, spb = 4 * (32 / n);
+    const size_t smem = (size_t)spb * n * n * sizeof(double2);
+    const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (w) {
+        case 1: dm_reg_kernel<1, true><<<blocks, 128, smem, st>>>(p, sp); break;
+        case 2: dm_reg_kernel<2, true><<<blocks, 128, smem, st>>>(p, sp); break;
+        case 3: dm_reg_kernel<3, true><<<blocks, 128, smem, st>>>(p, sp); break;
+        case 4: dm_reg_kernel<4, true><<<blocks, 128, smem, st>>>(p, sp); break;
+        default:
+            CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            dm_reg_kernel<5, true><<<blocks, 128, smem, st>>>(p, sp);
+            break;
+    }
+    return after_launch("dm_reg_kernel<sampled>");
+}
 
 int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                         const void* d_inputs, int32_t input_mode, int64_t batch,

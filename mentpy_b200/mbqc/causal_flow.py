@@ -92,11 +92,37 @@ class Flow:
     def __repr__(self):
         return f"Flow(n={self.graph.number_of_nodes()})"
 
-    def adapt_angles(self, angles, outcomes):
-        raise NotImplementedError
+    def _correction_sources(self):
+        """node -> (X sources, Z sources) under the rule of pennylane_simulator.py:145-153."""
+        if self.func is None:
+            raise ValueError("the graph has no causal flow")
+        order = self.measurement_order
+        pos = {v: i for i, v in enumerate(order)}
+        xs = {v: [] for v in order}
+        zs = {v: [] for v in order}
+        for node in order:
+            if node in self.output_nodes:
+                continue
+            tgt = self.func(node)
+            xs[tgt].append(node)
+            for nb in self.graph.neighbors(tgt):
+                if nb != node and pos[nb] > pos[node]:
+                    zs[nb].append(node)
+        return xs, zs
 
     def adapt_angle(self, angle, node, previous_outcomes):
-        raise NotImplementedError
+        """XY-plane angle of `node` given the outcomes (dict node -> 0/1) measured so far:
+        (-1)^a angle + b pi, a / b = parity of the outcomes that put an X / Z on `node`.
+        (A stub in the reference, flow.py:105-109; the rule is pennylane_simulator.py:145-153.)"""
+        xs, zs = self._correction_sources()
+        a = sum(int(previous_outcomes.get(i, 0)) for i in xs[node]) % 2
+        b = sum(int(previous_outcomes.get(i, 0)) for i in zs[node]) % 2
+        return (-1) ** a * angle + b * 3.141592653589793
+
+    def adapt_angles(self, angles, outcomes):
+        """Adapted angles for all measured nodes in measurement order (angles: same order)."""
+        measured = [v for v in self.measurement_order if v not in self.output_nodes]
+        return [self.adapt_angle(a, v, outcomes) for a, v in zip(angles, measured)]
 
 
 def check_if_flow(graph, input_nodes, output_nodes, flow: Callable, partial_order: Callable) -> bool:

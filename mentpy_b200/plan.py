@@ -207,6 +207,62 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
                        first_window, first_slots)
 
 
+@dataclass
+class FeedForward:
+    """Flow corrections of one measurement step in the form the kernels consume: the outcome of
+    this step, if 1, is remembered in a shift register (bit d of it = outcome of step m-1-d);
+    xdep / zdep select the earlier outcomes that put a pending X / Z on THIS step's qubit
+    (theta' = (-1)^a theta + b pi), outx / outz the output qubits (bit q = q-th output node) whose
+    byproduct toggles when this step's outcome is 1."""
+    xdep: int = 0
+    zdep: int = 0
+    outx: int = 0
+    outz: int = 0
+
+
+def correction_sources(circuit, schedule: Sequence[int]):
+    """node -> (x_sources, z_sources): the measured nodes whose outcome 1 toggles a pending X / Z
+    on `node`.  The rule of mentpy/simulators/pennylane_simulator.py:145-153: outcome 1 at node i
+    applies X to f(i) and Z to every neighbour of f(i) other than i that is measured after i."""
+    if circuit.flow is None:
+        raise ValueError("outcome sampling needs a causal flow for the byproduct corrections")
+    pos = {v: i for i, v in enumerate(schedule)}
+    outs = set(circuit.quantum_output_nodes)
+    xs: Dict[int, List[int]] = {v: [] for v in schedule}
+    zs: Dict[int, List[int]] = {v: [] for v in schedule}
+    for node in schedule:
+        if node in outs:
+            continue
+        tgt = circuit.flow(node)
+        xs[tgt].append(node)
+        for nb in circuit.graph.neighbors(tgt):
+            if nb != node and pos[nb] > pos[node]:
+                zs[nb].append(node)
+    return xs, zs
+
+
+def feedforward(circuit, plan: LoweredPlan) -> List[FeedForward]:
+    """Per-step correction masks for sampled runs (force0=False)."""
+    xs, zs = correction_sources(circuit, plan.schedule)
+    step_of = {st.node: m for m, st in enumerate(plan.steps)}
+    ff = [FeedForward() for _ in plan.steps]
+    for m, st in enumerate(plan.steps):
+        if st.plane != _lib.PLANE_XY:
+            raise NotImplementedError("byproduct corrections are implemented for XY-plane (and X, Y) measurements")
+        for src, attr in ((xs[st.node], "xdep"), (zs[st.node], "zdep")):
+            for i in src:
+                d = m - 1 - step_of[i]
+                if not 0 <= d < 32:
+                    raise NotImplementedError(f"node {st.node} depends on the outcome of node {i}, {d + 1} steps back (max 32)")
+                setattr(ff[m], attr, getattr(ff[m], attr) ^ (1 << d))
+    for q, v in enumerate(plan.output_nodes):
+        for i in xs[v]:
+            ff[step_of[i]].outx ^= 1 << q
+        for i in zs[v]:
+            ff[step_of[i]].outz ^= 1 << q
+    return ff
+
+
 def window_is_valid(plan: LoweredPlan) -> bool:
     """True when no CZ was dropped because a neighbour had already left the window."""
     return all(not st.dropped_neighbours for st in plan.steps)
@@ -294,6 +350,17 @@ class DevicePlan:
         self.n_in = len(plan.input_slot)
         self.n_steps = len(steps)
         self._lib = lib
+        self.has_feedforward = False
+
+    def set_feedforward(self, ff: Sequence[FeedForward]):
+        """Attach the correction masks (once, before the plan is used for sampled runs)."""
+        if len(ff) != self.n_steps:
+            raise ValueError("one FeedForward record per measurement step")
+        arr = (_lib.FeedForwardC * max(len(ff), 1))()
+        for i, f in enumerate(ff):
+            arr[i].xdep, arr[i].zdep, arr[i].outx, arr[i].outz = f.xdep, f.zdep, f.outx, f.outz
+        _lib.check(self._lib.mbqc_plan_set_feedforward(self.handle, arr, len(ff)))
+        self.has_feedforward = True
 
     def __del__(self):
         h, self.handle = getattr(self, "handle", None), None

@@ -9,14 +9,20 @@ output order).  All arithmetic runs in the sm_100a kernels through the C ABI
 in one launch (numpy in -> numpy out with host<->device copies; torch CUDA tensor in -> torch out,
 fully asynchronous on the current stream).
 """
+import ctypes as C
+from collections import namedtuple
 from typing import List, Optional, Tuple
 
 import numpy as np
 import torch
 
 from .. import _lib
-from ..plan import DevicePlan, LoweredPlan, kraus_set, lower, noise_from_kraus
+from ..plan import DevicePlan, LoweredPlan, feedforward, kraus_set, lower, noise_from_kraus
 from .backend_base import BaseSimulator
+
+# result of a sampled run: states [B,2^k] / [B,2^k,2^k]; outcomes [B,M] (schedule order); x, z
+# byproduct bits [B,k] (output-node order); prob [B] = probability of the outcome record
+SampledBatch = namedtuple("SampledBatch", ["states", "outcomes", "x", "z", "prob"])
 
 _NOISE_KINDS = ("depolarizing", "amplitude_damping", "phase_damping", "phase_flip", "bit_flip",
                 "generalized_amplitude_damping")
@@ -83,8 +89,10 @@ class _CudaPatternBase(BaseSimulator):
         if dtype not in ("complex128", "complex64"):
             raise ValueError("dtype must be 'complex128' or 'complex64'")
         self.dtype = dtype
-        if not self.force0:
-            raise NotImplementedError("Numpy simulator does not support force0=False.")
+        # force0=False (NotImplementedError in the reference, np_simulator_sv.py:50-51) samples the
+        # outcomes and applies the flow corrections: see sample_batch
+        self.seed = int(kwargs.pop("seed", 0))
+        self._shots_done = 0
         if self.dev_mode:
             raise NotImplementedError("dev_mode scheduling is not supported by the CUDA backends.")
         self._noise = self._parse_noise(kwargs)
@@ -93,6 +101,10 @@ class _CudaPatternBase(BaseSimulator):
         self.window_size = self.plan.window
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure
+        if not self.force0:  # fail early (no GPU needed): flow, planes and window of the sampled path
+            if self.plan.window > _lib.MAX_WINDOW_REG:
+                raise NotImplementedError(f"force0=False covers window_size <= {_lib.MAX_WINDOW_REG}")
+            feedforward(mbqcircuit, self.plan)
         if input_state is None:
             n_in = len(mbqcircuit.input_nodes)
             input_state = np.full(2**n_in, 2.0 ** (-n_in / 2))
@@ -189,6 +201,83 @@ class _CudaPatternBase(BaseSimulator):
         if (st & _lib.STATUS_BAD_NORM).any():
             raise ValueError("qstate has nan, you might want to increase the window size")
         return st
+
+    # -- sampled runs (force0=False) ---------------------------------------------------------------
+    def _sampling_plan(self) -> DevicePlan:
+        dplan = self._full_plan()
+        if not dplan.has_feedforward:
+            dplan.set_feedforward(feedforward(self.mbqcircuit, self.plan))
+        return dplan
+
+    def sample_batch(self, angles, input_states=None, output_form: Optional[str] = None, seed: Optional[int] = None,
+                     sample_offset: Optional[int] = None, forced_outcomes=None, correct: bool = True):
+        """Run B shots with Born-rule outcomes (or the given `forced_outcomes` [B,M]) and flow
+        corrections; see csrc/sample.cuh.  Returns a `SampledBatch` (states, outcomes [B,M] in
+        schedule order, x / z byproduct bits [B,k] per output node, probability of each record);
+        numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
+
+        Shot b uses the Philox stream (seed, sample_offset + b); by default sample_offset continues
+        where the previous call stopped, so repeated calls give fresh, reproducible shots.  With
+        correct=True the byproducts are applied to the outputs (noiseless shots then all equal the
+        force0 state up to a global phase); with correct=False the raw branch state is returned."""
+        dev = self._dev()
+        lib = _lib.load()
+        if self.dtype != "complex128":
+            raise NotImplementedError("sampled runs are complex128 only")
+        if self.plan.window > _lib.MAX_WINDOW_REG:
+            raise NotImplementedError(f"sampled runs cover window_size <= {_lib.MAX_WINDOW_REG}")
+        form = (output_form or ("dm" if self.mixed else "sv")).lower()
+        if form not in ("sv", "statevector", "dm", "densitymatrix"):
+            raise ValueError(f"Output form {output_form} is not supported.")
+        want_dm = form in ("dm", "densitymatrix")
+        if self.mixed and not want_dm:
+            raise ValueError("the density-matrix backend returns density matrices")
+        with torch.cuda.device(dev):
+            dplan = self._sampling_plan()
+            a, on_host = self._stage_angles(angles, dev)
+            batch, M, k = a.shape[0], dplan.n_steps, dplan.n_out
+            inp, mode = self._stage_inputs(input_states, batch, dev)
+            dim = 2 ** k
+            out = torch.empty((batch, dim, dim) if self.mixed else (batch, dim), dtype=torch.complex128, device=dev)
+            if forced_outcomes is None:
+                outc = torch.zeros((batch, max(M, 1)), dtype=torch.int8, device=dev)
+                omode = _lib.OUTCOMES_SAMPLE
+            else:
+                outc = torch.as_tensor(forced_outcomes).to(device=dev, dtype=torch.int8).reshape(batch, -1).contiguous()
+                if outc.shape[1] != M:
+                    raise ValueError(f"forced_outcomes must have shape ({batch}, {M})")
+                if M == 0:
+                    outc = torch.zeros((batch, 1), dtype=torch.int8, device=dev)
+                omode = _lib.OUTCOMES_FORCED
+            byp = torch.zeros(batch, dtype=torch.int32, device=dev)
+            prob = torch.empty(batch, dtype=torch.float64, device=dev)
+            status = torch.empty(batch, dtype=torch.int32, device=dev)
+            if sample_offset is None:
+                sample_offset = self._shots_done
+                self._shots_done += batch
+            fn = lib.mbqc_run_batch_dm_sampled if self.mixed else lib.mbqc_run_batch_sv_sampled
+            _lib.check(fn(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode, batch,
+                          C.c_uint64(self.seed if seed is None else int(seed)), C.c_uint64(int(sample_offset)),
+                          omode, 1 if correct else 0, _ptr(out), _ptr(outc), _ptr(byp), _ptr(prob), _ptr(status),
+                          torch.cuda.current_stream(dev).cuda_stream))
+            if want_dm and not self.mixed:
+                out = out[:, :, None] * out.conj()[:, None, :]
+            q = torch.arange(k, device=dev, dtype=torch.int32)
+            bx = ((byp[:, None] >> q[None, :]) & 1).to(torch.int8)
+            bz = ((byp[:, None] >> (q[None, :] + 16)) & 1).to(torch.int8)
+            outc = outc[:, :M]
+            if on_host:
+                self._check_status(status)
+                return SampledBatch(out.cpu().numpy(), outc.cpu().numpy(), bx.cpu().numpy(), bz.cpu().numpy(),
+                                    prob.cpu().numpy())
+            self.last_status = status
+            return SampledBatch(out, outc, bx, bz, prob)
+
+    def _sampled_run(self, angles, output_form):
+        res = self.sample_batch(np.asarray(angles, dtype=np.float64)[None, :], output_form=output_form)
+        self.outcomes = {v: int(o) for v, o in zip(self.schedule_measure, res.outcomes[0])}
+        self.byproducts = {v: (int(x), int(z)) for v, x, z in zip(self.plan.output_nodes, res.x[0], res.z[0])}
+        return res.states[0]
 
     # -- reference-compatible state machine -----------------------------------------------------
     def reset(self, input_state: np.ndarray = None):
@@ -358,6 +447,8 @@ class CudaSimulatorSV(_CudaPatternBase):
         return res.copy() if copy else res
 
     def measure(self, angle: float) -> Tuple[np.ndarray, int]:
+        if not self.force0:
+            raise NotImplementedError("step-by-step measure() is deterministic (force0=True) only; use run / sample_batch")
         st = self._record_angle(angle)
         self.current_measurement += 1
         self.outcomes[st.node] = 0
@@ -378,6 +469,10 @@ class CudaSimulatorSV(_CudaPatternBase):
             )
         if self.current_measurement != 0:
             raise ValueError("No more measurements to be done.")
+        if not self.force0:
+            res = self._sampled_run(angles, output_form)
+            self.current_measurement = len(self.schedule_measure)
+            return res
         res = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], output_form=output_form)[0]
         self.current_measurement = len(self.schedule_measure)
         self._angles_seen[: self.plan.n_angles] = np.asarray(angles, dtype=np.float64)
@@ -465,6 +560,10 @@ class CudaSimulatorDM(_CudaPatternBase):
             )
         if self.current_measurement != 0:
             raise ValueError("No more measurements to be done.")
+        if not self.force0:
+            res = self._sampled_run(angles, "dm")
+            self.current_measurement = len(self.schedule_measure)
+            return res
         rho, oc = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], return_outcomes=True)
         self.current_measurement = len(self.schedule_measure)
         self._angles_seen[: self.plan.n_angles] = np.asarray(angles, dtype=np.float64)

@@ -119,7 +119,10 @@ def test_facade_contract_without_gpu():
     with pytest.raises(TypeError):
         mb.PatternSimulator(gs, input_state=[1, 0])
     with pytest.raises(NotImplementedError):
-        mb.PatternSimulator(gs, backend="cuda-sv", force0=False)
+        mb.PatternSimulator(gs, backend="cuda-sv-stream", force0=False)
+    with pytest.raises(NotImplementedError):  # sampled runs: register kernels only
+        mb.PatternSimulator(mb.templates.grid_cluster(6, 3), backend="cuda-sv", force0=False)
+    assert mb.PatternSimulator(gs, backend="cuda-sv", force0=False, seed=5).seed == 5
     ps = mb.PatternSimulator(gs, backend="CUDA-SV", some_unknown_kwarg=3)
     assert ps.window_size == 2 and ps.mbqcircuit is gs and ps.outcomes == {}
     assert ps.schedule_measure == [0, 1]
