@@ -136,6 +136,17 @@ int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_
                            int32_t out_form, void* d_work, int64_t work_bytes,
                            int32_t* h_status_any, int32_t n_chunks);
 
+/* Asynchronous form: _submit queues the call and returns a ticket at once, mbqc_host_wait blocks
+ * until that call's h_out is complete.  Up to 4 calls may be in flight per device (each with its
+ * own h_angles / h_out / d_work); consecutive calls run on alternating stream sets, so the H2D
+ * copies of call n+1 overlap the kernels and result transfers of call n (PCIe is full duplex).
+ * mbqc_run_batch_sv_host == submit + wait. */
+int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                                  const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                                  int32_t out_form, void* d_work, int64_t work_bytes, int32_t n_chunks,
+                                  int32_t* ticket);
+int mbqc_host_wait(int32_t ticket, int32_t* h_status_any);
+
 /* NumpySimulatorDM.run over a batch (np_simulator_dm.py:218-283), optional noise from the plan:
  * out [B][2^k][2^k]; d_outcomes (may be NULL) [B][n_steps] int8 receives the outcome record
  * (simulator.outcomes). */

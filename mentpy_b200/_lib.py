@@ -65,6 +65,10 @@ _SIGNATURES = {
     "mbqc_run_batch_sv_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.POINTER(C.c_int32), C.c_int32]),
+    "mbqc_run_batch_sv_host_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                                C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                                C.c_int32, C.POINTER(C.c_int32)]),
+    "mbqc_host_wait": (C.c_int, [C.c_int32, C.POINTER(C.c_int32)]),
     "mbqc_run_batch_dm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,

@@ -354,11 +354,21 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
 
 // ---- host-buffer pipeline --------------------------------------------------------------------
 namespace {
-constexpr int kPipeStreams = 4;
-struct PipeState {  // created lazily, once per device
-    cudaStream_t s[kPipeStreams];
-    cudaEvent_t done[kPipeStreams];
+constexpr int kPipeStreams = 4;   // chunks of one call run on up to 4 streams
+constexpr int kPipeSets = 2;      // consecutive calls alternate between two stream sets
+constexpr int kPipeTickets = 4;   // calls that may be in flight per device
+struct PipeTicket {
+    cudaEvent_t done;
     int32_t* h_flags = nullptr;  // page-locked, kPipeStreams words
+    int32_t* d_any = nullptr;    // the call's status words inside its workspace
+    int used = 0;
+    bool busy = false;
+};
+struct PipeState {  // created lazily, once per device
+    cudaStream_t s[kPipeSets][kPipeStreams];
+    cudaEvent_t joined[kPipeSets][kPipeStreams];
+    PipeTicket ticket[kPipeTickets];
+    unsigned next = 0;
     bool ready = false;
 };
 PipeState g_pipe[64];
@@ -367,11 +377,15 @@ int pipe_state(int device, PipeState** out) {
     if (device < 0 || device >= 64) return fail(MBQC_E_ARG, "device index %d out of range", device);
     PipeState& ps = g_pipe[device];
     if (!ps.ready) {
-        for (int i = 0; i < kPipeStreams; ++i) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&ps.s[i], cudaStreamNonBlocking));
-            CUDA_TRY(cudaEventCreateWithFlags(&ps.done[i], cudaEventDisableTiming));
+        for (int g = 0; g < kPipeSets; ++g)
+            for (int i = 0; i < kPipeStreams; ++i) {
+                CUDA_TRY(cudaStreamCreateWithFlags(&ps.s[g][i], cudaStreamNonBlocking));
+                CUDA_TRY(cudaEventCreateWithFlags(&ps.joined[g][i], cudaEventDisableTiming));
+            }
+        for (int t = 0; t < kPipeTickets; ++t) {
+            CUDA_TRY(cudaEventCreateWithFlags(&ps.ticket[t].done, cudaEventDisableTiming));
+            CUDA_TRY(cudaHostAlloc((void**)&ps.ticket[t].h_flags, kPipeStreams * sizeof(int32_t), cudaHostAllocDefault));
         }
-        CUDA_TRY(cudaHostAlloc((void**)&ps.h_flags, kPipeStreams * sizeof(int32_t), cudaHostAllocDefault));
         ps.ready = true;
     }
     *out = &ps;
@@ -388,25 +402,37 @@ extern "C" int64_t mbqc_host_workspace_bytes(const mbqc_plan* plan, int64_t batc
     return (int64_t)(align256((size_t)batch * T * sizeof(double)) + align256((size_t)batch * out_elems * sizeof(double2)) + 256);
 }
 
-extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
-                                      const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
-                                      int32_t out_form, void* d_work, int64_t work_bytes,
-                                      int32_t* h_status_any, int32_t n_chunks) {
+extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                                             const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                                             int32_t out_form, void* d_work, int64_t work_bytes, int32_t n_chunks,
+                                             int32_t* ticket) {
     int rc = check_batch_args(plan, h_angles, angle_stride, d_inputs, input_mode, batch, h_out);
     if (rc) return rc;
+    if (!ticket) return fail(MBQC_E_ARG, "ticket is NULL");
     if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
     if (!d_work || work_bytes < mbqc_host_workspace_bytes(plan, batch, out_form))
         return fail(MBQC_E_ARG, "d_work too small: need %lld bytes", (long long)mbqc_host_workspace_bytes(plan, batch, out_form));
     for (int m = 0; m < plan->tab.n_steps; ++m)
         if (plan->h_steps[m].plane != MBQC_PLANE_XY)
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
-    if (h_status_any) *h_status_any = 0;
-    if (batch == 0) return MBQC_OK;
     PipeState* ps = nullptr;
     int device = 0;
     CUDA_TRY(cudaGetDevice(&device));
     rc = pipe_state(device, &ps);
     if (rc) return rc;
+    const unsigned slot = ps->next % kPipeTickets;
+    PipeTicket& tk = ps->ticket[slot];
+    if (tk.busy) return fail(MBQC_E_ARG, "%d host calls already in flight on device %d: wait for the oldest first", kPipeTickets, device);
+    const int set = (int)(ps->next % kPipeSets);
+    cudaStream_t* str = ps->s[set];
+    *ticket = device * kPipeTickets + (int)slot;
+    ps->next++;
+    tk.busy = true;
+    tk.used = 0;
+    if (batch == 0) {
+        CUDA_TRY(cudaEventRecord(tk.done, str[0]));
+        return MBQC_OK;
+    }
     const int T = plan->tab.n_angles;
     const int Tw = T > 0 ? T : 1;
     const int k = plan->tab.n_out;
@@ -431,13 +457,13 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
     if ((int64_t)n_chunks > (batch + 1023) / 1024) n_chunks = (int)((batch + 1023) / 1024);
     if (n_chunks < 1) n_chunks = 1;
     const int used = n_chunks < kPipeStreams ? n_chunks : kPipeStreams;
-    for (int i = 0; i < used; ++i) CUDA_TRY(cudaMemsetAsync(d_any + i, 0, sizeof(int32_t), ps->s[i]));
+    for (int i = 0; i < used; ++i) CUDA_TRY(cudaMemsetAsync(d_any + i, 0, sizeof(int32_t), str[i]));
     const int64_t per = (batch + n_chunks - 1) / n_chunks;
     for (int c = 0; c < n_chunks; ++c) {
         const int64_t lo = (int64_t)c * per;
         const int64_t hi = (lo + per < batch) ? lo + per : batch;
         if (hi <= lo) break;
-        cudaStream_t st = ps->s[c % kPipeStreams];
+        cudaStream_t st = str[c % kPipeStreams];
         if (T > 0) {
             if (angle_stride == T) {
                 CUDA_TRY(cudaMemcpyAsync(d_angles + lo * T, h_angles + lo * T, (size_t)(hi - lo) * T * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -459,24 +485,44 @@ extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_ang
             CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
                                      cudaMemcpyDeviceToHost, st));
     }
-    // join: every stream's tail feeds stream 0, which fetches the status words; one host wait
+    // join: every stream's tail feeds stream 0 of the set, which fetches the status words
     for (int i = 1; i < used; ++i) {
-        CUDA_TRY(cudaEventRecord(ps->done[i], ps->s[i]));
-        CUDA_TRY(cudaStreamWaitEvent(ps->s[0], ps->done[i], 0));
+        CUDA_TRY(cudaEventRecord(ps->joined[set][i], str[i]));
+        CUDA_TRY(cudaStreamWaitEvent(str[0], ps->joined[set][i], 0));
     }
-    CUDA_TRY(cudaMemcpyAsync(ps->h_flags, d_any, used * sizeof(int32_t), cudaMemcpyDeviceToHost, ps->s[0]));
-    CUDA_TRY(cudaStreamSynchronize(ps->s[0]));
+    CUDA_TRY(cudaMemcpyAsync(tk.h_flags, d_any, used * sizeof(int32_t), cudaMemcpyDeviceToHost, str[0]));
+    CUDA_TRY(cudaEventRecord(tk.done, str[0]));
+    tk.used = used;
+    return MBQC_OK;
+}
+
+extern "C" int mbqc_host_wait(int32_t ticket, int32_t* h_status_any) {
+    if (ticket < 0 || ticket >= 64 * kPipeTickets) return fail(MBQC_E_ARG, "ticket %d out of range", ticket);
+    PipeState& ps = g_pipe[ticket / kPipeTickets];
+    if (!ps.ready) return fail(MBQC_E_ARG, "ticket %d: nothing was submitted on that device", ticket);
+    PipeTicket& tk = ps.ticket[ticket % kPipeTickets];
+    if (!tk.busy) return fail(MBQC_E_ARG, "ticket %d is not in flight", ticket);
+    tk.busy = false;
+    CUDA_TRY(cudaEventSynchronize(tk.done));
     if (h_status_any) {
         int32_t any = 0;
-        for (int i = 0; i < used; ++i) any |= ps->h_flags[i];
+        for (int i = 0; i < tk.used; ++i) any |= tk.h_flags[i];
         *h_status_any = any;
     }
     return MBQC_OK;
 }
 
-extern "C" {
-
-}  // extern "C"
+extern "C" int mbqc_run_batch_sv_host(const mbqc_plan* plan, const double* h_angles, int64_t angle_stride,
+                                      const void* d_inputs, int32_t input_mode, int64_t batch, void* h_out,
+                                      int32_t out_form, void* d_work, int64_t work_bytes,
+                                      int32_t* h_status_any, int32_t n_chunks) {
+    int32_t ticket = -1;
+    if (h_status_any) *h_status_any = 0;
+    int rc = mbqc_run_batch_sv_host_submit(plan, h_angles, angle_stride, d_inputs, input_mode, batch, h_out, out_form,
+                                           d_work, work_bytes, n_chunks, &ticket);
+    if (rc) return rc;
+    return mbqc_host_wait(ticket, h_status_any);
+}
 
 template <int W, bool DM>
 static int launch_sv_reg_f32_w(const SvBatchParams& p, const mbqc_plan* plan, cudaStream_t st) {

@@ -3,6 +3,7 @@ C1 linear_cluster(5) SV, C2 grid 2x6 SV, C3 grid 3x8 DM (+depolarizing), C4 grid
 C5 streaming linear_cluster(w+16, window w).  One JSON line per config -> profiles/."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np, torch
 import mentpy_b200 as mb
 from mentpy_b200 import _lib
@@ -51,6 +52,24 @@ for p in (0.0, 0.01, 0.1):
     t = timeit(lambda: ps.run_batch(ang), 20)
     by = 4096 * (8 * T + 16 * 64)
     emit(config="C3", pattern="grid_cluster(3,8) DM", depolarizing_p=p, batch=4096, evals_per_s=4096 / t, ms=t * 1e3, algorithmic_GBps=by / t / 1e9, hbm_frac=by / t / 1e9 / PEAK)
+# C3 at kernel level (C-ABI launches captured in a CUDA graph, no Python per-call overhead)
+from perf_dm import time_kernel as dm_time_kernel  # noqa: E402
+for p, B in ((0.0, 4096), (0.01, 4096), (0.0, 65536), (0.01, 65536)):
+    us = dm_time_kernel([3, 8], B, p)
+    by = B * (8 * T + 16 * 64)
+    emit(config="C3-kernel", pattern="grid_cluster(3,8) DM", depolarizing_p=p, batch=B, evals_per_s=B / us * 1e6, us_per_launch=us,
+         algorithmic_GBps=by / us / 1e3, hbm_frac=by / us / 1e3 / PEAK)
+# sampled runs (force0=False): Philox outcomes + flow corrections
+gs = mb.templates.grid_cluster(2, 6); T = len(gs.trainable_nodes)
+ps = mb.PatternSimulator(gs, backend="cuda-sv", force0=False, seed=1)
+ang = torch.rand((1 << 20, T), device=dev, dtype=torch.float64) * 6.283
+t = timeit(lambda: ps.sample_batch(ang), 20)
+emit(config="C2-sampled", pattern="grid_cluster(2,6) SV force0=False", batch=1 << 20, shots_per_s=(1 << 20) / t, ms=t * 1e3)
+gs = mb.templates.grid_cluster(3, 8); T = len(gs.trainable_nodes)
+ps = mb.PatternSimulator(gs, backend="cuda-dm", force0=False, seed=1, circuit_noise="depolarizing", p=0.01)
+ang = torch.rand((1 << 16, T), device=dev, dtype=torch.float64) * 6.283
+t = timeit(lambda: ps.sample_batch(ang), 10)
+emit(config="C3-sampled", pattern="grid_cluster(3,8) DM force0=False depolarizing 0.01", batch=1 << 16, shots_per_s=(1 << 16) / t, ms=t * 1e3)
 # C4: gradient
 gs = mb.templates.grid_cluster(4, 5); T = len(gs.trainable_nodes)
 ps = mb.PatternSimulator(gs, backend="cuda-sv")
@@ -59,6 +78,15 @@ for B in (1 << 16, 1 << 20):
     ang = torch.rand((B, T), device=dev, dtype=torch.float64) * 6.283
     t = timeit(lambda: psr_gradient_batched(ps, ang, tgt), 5)
     emit(config="C4", pattern="grid_cluster(4,5) psr gradient", base_vectors=B, gradients_per_s=B / t, pattern_evals_per_s=B * 2 * T / t, ms=t * 1e3, algorithmic_GBps=B * 256 / t / 1e9, hbm_frac=B * 256 / t / 1e9 / PEAK)
+# data-set averaged gradient (one optimiser step of the QML tutorial): P vectors x S data items
+from mentpy_b200.gradients import psr_gradient_dataset  # noqa: E402
+P, S = 64, 4096
+X = torch.rand((P, T), device=dev, dtype=torch.float64) * 6.283
+ins = torch.randn((S, 16), device=dev, dtype=torch.complex128); ins = ins / ins.norm(dim=1, keepdim=True)
+tgs = torch.randn((S, 16), device=dev, dtype=torch.complex128); tgs = tgs / tgs.norm(dim=1, keepdim=True)
+t = timeit(lambda: psr_gradient_dataset(ps, X, tgs, ins), 5)
+emit(config="C4-dataset", pattern="grid_cluster(4,5) data-set psr gradient", vectors=P, data_items=S,
+     gradients_per_s=P / t, pattern_evals_per_s=P * S * 2 * T / t, ms=t * 1e3)
 # C5: streaming
 for w in (28, 30, 32):
     try:

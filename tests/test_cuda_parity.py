@@ -578,3 +578,34 @@ def test_dm_kernels_agree(monkeypatch):
             for suffix in ("", "_plus"):
                 assert np.allclose(res["reg" + suffix][0], res["smem" + suffix][0], atol=1e-12)
                 assert np.array_equal(res["reg" + suffix][1], res["smem" + suffix][1])
+
+
+def test_async_host_calls_match_blocking_calls():
+    """run_batch_async (submit / wait tickets): several calls in flight return exactly what the
+    blocking call returns; too many outstanding calls and double waits are reported."""
+    gs = mb.templates.grid_cluster(2, 6)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    rng = np.random.default_rng(12)
+    batches = [rng.uniform(0, 2 * np.pi, (20000, 10)) for _ in range(7)]
+    want = [ps.run_batch(a) for a in batches]
+    pend, got = [], []
+    for a in batches:
+        pend.append(ps.run_batch_async(a))
+        if len(pend) == 2:
+            got.append(pend.pop(0).result(copy=True))
+    got += [h.result(copy=True) for h in pend]
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    h = ps.run_batch_async(batches[0], output_form="dm")
+    assert np.allclose(h.result(), want[0][:, :, None] * want[0].conj()[:, None, :], atol=1e-15)
+    assert h.result() is not None and h.status_any == 0          # second result(): no second wait
+    assert ps.run_batch_async(np.zeros((0, 10))).result().shape == (0, 4)
+    hs = [ps.run_batch_async(batches[i]) for i in range(3)]       # rotating buffers: 3 sets
+    with pytest.raises(ValueError):
+        import torch
+        ps.run_batch_async(torch.zeros((4, 10), device="cuda", dtype=torch.float64))
+    for x in hs:
+        x.result()
+    lib = mb._lib.load()
+    import ctypes as C
+    assert lib.mbqc_host_wait(0, None) == mb._lib.MBQC_E_ARG and b"not in flight" in lib.mbqc_last_error()
