@@ -426,11 +426,14 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
     const int set = (int)(ps->next % kPipeSets);
     cudaStream_t* str = ps->s[set];
     *ticket = device * kPipeTickets + (int)slot;
-    ps->next++;
-    tk.busy = true;
     tk.used = 0;
+    auto commit = [&]() {  // the slot is taken only once everything was queued
+        ps->next++;
+        tk.busy = true;
+    };
     if (batch == 0) {
         CUDA_TRY(cudaEventRecord(tk.done, str[0]));
+        commit();
         return MBQC_OK;
     }
     const int T = plan->tab.n_angles;
@@ -493,6 +496,7 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
     CUDA_TRY(cudaMemcpyAsync(tk.h_flags, d_any, used * sizeof(int32_t), cudaMemcpyDeviceToHost, str[0]));
     CUDA_TRY(cudaEventRecord(tk.done, str[0]));
     tk.used = used;
+    commit();
     return MBQC_OK;
 }
 
