@@ -456,7 +456,7 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
         else
             cudaGetLastError();  // clear the error state a plain malloc'ed pointer may leave
     }
-    if (n_chunks < 1) n_chunks = dev_view_of_host_out ? 4 : 2;  // measured: more pieces only add engine hand-offs
+    if (n_chunks < 1) n_chunks = 2;  // measured (profiles/): more pieces only add engine hand-offs
     if ((int64_t)n_chunks > (batch + 1023) / 1024) n_chunks = (int)((batch + 1023) / 1024);
     if (n_chunks < 1) n_chunks = 1;
     const int used = n_chunks < kPipeStreams ? n_chunks : kPipeStreams;
