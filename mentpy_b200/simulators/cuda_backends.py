@@ -46,10 +46,10 @@ class _HostCall:
     """Everything a steady-state host-array `run_batch` call needs, resolved once per
     (plan, batch, output form): rotating sets of (device workspace, page-locked output buffer with
     its numpy view, raw pointers).  The hot call is then: pointer of the input, one ctypes call,
-    return a view.  Three sets: up to two calls in flight (run_batch_async) while the caller still
+    return a view.  Four sets: up to three calls in flight (run_batch_async) while the caller still
     reads the result of the one before."""
 
-    DEPTH = 3
+    DEPTH = 4
 
     def __init__(self, lib, dplan, dev, batch, T, code):
         dim = 2 ** dplan.n_out
@@ -85,7 +85,7 @@ class PendingBatch:
 
     def result(self, copy: bool = False) -> np.ndarray:
         """Block until the call finished and return its output ([B,2^k] or [B,2^k,2^k]).  With
-        copy=False this is a view of a rotating page-locked buffer, valid until two further calls
+        copy=False this is a view of a rotating page-locked buffer, valid until three further calls
         have been submitted."""
         if not self._done:
             flag = C.c_int32(0)
@@ -491,7 +491,7 @@ class CudaSimulatorSV(_CudaPatternBase):
 
     def run_batch_async(self, angles, input_states=None, output_form: str = "sv", check: bool = True) -> "PendingBatch":
         """Queue a host-array `run_batch` and return at once; `.result()` of the returned handle
-        blocks until the output is complete.  Up to two calls may be in flight: the host-to-device
+        blocks until the output is complete.  Up to three calls may be in flight: the host-to-device
         copy of call n+1 then overlaps the kernels and result transfer of call n (PCIe is full
         duplex), which roughly halves the per-call time of a stream of batches.  `angles` must be
         a host array (numpy / CPU tensor, ideally page-locked) and must stay untouched until
