@@ -86,3 +86,61 @@ def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, grou
     if not gather:
         return local, (lo, hi)
     return gather_slices(local, B, group)
+
+
+def sample_batch_distributed(simulator, angles, group=None, seed: Optional[int] = None, sample_offset: int = 0,
+                             **kwargs):
+    """Sampled shots (force0=False) split across the ranks of `group`.  Shot b draws from the
+    Philox stream (seed, sample_offset + b) wherever it runs, so the gathered outcome records are
+    identical to a single-GPU `sample_batch(angles, seed=seed, sample_offset=sample_offset)`.
+    Returns the full SampledBatch on every rank (CUDA tensors)."""
+    import torch
+
+    from .simulators.cuda_backends import SampledBatch
+
+    rank, world = _rank_world(group)
+    sim = getattr(simulator, "simulator", simulator)
+    B = len(angles)
+    lo, hi = slice_bounds(B, rank, world)
+    part = angles[lo:hi]
+    if not isinstance(part, torch.Tensor):
+        part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
+    ins = kwargs.pop("input_states", None)
+    if ins is not None and getattr(ins, "ndim", 1) == 2:
+        ins = ins[lo:hi]
+    local = sim.sample_batch(part.to(sim._dev()), input_states=ins, seed=seed, sample_offset=sample_offset + lo, **kwargs)
+    return SampledBatch(*[gather_slices(x, B, group) for x in local])
+
+
+def psr_gradient_dataset_distributed(simulator, angles, targets, input_states=None, shift: float = 1.5, group=None,
+                                     return_cost: bool = False):
+    """Data-set averaged gradient with the S data items split across the GPUs: every rank runs the
+    fused kernel on its items for all P parameter vectors; ONE all_reduce(sum) of P*(T+1) doubles
+    combines the partial means ('for a dataset-averaged cost gradient, all-reduce of T
+    doubles')."""
+    import torch
+    import torch.distributed as dist
+
+    from .gradients import psr_gradient_dataset
+
+    rank, world = _rank_world(group)
+    sim = getattr(simulator, "simulator", simulator)
+    S = len(targets)
+    lo, hi = slice_bounds(S, rank, world)
+    dev = sim._dev()
+    a = angles if isinstance(angles, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(angles, dtype=np.float64))
+    a = a.to(dev)
+    if hi > lo:
+        g, c = psr_gradient_dataset(sim, a, targets[lo:hi], None if input_states is None else input_states[lo:hi],
+                                    shift=shift, return_cost=True)
+        w = (hi - lo) / S
+        packed = torch.cat([g.reshape(-1) * w, c.reshape(-1) * w])
+    else:
+        P = 1 if a.dim() == 1 else a.shape[0]
+        packed = torch.zeros(P * (a.shape[-1] + 1), dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(packed, group=group)
+    n_c = 1 if a.dim() == 1 else a.shape[0]
+    g = packed[: packed.numel() - n_c].reshape(a.shape)
+    c = packed[packed.numel() - n_c:] if a.dim() == 2 else packed[-1]
+    return (g, c) if return_cost else g

@@ -8,8 +8,9 @@ import torch
 import torch.distributed as dist
 
 import mentpy_b200 as mb
-from mentpy_b200.dist import psr_gradient_distributed, run_batch_distributed
-from mentpy_b200.gradients import psr_gradient_batched
+from mentpy_b200.dist import (psr_gradient_dataset_distributed, psr_gradient_distributed, run_batch_distributed,
+                              sample_batch_distributed)
+from mentpy_b200.gradients import psr_gradient_batched, psr_gradient_dataset
 
 
 def main():
@@ -27,6 +28,20 @@ def main():
     g = psr_gradient_distributed(ps, ang[:515], tgt)
     gref = psr_gradient_batched(ps, torch.from_numpy(ang[:515]).cuda(), tgt)
     ok = ok and torch.equal(g, gref)
+    # sampled shots: the Philox stream is indexed by the global shot number -> identical records
+    pss = mb.PatternSimulator(gs, backend="cuda-sv", force0=False, seed=9)
+    shots = sample_batch_distributed(pss, ang, seed=9, sample_offset=100)
+    one = pss.sample_batch(torch.from_numpy(ang).cuda(), seed=9, sample_offset=100)
+    ok = ok and torch.equal(shots.outcomes, one.outcomes) and torch.equal(shots.states, one.states)
+    ok = ok and torch.equal(shots.x, one.x) and torch.equal(shots.prob, one.prob)
+    # data-set averaged gradient, data items split across the ranks, one all_reduce
+    rng = np.random.default_rng(5)
+    S = 301
+    ins = rng.normal(size=(S, 16)) + 1j * rng.normal(size=(S, 16)); ins /= np.linalg.norm(ins, axis=1, keepdims=True)
+    tg = rng.normal(size=(S, 16)) + 1j * rng.normal(size=(S, 16)); tg /= np.linalg.norm(tg, axis=1, keepdims=True)
+    gd, cd = psr_gradient_dataset_distributed(ps, ang[:7], tg, ins, return_cost=True)
+    gd1, cd1 = psr_gradient_dataset(ps, torch.from_numpy(ang[:7]).cuda(), tg, ins, return_cost=True)
+    ok = ok and torch.allclose(gd, gd1, atol=1e-13, rtol=0) and torch.allclose(cd, cd1, atol=1e-13, rtol=0)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0 and int(flag.item()) == 1:
