@@ -37,6 +37,7 @@ extern "C" {
 #define MBQC_PLANE_XY 0
 #define MBQC_PLANE_XZ 1
 #define MBQC_PLANE_YZ 2
+#define MBQC_PLANE_Z 3 /* DM path, expectation mode only: trace the qubit out, record prob1 */
 
 #define MBQC_STEP_APPEND 1u /* a |+> qubit enters the freed slot and is CZ'ed with nbr_mask */
 
@@ -153,6 +154,16 @@ int mbqc_host_wait(int32_t ticket, int32_t* h_status_any);
 int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                       const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
                       int8_t* d_outcomes, int32_t* d_status, void* stream);
+
+/* mode="expectation" of NumpySimulatorDM.run (np_simulator_dm.py:327-344): as mbqc_run_batch_dm,
+ * but steps in MBQC_PLANE_Z are not projected -- the qubit is traced out and prob1 / (prob0 + prob1)
+ * is recorded in d_expect[b][step] (double, [B][n_steps], 0 for the other steps; required when
+ * the plan has plane-Z steps) -- the classifier read-out of a pattern.  Window <= 5.  Plans with
+ * plane-Z steps are rejected by mbqc_run_batch_dm (the reference draws those outcomes at random
+ * there, even under force0). */
+int mbqc_run_batch_dm_expect(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                             const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                             int8_t* d_outcomes, double* d_expect, int32_t* d_status, void* stream);
 
 /* Attach the feed-forward table (n_steps records) to a plan.  Call once, right after
  * mbqc_plan_create and before the plan is shared between threads. */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MBQC_LIB_PATH", os.path.join(_HERE, "_mbqc_b200.so"))  # override: kernel experiments
 
 MBQC_OK, MBQC_E_ARG, MBQC_E_CUDA, MBQC_E_UNSUPPORTED = 0, -1, -2, -3
-PLANE_XY, PLANE_XZ, PLANE_YZ = 0, 1, 2
+PLANE_XY, PLANE_XZ, PLANE_YZ, PLANE_Z = 0, 1, 2, 3
 STEP_APPEND = 1
 STATUS_BAD_NORM, STATUS_OUTCOME1 = 1, 2
 OUT_SV, OUT_DM = 0, 1
@@ -74,6 +74,8 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mbqc_run_batch_dm_expect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_plan_set_feedforward": (C.c_int, [C.c_void_p, C.POINTER(FeedForwardC), C.c_int32]),
     "mbqc_run_batch_sv_sampled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int64,
                                             C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p,

@@ -29,6 +29,7 @@ struct DmBatchParams {
     double2* __restrict__ out;      // [B][4^k]
     int8_t* __restrict__ outcomes;  // [B][n_steps] or null
     int32_t* __restrict__ status;
+    double* __restrict__ expect;    // [B][n_steps] prob1 of plane-Z steps (expectation mode) or null
 };
 
 struct MeasCoef {
@@ -42,6 +43,8 @@ __device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, con
         p00 = 0.5; p11 = 0.5; p10r = 0.5 * c; p10i = 0.5 * s;
     } else if (plane == MBQC_PLANE_XZ) {
         p00 = 0.5 * (1.0 + s); p11 = 0.5 * (1.0 - s); p10r = 0.5 * c; p10i = 0.0;
+    } else if (plane == MBQC_PLANE_Z) {  // expectation mode: P0 + P1 = I, the qubit is only traced out
+        p00 = 1.0; p11 = 1.0; p10r = 0.0; p10i = 0.0;
     } else {
         p00 = 0.5 * (1.0 + s); p11 = 0.5 * (1.0 - s); p10r = 0.0; p10i = 0.5 * c;
     }

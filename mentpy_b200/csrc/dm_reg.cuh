@@ -41,13 +41,30 @@ __device__ __forceinline__ double select_diag(const double (&v)[1 << (W - 1)], u
     return sel[0];
 }
 
+// re[r] for a lane-varying r: binary select tree over all column bits
+template <int W>
+__device__ __forceinline__ double select_own(const double (&v)[1 << W], uint32_t r) {
+    double sel[1 << W];
+#pragma unroll
+    for (int i = 0; i < (1 << W); ++i) sel[i] = v[i];
+    int n = 1 << W;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const bool hi = (r >> j) & 1u;
+        n >>= 1;
+#pragma unroll
+        for (int i = 0; i < n; ++i) sel[i] = hi ? sel[2 * i + 1] : sel[2 * i];
+    }
+    return sel[0];
+}
+
 // One measurement of slot S.  rho is kept UNNORMALISED (trace `trc`, uniform over the sample's
 // lanes): the new blocks are +-sigma, so trace' = 2 tr(sigma) and no division is needed per step;
 // prob0 = tr(sigma0) / trc decides the outcome exactly as the reference's normalised state does.
 // rule: kDmRuleThreshold = the reference's deterministic rule; kDmRuleSample: outcome 0 with
 // probability prob0 (u = uniform draw); kDmRuleForced: outcome = (u != 0).  pstep receives the
 // probability of the outcome taken.
-constexpr int kDmRuleThreshold = 0, kDmRuleSample = 1, kDmRuleForced = 2;
+constexpr int kDmRuleThreshold = 0, kDmRuleSample = 1, kDmRuleForced = 2, kDmRuleTrace = 3;  // Trace: plane Z, expectation mode
 
 template <int W, int S>
 __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[1 << W], const MeasCoef& q,
@@ -81,8 +98,10 @@ __device__ __forceinline__ void dm_reg_stage(double (&re)[1 << W], double (&im)[
         outcome = (0.5 * t2 < 1e-4 * trc) ? 1 : 0;  // prob0 < 1e-4, np_simulator_dm.py:335-338
     else if (rule == kDmRuleSample)
         outcome = (u * trc < 0.5 * t2) ? 0 : 1;
-    else
+    else if (rule == kDmRuleForced)
         outcome = (u != 0.0) ? 1 : 0;
+    else
+        outcome = 0;
     if (__any_sync(0xffffffffu, outcome)) {
         // rare: sigma1 = tr_s(rho) - sigma0, tr_s(rho) = rho_00 + rho_11 (own diagonal block + partner's)
         double fr[NP], fi[NP];
@@ -226,6 +245,17 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
             }
         }
         const MeasCoef q = meas_coef(st.plane, c, s, t);
+        if (st.plane == MBQC_PLANE_Z) {
+            // expectation mode (np_simulator_dm.py:327-344): record prob1 = tr(P1 E(rho)) / tr(rho)
+            // (P1 = |1><1| seen through the channel: weights pop[2], pop[3] on rho00, rho11)
+            rule = kDmRuleTrace;
+            const bool one = (r >> st.slot) & 1u;
+            const double w1 = t.has_noise ? (one ? t.noise.pop[3] : t.noise.pop[2]) : (one ? 1.0 : 0.0);
+            double p1 = w1 * select_own<W>(re, r);
+#pragma unroll
+            for (int o = N >> 1; o > 0; o >>= 1) p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            if (live && r == 0 && p.expect) p.expect[b * t.n_steps + m] = p1 / trc;
+        }
         // column-parity table of this step's CZ mask, one bit per lane of the sample (0 for tail steps)
         const bool odd = (st.flags & MBQC_STEP_APPEND) && parity64((uint64_t)r & st.nbr_mask);
         const uint32_t colpar = __ballot_sync(0xffffffffu, odd) >> lane_base;

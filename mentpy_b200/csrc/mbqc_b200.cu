@@ -88,7 +88,7 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
         const mbqc_step& s = steps[m];
         if (s.slot < 0 || s.slot >= window) return fail(MBQC_E_ARG, "step %d: slot %d outside window", m, s.slot);
         if (s.angle_idx < -1 || s.angle_idx >= n_angles) return fail(MBQC_E_ARG, "step %d: angle_idx %d outside [ -1, %d)", m, s.angle_idx, n_angles);
-        if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_YZ) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
+        if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_Z) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
         if (s.nbr_mask & ~wmask) return fail(MBQC_E_ARG, "step %d: nbr_mask outside window", m);
         if ((s.nbr_mask >> s.slot) & 1ull) return fail(MBQC_E_ARG, "step %d: nbr_mask contains the step's own slot", m);
     }
@@ -572,14 +572,22 @@ int mbqc_run_batch_sv_f32(const mbqc_plan* plan, const double* d_angles, int64_t
     }
 }
 
-int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
-                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
-                      int8_t* d_outcomes, int32_t* d_status, void* stream) {
+static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                             const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                             int8_t* d_outcomes, double* d_expect, bool expect_mode, int32_t* d_status, void* stream) {
     int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
     if (rc) return rc;
     const int w = plan->tab.window;
     if (w > MBQC_MAX_WINDOW_SMEM_DM)
         return fail(MBQC_E_UNSUPPORTED, "batched DM covers window <= %d (got %d)", MBQC_MAX_WINDOW_SMEM_DM, w);
+    bool has_z = false;
+    for (int m = 0; m < plan->tab.n_steps; ++m) has_z |= plan->h_steps[m].plane == MBQC_PLANE_Z;
+    if (has_z && !expect_mode)
+        return fail(MBQC_E_UNSUPPORTED, "plane-Z steps are drawn at random by the reference outside mode='expectation' "
+                                        "(np_simulator_dm.py:329-333): use mbqc_run_batch_dm_expect");
+    if (has_z && !d_expect) return fail(MBQC_E_ARG, "d_expect is NULL but the plan has plane-Z steps");
+    if (has_z && w > MBQC_MAX_WINDOW_REG)
+        return fail(MBQC_E_UNSUPPORTED, "plane-Z steps cover window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
     if (batch == 0) return MBQC_OK;
     DmBatchParams p;
     memset(&p, 0, sizeof(p));
@@ -593,9 +601,11 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
     p.out = (double2*)d_out;
     p.outcomes = d_outcomes;
     p.status = d_status;
+    p.expect = d_expect;
+    if (d_expect) CUDA_TRY(cudaMemsetAsync(d_expect, 0, sizeof(double) * (size_t)batch * plan->tab.n_steps, (cudaStream_t)stream));
     // w <= 5: one lane per row of rho, registers + shuffles; w = 6: rho in shared memory
     const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
-    if (w <= 5 && !(force && !strcmp(force, "smem"))) {
+    if (w <= 5 && (has_z || !(force && !strcmp(force, "smem")))) {
         const int n = 1 << w, spb = 4 * (32 / n);
         const size_t smem = (size_t)spb * n * n * sizeof(double2);
         const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
@@ -627,6 +637,20 @@ int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t ang
     const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
     dm_smem_kernel<<<blocks, tps * spb, smem, (cudaStream_t)stream>>>(p, tps_log2, spb);
     return after_launch("dm_smem_kernel");
+}
+
+int mbqc_run_batch_dm(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                      const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                      int8_t* d_outcomes, int32_t* d_status, void* stream) {
+    return run_batch_dm_impl(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_outcomes, nullptr,
+                             false, d_status, stream);
+}
+
+int mbqc_run_batch_dm_expect(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                             const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
+                             int8_t* d_outcomes, double* d_expect, int32_t* d_status, void* stream) {
+    return run_batch_dm_impl(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_outcomes, d_expect,
+                             true, d_status, stream);
 }
 
 }  // extern "C"

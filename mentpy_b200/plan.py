@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 
 _PLANE_CODE = {"XY": _lib.PLANE_XY, "X": _lib.PLANE_XY, "Y": _lib.PLANE_XY,
-               "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ}
+               "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ, "Z": _lib.PLANE_Z}
 
 
 @dataclass
@@ -169,11 +169,12 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
         ment = circuit[node]
         plane = ment.plane
         if plane not in _PLANE_CODE:
-            raise NotImplementedError(
-                f"Node {node}: plane {plane} is not supported on the CUDA path "
-                "(plane Z is sampled by the reference even under force0, np_simulator_dm.py:329-333)."
-            )
-        if node in trainable:
+            raise NotImplementedError(f"Node {node}: plane {plane} is not supported on the CUDA path.")
+        if plane == "Z" and window_size > _lib.MAX_WINDOW_REG:
+            raise NotImplementedError(f"plane-Z measurements cover window_size <= {_lib.MAX_WINDOW_REG}")
+        if plane == "Z":  # angle-free; only mode="expectation" runs it (np_simulator_dm.py:327-344)
+            angle_idx, fixed, fc, fs = -1, None, 1.0, 0.0
+        elif node in trainable:
             angle_idx, fixed, fc, fs = trainable.index(node), None, 1.0, 0.0
         else:
             if ment.angle is None:

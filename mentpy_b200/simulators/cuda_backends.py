@@ -333,6 +333,8 @@ class _CudaPatternBase(BaseSimulator):
         if self.current_measurement >= len(self.schedule_measure):
             raise ValueError("No more measurements to be done.")
         st = self.plan.steps[self.current_measurement]
+        if st.plane == _lib.PLANE_Z:
+            return st  # angle-free
         if st.angle_idx >= 0:
             if angle is None:
                 raise ValueError("Measurement is trainable, please provide an angle.")
@@ -573,13 +575,25 @@ class CudaSimulatorDM(_CudaPatternBase):
     def _noise_for_prefix(self):
         return self._noise
 
-    def run_batch(self, angles, input_states=None, check: bool = True, return_outcomes: bool = False):
-        """angles [B,T] -> rho [B,2^k,2^k] (and the outcome record [B,M] if requested)."""
-        return self._run_plan(self._full_plan(), angles, input_states, check, return_outcomes)
+    def run_batch(self, angles, input_states=None, check: bool = True, return_outcomes: bool = False,
+                  mode: str = "sample"):
+        """angles [B,T] -> rho [B,2^k,2^k] (and the outcome record [B,M] if requested).
 
-    def _run_plan(self, dplan, angles, input_states, check, return_outcomes):
+        Patterns with plane-Z nodes need mode="expectation" (np_simulator_dm.py:327-344): those
+        qubits are traced out unprojected and their entry of the outcome record is prob1 (the
+        record is then float64); in mode="sample" the reference draws them at random."""
+        return self._run_plan(self._full_plan(), angles, input_states, check, return_outcomes, mode)
+
+    def _has_z(self, n_steps):
+        return any(st.plane == _lib.PLANE_Z for st in self.plan.steps[:n_steps])
+
+    def _run_plan(self, dplan, angles, input_states, check, return_outcomes, zmode="sample"):
         dev = self._dev()
         lib = _lib.load()
+        expect = self._has_z(dplan.n_steps)
+        if expect and zmode not in ("expectation", "exp"):
+            raise NotImplementedError("plane-Z nodes are drawn at random by the reference in mode='sample' "
+                                      "(np_simulator_dm.py:329-333); use mode='expectation'")
         with torch.cuda.device(dev):
             a, on_host = self._stage_angles(angles, dev)
             batch = a.shape[0]
@@ -588,9 +602,16 @@ class CudaSimulatorDM(_CudaPatternBase):
             out = torch.empty((batch, dim, dim), dtype=torch.complex128, device=dev)
             status = torch.empty(batch, dtype=torch.int32, device=dev)
             outc = torch.zeros((batch, max(dplan.n_steps, 1)), dtype=torch.int8, device=dev)
-            _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
-                                             batch, _ptr(out), _ptr(outc), _ptr(status),
-                                             torch.cuda.current_stream(dev).cuda_stream))
+            if expect:
+                zp = torch.empty((batch, max(dplan.n_steps, 1)), dtype=torch.float64, device=dev)
+                _lib.check(lib.mbqc_run_batch_dm_expect(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
+                                                        batch, _ptr(out), _ptr(outc), _ptr(zp), _ptr(status),
+                                                        torch.cuda.current_stream(dev).cuda_stream))
+                outc = outc.to(torch.float64) + zp  # plane-Z entries: prob1; the others stay 0 / 1
+            else:
+                _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
+                                                 batch, _ptr(out), _ptr(outc), _ptr(status),
+                                                 torch.cuda.current_stream(dev).cuda_stream))
             if on_host:
                 res = out.cpu().numpy()
                 oc = outc.cpu().numpy()[:, : dplan.n_steps]
@@ -604,15 +625,16 @@ class CudaSimulatorDM(_CudaPatternBase):
         st = self._record_angle(angle)
         self.current_measurement += 1
         dplan, _nodes = self._prefix_plan(self.current_measurement)
-        rho, oc = self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, True)
-        outcome = int(oc[0, self.current_measurement - 1])
+        rho, oc = self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, True, mode)
+        outcome = oc[0, self.current_measurement - 1]
+        outcome = float(outcome) if st.plane == _lib.PLANE_Z else int(outcome)
         self.outcomes[st.node] = outcome
         return rho[0], outcome
 
     @property
     def qstate(self) -> np.ndarray:
         dplan, _nodes = self._prefix_plan(self.current_measurement)
-        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, False)[0]
+        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, False, "expectation")[0]
 
     def run(self, angles: List[float], mode="sample", input_state=None):
         if input_state is not None:
@@ -627,10 +649,11 @@ class CudaSimulatorDM(_CudaPatternBase):
             res = self._sampled_run(angles, "dm")
             self.current_measurement = len(self.schedule_measure)
             return res
-        rho, oc = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], return_outcomes=True)
+        rho, oc = self.run_batch(np.asarray(angles, dtype=np.float64)[None, :], return_outcomes=True, mode=mode)
         self.current_measurement = len(self.schedule_measure)
         self._angles_seen[: self.plan.n_angles] = np.asarray(angles, dtype=np.float64)
-        self.outcomes = {v: int(o) for v, o in zip(self.schedule_measure, oc[0])}
+        self.outcomes = {st.node: (float(o) if st.plane == _lib.PLANE_Z else int(o))
+                         for st, o in zip(self.plan.steps, oc[0])}
         return rho[0]
 
     def reorder_qubits(self, state, current_order, target_order):

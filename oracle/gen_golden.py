@@ -199,6 +199,31 @@ def main():
                    "pattern": PatternData.from_circuit(gs).to_json(),
                    "input_state": cplx(inp), "runs": quirk}, f)
 
+    # 2c. plane-Z measurements in mode="expectation" (np_simulator_dm.py:327-344): the qubit is traced
+    # out unprojected and the recorded "outcome" is prob1 -- the classifier read-out of a pattern
+    zcases = []
+    for spec, seed, w, planes, haar in (
+            (("grid_cluster", [2, 4], {}), 30, None, {3: "Z", 7: "Z"}, False),
+            (("grid_cluster", [2, 5], {}), 31, 4, {2: "Z", 6: "X"}, True),
+            (("linear_cluster", [6], {}), 32, 3, {2: "Z", 5: "Z"}, True),
+            (("grid_cluster", [3, 4], {}), 33, None, {3: "Z", 7: "Z", 11: "Z", 5: "Y"}, True)):
+        gs = build(mp, spec)
+        for v, pl in planes.items():
+            gs[v] = mp.Ment(pl)
+        T = len(gs.trainable_nodes)
+        angles = np.random.default_rng(seed).uniform(0, 2 * np.pi, T)
+        inp = haar_state(len(gs.input_nodes), seed) if haar else None
+        kw = {} if w is None else {"window_size": w}
+        ps = mp.PatternSimulator(gs, input_state=inp, backend="numpy-dm", **kw)
+        out = ps.run(angles, mode="expectation")
+        zcases.append({"spec": spec, "seed": seed, "window_size": int(ps.window_size),
+                       "planes": {str(k): v for k, v in planes.items()},
+                       "pattern": PatternData.from_circuit(gs).to_json(), "angles": angles.tolist(),
+                       "input_state": None if inp is None else cplx(inp), "output": cplx(out),
+                       "outcomes": {str(k): float(v) for k, v in ps.outcomes.items()}})
+    with open(os.path.join(GOLDEN, "dm_z_expectation.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py", "source": "bestquark/mentpy (unmodified)", "cases": zcases}, f)
+
     # 3. gradient + optimiser known answers: grid_cluster(4,5), cost 1 - <t|rho|t>
     gs = mp.templates.grid_cluster(4, 5)
     ps = mp.PatternSimulator(gs, backend="numpy-sv")

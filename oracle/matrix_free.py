@@ -89,6 +89,8 @@ def _angles_for_step(pat, node, angles):
         return "XY", np.zeros(angles.shape[0])
     if plane == "Y":
         return "XY", np.full(angles.shape[0], np.pi / 2)
+    if plane == "Z":
+        return "Z", np.zeros(angles.shape[0])
     return plane, np.full(angles.shape[0], fixed)
 
 
@@ -204,13 +206,17 @@ def _projector(plane, th):
         return (1 + s) / 2, (1 - s) / 2, 0.5 * c + 0j
     if plane == "YZ":
         return (1 + s) / 2, (1 - s) / 2, 0.5j * c
+    if plane == "Z":
+        return np.ones_like(c), np.zeros_like(c), np.zeros_like(c) + 0j
     raise NotImplementedError(f"plane {plane}")
 
 
 def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
-                 noise=None, noise_kwargs=None, return_outcomes=False):
+                 noise=None, noise_kwargs=None, return_outcomes=False, mode="sample"):
     """Batched restatement of NumpySimulatorDM.run (np_simulator_dm.py:218-283) + optional noise.
-    angles [B,T] -> rho [B,2^k,2^k]."""
+    angles [B,T] -> rho [B,2^k,2^k].  Plane-Z nodes: mode="expectation" traces the qubit out
+    unprojected and records prob1 as the (float) outcome (np_simulator_dm.py:327-344); in
+    mode="sample" the reference draws them at random even under force0 -- not restated."""
     angles = np.atleast_2d(np.asarray(angles, dtype=float))
     B = angles.shape[0]
     schedule, sched_meas, w = _plan(pat, window_size, schedule, mixed=True)
@@ -218,7 +224,10 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
     rho = psi[:, :, None] * np.conj(psi[:, None, :])
     kr = kraus_ops(noise, **(noise_kwargs or {})) if noise else None
     N = pat.n_nodes
-    outcomes = np.zeros((B, len(sched_meas)), dtype=np.int8)
+    has_z = any(pat.measurements[v][0] == "Z" for v in sched_meas)
+    outcomes = np.zeros((B, len(sched_meas)), dtype=np.float64 if has_z else np.int8)
+    if has_z and mode not in ("expectation", "exp"):
+        raise NotImplementedError("plane Z in mode='sample' is random in the reference")
     for cm0, node in enumerate(sched_meas):
         plane, th = _angles_for_step(pat, node, angles)
         if kr is not None:
@@ -232,10 +241,14 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
         full = r00 + r11
         prob0 = np.real(np.trace(sig0, axis1=1, axis2=2))
         prob1 = np.real(np.trace(full, axis1=1, axis2=2)) - prob0
-        take1 = prob0 < 1e-4
-        outcomes[:, cm0] = take1
-        sig = np.where(take1[:, None, None], (full - sig0) / np.where(take1, prob1, 1.0)[:, None, None],
-                       sig0 / np.where(take1, 1.0, prob0)[:, None, None])
+        if plane == "Z":  # expectation mode: no projection, outcome = prob1 / (prob0 + prob1)
+            outcomes[:, cm0] = prob1 / (prob0 + prob1)
+            sig = full
+        else:
+            take1 = prob0 < 1e-4
+            outcomes[:, cm0] = take1
+            sig = np.where(take1[:, None, None], (full - sig0) / np.where(take1, prob1, 1.0)[:, None, None],
+                           sig0 / np.where(take1, 1.0, prob0)[:, None, None])
         cm = cm0 + 1
         if cm + w <= N:
             win = schedule[cm : cm + w]

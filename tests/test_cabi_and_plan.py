@@ -87,7 +87,17 @@ def test_lowering_errors_mirror_reference():
     with pytest.raises(ValueError, match="only XY plane is supported"):
         lower(gs)
     lower(gs, mixed=True)
-    gs[1] = mb.Ment("Z")
+    gs[1] = mb.Ment("Z")  # DM path only (mode="expectation"), angle-free, register kernels only
+    zp = lower(gs, mixed=True)
+    zs = next(st for st in zp.steps if st.node == 1)
+    assert zs.plane == _lib.PLANE_Z and zs.angle_idx == -1 and zp.n_angles == len(gs.trainable_nodes) == 5
+    with pytest.raises(ValueError, match="only XY plane is supported"):
+        lower(gs)
+    big = mb.templates.grid_cluster(6, 3)
+    big[1] = mb.Ment("Z")
+    with pytest.raises(NotImplementedError):
+        lower(big, mixed=True)
+    gs[1] = mb.Ment((0.1, 0.2), "XYZ")
     with pytest.raises(NotImplementedError):
         lower(gs, mixed=True)
     tri = mb.MBQCircuit(mb.GraphState([(0, 1), (1, 2), (2, 0)]), input_nodes=[0], output_nodes=[2])

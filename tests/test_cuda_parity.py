@@ -609,3 +609,50 @@ def test_async_host_calls_match_blocking_calls():
     lib = mb._lib.load()
     import ctypes as C
     assert lib.mbqc_host_wait(0, None) == mb._lib.MBQC_E_ARG and b"not in flight" in lib.mbqc_last_error()
+
+
+def test_plane_z_expectation_mode():
+    """Plane-Z nodes in mode='expectation' (np_simulator_dm.py:327-344): the qubit is traced out
+    and prob1 recorded -- against the reference (tests/golden/dm_z_expectation.json), the oracle
+    (batch, noise) and the stateful API."""
+    from scipy.stats import unitary_group
+
+    for c in load_golden("dm_z_expectation.json")["cases"]:
+        name, args, kwargs = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kwargs)
+        for v, pl in c["planes"].items():
+            gs[int(v)] = mb.Ment(pl)
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])
+        ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"])
+        ang = np.asarray(c["angles"])
+        rho = ps.run(ang, mode="expectation")
+        want = from_cplx(c["output"])
+        assert rho.shape == want.shape and np.abs(rho - want).max() < 1e-12
+        assert {str(k): v for k, v in ps.outcomes.items()}.keys() == c["outcomes"].keys()
+        for k, v in ps.outcomes.items():
+            assert abs(v - c["outcomes"][str(k)]) < 1e-12
+            assert isinstance(v, float) == (c["planes"].get(str(k)) == "Z")
+        ps.reset()
+        with pytest.raises(NotImplementedError):
+            ps.run(ang)                                   # mode="sample": random in the reference
+        ps.reset()
+        for node in ps.schedule_measure:                  # step-by-step API
+            a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
+            st, oc = ps.measure(a, mode="expectation")
+            assert abs(oc - c["outcomes"][str(node)]) < 1e-12
+        assert np.abs(st - want).max() < 1e-12
+        # batch + noise against the oracle
+        pat = PatternData.from_circuit(gs)
+        B, n_in = 33, len(gs.input_nodes)
+        A = np.random.default_rng(3).uniform(0, 2 * np.pi, (B, len(ang)))
+        ins = np.stack([unitary_group.rvs(2**n_in, random_state=s)[:, 0] for s in range(B)])
+        for noise in ({}, {"circuit_noise": "amplitude_damping", "p": 0.2}, {"circuit_noise": "depolarizing", "p": 0.1}):
+            pn = mb.PatternSimulator(gs, backend="cuda-dm", window_size=c["window_size"], **noise)
+            got, oc = pn.run_batch(A, input_states=ins, return_outcomes=True, mode="expectation")
+            kw = {k: v for k, v in noise.items() if k != "circuit_noise"}
+            ref, roc = matrix_free.run_dm_batch(pat, A, input_states=ins, window_size=c["window_size"],
+                                                noise=noise.get("circuit_noise"), noise_kwargs=kw,
+                                                return_outcomes=True, mode="expectation")
+            assert np.abs(got - ref).max() < 1e-11 and np.abs(oc - roc).max() < 1e-11
+    with pytest.raises(ValueError):
+        mb.PatternSimulator(gs, backend="cuda-sv")        # SV path: XY planes only, like the reference

@@ -152,3 +152,20 @@ def test_noise_windowed_equals_fullgraph():
             assert dm_distance(a, b) < 1e-12, (case["spec"], kind)
             done += 1
     assert done >= 12
+
+
+def test_plane_z_expectation_mode_oracle():
+    """Plane-Z nodes in mode='expectation' (np_simulator_dm.py:327-344): recorded prob1 and final
+    state against the reference."""
+    for c in load_golden("dm_z_expectation.json")["cases"]:
+        pat = PatternData.from_json(c["pattern"])
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])[None]
+        rho, oc = matrix_free.run_dm_batch(pat, np.asarray(c["angles"])[None], input_states=inp,
+                                           window_size=c["window_size"], return_outcomes=True, mode="expectation")
+        want = from_cplx(c["output"])
+        assert rho[0].shape == want.shape and np.abs(rho[0] - want).max() < 1e-12
+        sched_meas = [v for v in pat.measurement_order if v not in pat.quantum_output_nodes]
+        for m, v in enumerate(sched_meas):
+            assert abs(oc[0, m] - c["outcomes"][str(v)]) < 1e-12
+    with pytest.raises(NotImplementedError):
+        matrix_free.run_dm_batch(pat, np.asarray(c["angles"])[None], window_size=c["window_size"])
