@@ -1,0 +1,56 @@
+"""Seeded random MBQC patterns built through the PUBLIC circuit API (templates, hstack, vstack,
+merge, Ment), usable with the reference package (`mp`) and with mentpy_b200 (`mb`) alike -- the
+generator only calls names both expose.  Used to fuzz the oracle against the live reference (CPU,
+build container) and the CUDA path against the oracle (GPU)."""
+import numpy as np
+
+
+def random_pattern(lib, seed: int, mixed: bool):
+    """-> (circuit, window_size, angles [T], input_state [2^|I|])."""
+    from scipy.stats import unitary_group
+
+    rng = np.random.default_rng(seed)
+    T = lib.templates
+
+    def base():
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            return T.linear_cluster(int(rng.integers(3, 8)))
+        if kind == 1:
+            return T.grid_cluster(2, int(rng.integers(2, 6)))
+        if kind == 2:
+            return T.grid_cluster(3, int(rng.integers(2, 5)))
+        return T.muta(2, 1, one_column=True)
+
+    gs = base()
+    op = rng.integers(0, 4)
+    if op == 1:  # extend every wire with another block of the same height
+        rows = len(gs.output_nodes)
+        tail = T.linear_cluster(int(rng.integers(2, 5))) if rows == 1 else T.grid_cluster(rows, int(rng.integers(2, 4)))
+        gs = lib.hstack([gs, tail])
+    elif op == 2 and len(gs.input_nodes) <= 2:  # independent extra wire
+        gs = lib.vstack([gs, T.linear_cluster(int(rng.integers(2, 5)))])
+    elif op == 3 and len(gs.output_nodes) >= 1:  # glue a wire onto the first output
+        other = T.linear_cluster(int(rng.integers(2, 5)))
+        gs = lib.merge(gs, other, along=[(gs.output_nodes[0], other.input_nodes[0])])
+    nodes = [v for v in gs.measurement_order if v not in gs.output_nodes]
+    picks = rng.permutation(nodes)[: min(3, len(nodes))]
+    planes = ["X", "Y", "fixed"] + (["XZ", "YZ"] if mixed else [])
+    for v in picks:
+        if len(gs.trainable_nodes) <= 2:
+            break
+        choice = planes[int(rng.integers(0, len(planes)))]
+        if choice == "fixed":
+            gs[int(v)] = lib.Ment(float(rng.uniform(0, 2 * np.pi)), "XY")
+        elif choice in ("XZ", "YZ"):
+            gs[int(v)] = lib.Ment(float(rng.uniform(0, 2 * np.pi)), choice) if rng.integers(0, 2) else lib.Ment(choice)
+        else:
+            gs[int(v)] = lib.Ment(choice)
+    n_in = len(gs.input_nodes)
+    n_meas = len(gs.measurement_order) - len(gs.quantum_output_nodes if mixed else gs.output_nodes)
+    hi = min(n_meas, 5)
+    lo = min(n_in + 1, hi)
+    window = int(rng.integers(lo, hi + 1))
+    angles = rng.uniform(0, 2 * np.pi, len(gs.trainable_nodes))
+    inp = unitary_group.rvs(2**n_in, random_state=int(seed))[:, 0] if n_in else np.ones(1, dtype=complex)
+    return gs, window, angles, inp

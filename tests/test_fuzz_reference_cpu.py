@@ -1,0 +1,70 @@
+"""CPU, build container only (needs /root/reference): the oracle against the LIVE reference on
+seeded random patterns -- composite circuits, random planes, windows and Haar inputs.  This is
+what pins oracle/matrix_free.py beyond the committed golden vectors; the GPU twin
+(test_cuda_fuzz.py) then compares the CUDA path with the oracle on the same generator."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import dm_distance, infidelity_pure
+from fuzz_patterns import random_pattern
+from oracle import matrix_free
+from oracle.pattern_data import PatternData
+from oracle.ref_shim import import_reference, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_oracle_equals_live_reference(seed):
+    mp = import_reference()
+    mixed = seed % 2 == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            gs, w, ang, inp = random_pattern(mp, seed, mixed)
+            ps = mp.PatternSimulator(gs, input_state=inp, backend="numpy-dm" if mixed else "numpy-sv", window_size=w)
+        except Exception as e:  # generator hit a combination the reference itself rejects
+            pytest.skip(f"reference rejects the pattern: {type(e).__name__}")
+        pat = PatternData.from_circuit(gs)
+        if mixed:
+            want = ps.run(ang)
+            got, oc = matrix_free.run_dm_batch(pat, ang[None], input_states=inp[None], window_size=ps.window_size,
+                                               return_outcomes=True)
+            assert dm_distance(got[0], want) < 1e-10
+            assert [int(o) for o in oc[0]] == [int(ps.outcomes[v]) for v in ps.schedule_measure]
+        else:
+            want = ps.run(ang, output_form="sv")
+            got = matrix_free.run_sv_batch(pat, ang[None], input_states=inp[None], window_size=ps.window_size)[0]
+            assert infidelity_pure(got, want) < 1e-10
+            assert np.allclose(got, want, atol=1e-9)  # including the reference's global phase
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_host_indexing_equals_live_reference(seed):
+    """Same seed through both circuit layers: node labels, inputs/outputs, trainable nodes,
+    measurement order and the lowered plan are identical (integer work: bit-exact)."""
+    import mentpy_b200 as mb
+    from mentpy_b200.plan import lower
+
+    mp = import_reference()
+    mixed = seed % 2 == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            ref, w, ang, _ = random_pattern(mp, seed, mixed)
+        except Exception as e:
+            pytest.skip(f"reference rejects the pattern: {type(e).__name__}")
+        mine, w2, ang2, _ = random_pattern(mb, seed, mixed)
+    assert w == w2 and np.array_equal(ang, ang2)
+    assert list(ref.graph.nodes()) == list(mine.graph.nodes())
+    assert sorted(map(sorted, ref.graph.edges())) == sorted(map(sorted, mine.graph.edges()))
+    for attr in ("input_nodes", "output_nodes", "quantum_output_nodes", "trainable_nodes", "measurement_order"):
+        assert list(getattr(ref, attr)) == list(getattr(mine, attr)), attr
+    a, b = lower(ref, window_size=w, mixed=mixed), lower(mine, window_size=w, mixed=mixed)
+    assert (a.schedule, a.input_slot, a.output_slot, a.init_cz_mask) == (b.schedule, b.input_slot, b.output_slot, b.init_cz_mask)
+    for sa, sb in zip(a.steps, b.steps):
+        assert (sa.node, sa.slot, sa.angle_idx, sa.plane, sa.append, sa.new_node, sa.nbr_mask) == \
+               (sb.node, sb.slot, sb.angle_idx, sb.plane, sb.append, sb.new_node, sb.nbr_mask)
+        assert sa.fixed_cos == sb.fixed_cos and sa.fixed_sin == sb.fixed_sin
