@@ -197,7 +197,13 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
                                 new_node, mask, dropped))
 
     remaining = schedule[n_meas:]
-    out_order = list(circuit.quantum_output_nodes if mixed else circuit.output_nodes)
+    # np_simulator_dm.py:267-273 reorders to quantum_output_nodes; np_simulator_sv.py:286-290 leaves
+    # the window order alone when it already equals quantum_output_nodes and otherwise reorders to
+    # output_nodes (the two lists differ in order for merged circuits) -- reproduced as is
+    if mixed or list(circuit.quantum_output_nodes) == remaining:
+        out_order = list(circuit.quantum_output_nodes)
+    else:
+        out_order = list(circuit.output_nodes)
     if set(out_order) != set(remaining):
         raise ValueError(f"Both lists must have the same elements, but source={remaining} and target={out_order}")
     output_slot = [slot_of[v] for v in out_order]

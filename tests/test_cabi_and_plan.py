@@ -74,7 +74,10 @@ def test_lowering_matches_reference_window_bookkeeping():
                         if nb in win_after[:-1]:
                             want |= 1 << slots[nb]
                     assert st.nbr_mask == want
-            assert [pl.slot_of_after(len(pl.steps))[v] for v in pat.output_nodes] == pl.output_slot
+            # np_simulator_sv.py:286-290: window order kept when it equals quantum_output_nodes
+            tail = sched[len(pl.steps):]
+            assert pl.output_nodes == (pat.quantum_output_nodes if pat.quantum_output_nodes == tail else pat.output_nodes)
+            assert [pl.slot_of_after(len(pl.steps))[v] for v in pl.output_nodes] == pl.output_slot
 
 
 def test_lowering_errors_mirror_reference():
@@ -166,3 +169,25 @@ def test_lowering_accepts_reference_circuit_objects():
                                                     sb.new_node, sb.nbr_mask, sb.fixed_cos, sb.fixed_sin)
         sim = mb.simulators.CudaSimulatorSV(ref, None, window_size=w)   # constructs without a GPU
         assert sim.window_size == a.window
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_lowered_plan_emulation_matches_oracle_on_random_patterns(seed):
+    """The lowered plan (slots, sign masks, input / output slot lists), executed by a numpy
+    emulation of the kernels' index arithmetic, against the oracle on the fuzz patterns -- catches
+    lowering errors (e.g. the SV output-order rule for merged circuits) without a GPU."""
+    from fuzz_patterns import random_pattern
+    from oracle import matrix_free
+    from plan_emulator import run_dm, run_sv
+
+    mixed = seed % 2 == 1
+    gs, w, ang, inp = random_pattern(mb, seed, mixed)
+    pat = PatternData.from_circuit(gs)
+    pl = lower(gs, window_size=w, mixed=mixed)
+    if mixed:
+        want, woc = matrix_free.run_dm_batch(pat, ang[None], input_states=inp[None], window_size=w, return_outcomes=True)
+        got, oc = run_dm(pl, ang, inp)
+        assert np.abs(got - want[0]).max() < 1e-10 and oc == [int(o) for o in woc[0]]
+    else:
+        want = matrix_free.run_sv_batch(pat, ang[None], input_states=inp[None], window_size=w)[0]
+        assert 1 - abs(np.vdot(run_sv(pl, ang, inp), want)) ** 2 < 1e-10
