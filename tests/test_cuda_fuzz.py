@@ -36,3 +36,26 @@ def test_cuda_equals_oracle_on_random_patterns(seed):
         st = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv-stream", window_size=w)
         psi = st.run(ang, output_form="sv")
         assert 1 - abs(np.vdot(psi, want[0])) ** 2 < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(0, 40, 2))
+def test_sampled_runs_equal_oracle_on_random_patterns(seed):
+    """force0=False on the random SV patterns: outcome records bit-exact, corrected states equal."""
+    from oracle import feedforward as off
+
+    gs, w, ang, inp = random_pattern(mb, seed, False)
+    pat = PatternData.from_circuit(gs)
+    flow = {v: gs.flow(v) for v in gs.measurement_order if v not in gs.output_nodes}
+    A = np.vstack([ang[None], np.random.default_rng(2000 + seed).uniform(0, 2 * np.pi, (63, len(ang)))])
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=w, force0=False, seed=seed)
+    got = ps.sample_batch(A, sample_offset=5)
+    # the oracle orders outputs like quantum_output_nodes; the plan may use output_nodes (SV rule)
+    want, oc, prob, (xb, zb) = off.run_sv_sampled(pat, flow, A, seed=seed, sample_offset=5, input_states=inp[None],
+                                                  window_size=ps.window_size)
+    assert np.array_equal(got.outcomes, oc)
+    assert np.allclose(got.prob, prob, rtol=1e-9)
+    order = [pat.quantum_output_nodes.index(v) for v in ps.plan.output_nodes]
+    assert np.array_equal(got.x, xb[:, order]) and np.array_equal(got.z, zb[:, order])
+    k = len(order)
+    want = want.reshape([len(A)] + [2] * k).transpose([0] + [1 + p for p in order]).reshape(len(A), -1)
+    assert np.max(1 - np.abs(np.sum(got.states.conj() * want, axis=1)) ** 2) < 1e-10
