@@ -13,16 +13,24 @@ def random_pattern(lib, seed: int, mixed: bool):
     T = lib.templates
 
     def base():
-        kind = rng.integers(0, 4)
+        kind = rng.integers(0, 7)
         if kind == 0:
             return T.linear_cluster(int(rng.integers(3, 8)))
         if kind == 1:
             return T.grid_cluster(2, int(rng.integers(2, 6)))
         if kind == 2:
             return T.grid_cluster(3, int(rng.integers(2, 5)))
-        return T.muta(2, 1, one_column=True)
+        if kind == 3:
+            return T.muta(2, 1, one_column=True)
+        if kind == 4:
+            return T.many_wires([int(x) for x in rng.integers(2, 5, size=int(rng.integers(1, 4)))])
+        if kind == 5:
+            return T.grid_cluster(int(rng.integers(2, 4)), int(rng.integers(3, 5)), periodic=True)
+        return T.muta(2, 1)
 
     gs = base()
+    if len(gs.measurement_order) - len(gs.output_nodes) <= len(gs.input_nodes) + 1:
+        gs = T.linear_cluster(5)  # too few measurements for any window: both simulators refuse those
     op = rng.integers(0, 4)
     if op == 1:  # extend every wire with another block of the same height
         rows = len(gs.output_nodes)
@@ -48,9 +56,11 @@ def random_pattern(lib, seed: int, mixed: bool):
             gs[int(v)] = lib.Ment(choice)
     n_in = len(gs.input_nodes)
     n_meas = len(gs.measurement_order) - len(gs.quantum_output_nodes if mixed else gs.output_nodes)
-    hi = min(n_meas, 5)
+    hi = min(n_meas, 6 if mixed else 8)   # register, shared-memory and (SV) streaming kernels
     lo = min(n_in + 1, hi)
-    window = int(rng.integers(lo, hi + 1))
+    window = max(int(rng.integers(lo, hi + 1)), 2)  # window_size=1 means "default" in the reference
     angles = rng.uniform(0, 2 * np.pi, len(gs.trainable_nodes))
     inp = unitary_group.rvs(2**n_in, random_state=int(seed))[:, 0] if n_in else np.ones(1, dtype=complex)
+    if seed % 5 == 0:  # the default |+> input (pattern_simulator.py:58-61)
+        inp = np.full(2**n_in, 2.0 ** (-n_in / 2), dtype=complex)
     return gs, window, angles, inp

@@ -171,7 +171,7 @@ def test_lowering_accepts_reference_circuit_objects():
         assert sim.window_size == a.window
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(100))
 def test_lowered_plan_emulation_matches_oracle_on_random_patterns(seed):
     """The lowered plan (slots, sign masks, input / output slot lists), executed by a numpy
     emulation of the kernels' index arithmetic, against the oracle on the fuzz patterns -- catches

@@ -12,7 +12,7 @@ from oracle.pattern_data import PatternData
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(100))
 def test_cuda_equals_oracle_on_random_patterns(seed):
     mixed = seed % 2 == 1
     gs, w, ang, inp = random_pattern(mb, seed, mixed)
@@ -38,7 +38,7 @@ def test_cuda_equals_oracle_on_random_patterns(seed):
         assert 1 - abs(np.vdot(psi, want[0])) ** 2 < 1e-10
 
 
-@pytest.mark.parametrize("seed", range(0, 40, 2))
+@pytest.mark.parametrize("seed", range(0, 100, 2))
 def test_sampled_runs_equal_oracle_on_random_patterns(seed):
     """force0=False on the random SV patterns: outcome records bit-exact, corrected states equal."""
     from oracle import feedforward as off
@@ -47,6 +47,12 @@ def test_sampled_runs_equal_oracle_on_random_patterns(seed):
     pat = PatternData.from_circuit(gs)
     flow = {v: gs.flow(v) for v in gs.measurement_order if v not in gs.output_nodes}
     A = np.vstack([ang[None], np.random.default_rng(2000 + seed).uniform(0, 2 * np.pi, (63, len(ang)))])
+    if w > 5:
+        with pytest.raises(NotImplementedError):
+            mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=w, force0=False)
+        w = 5 if len(gs.input_nodes) <= 5 else None
+        if w is None:
+            pytest.skip("more inputs than the sampled kernels' window")
     ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=w, force0=False, seed=seed)
     got = ps.sample_batch(A, sample_offset=5)
     # the oracle orders outputs like quantum_output_nodes; the plan may use output_nodes (SV rule)

@@ -16,7 +16,7 @@ from oracle.ref_shim import import_reference, reference_available
 pytestmark = pytest.mark.skipif(not reference_available(), reason="reference tree not present")
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(100))
 def test_oracle_equals_live_reference(seed):
     mp = import_reference()
     mixed = seed % 2 == 1
@@ -41,7 +41,7 @@ def test_oracle_equals_live_reference(seed):
             assert np.allclose(got, want, atol=1e-9)  # including the reference's global phase
 
 
-@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("seed", range(100))
 def test_host_indexing_equals_live_reference(seed):
     """Same seed through both circuit layers: node labels, inputs/outputs, trainable nodes,
     measurement order and the lowered plan are identical (integer work: bit-exact)."""
