@@ -65,3 +65,46 @@ def test_sampled_runs_equal_oracle_on_random_patterns(seed):
     k = len(order)
     want = want.reshape([len(A)] + [2] * k).transpose([0] + [1 + p for p in order]).reshape(len(A), -1)
     assert np.max(1 - np.abs(np.sum(got.states.conj() * want, axis=1)) ** 2) < 1e-10
+
+
+@pytest.mark.parametrize("seed", range(1, 100, 4))
+def test_noisy_dm_equals_oracle_on_random_patterns(seed):
+    gs, w, ang, inp = random_pattern(mb, seed, True)
+    pat = PatternData.from_circuit(gs)
+    kinds = [("depolarizing", {"p": 0.07}), ("amplitude_damping", {"p": 0.15}), ("phase_damping", {"p": 0.2}),
+             ("phase_flip", {"p": 0.1}), ("generalized_amplitude_damping", {"p": 0.1, "p_gad": 0.4})]
+    kind, kw = kinds[seed % len(kinds)]
+    A = np.vstack([ang[None], np.random.default_rng(3000 + seed).uniform(0, 2 * np.pi, (8, len(ang)))])
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=w, circuit_noise=kind, **kw)
+    got = ps.run_batch(A)
+    want = matrix_free.run_dm_batch(pat, A, input_states=inp[None], window_size=ps.window_size, noise=kind, noise_kwargs=kw)
+    assert dm_distance(got, want) < 1e-10
+    assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", range(0, 100, 4))
+def test_gradients_equal_shifted_oracle_evaluations_on_random_patterns(seed):
+    from mentpy_b200.gradients import psr_gradient_batched
+    from scipy.stats import unitary_group
+
+    gs, w, ang, inp = random_pattern(mb, seed, False)
+    if w > 5:
+        w = 5 if len(gs.input_nodes) < 5 else None
+        if w is None:
+            pytest.skip("window too large for the fused gradient")
+    pat = PatternData.from_circuit(gs)
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=w)
+    k = len(gs.output_nodes)
+    tgt = unitary_group.rvs(2**k, random_state=seed)[:, 0]
+    X = np.vstack([ang[None], np.random.default_rng(4000 + seed).uniform(0, 2 * np.pi, (4, len(ang)))])
+    g, c = psr_gradient_batched(ps, X, tgt, return_cost=True)
+
+    def cost(Y):  # the oracle follows the same output-order rule as the plan
+        psi = matrix_free.run_sv_batch(pat, Y, input_states=inp[None], window_size=ps.window_size)
+        return 1 - np.abs(psi @ tgt.conj()) ** 2
+
+    assert np.allclose(c, cost(X), atol=1e-11)
+    T = len(ang)
+    for i in range(T):
+        e = np.zeros(T); e[i] = 1.5
+        assert np.allclose(g[:, i], (cost(X + e) - cost(X - e)) / 3.0, atol=1e-10)
