@@ -213,6 +213,29 @@ int mbqc_psr_grad_dataset(const mbqc_plan* plan, const double* d_angles, int64_t
                           double shift, double* d_grad, double* d_cost, int32_t* d_status,
                           void* d_workspace, void* stream);
 
+/* Device-resident training loop: num_iters iterations of [data-set gradient -> optimiser update]
+ * queued on `stream` from one call, two kernel launches per iteration, nothing returns to the
+ * host in between (the reference does 2T x S simulator runs and one numpy update per iteration:
+ * optimizers/adam.py:54-108, sgd.py:49-96 driven by gradients/_parameter_shift.py:9-25).
+ * d_x [P][T] (contiguous) is updated in place.  d_state: caller-owned, [2][P][T] doubles (Adam m, v;
+ * SGD uses the first half as velocity), zeroed by the caller before the first call;
+ * first_iteration = number of updates already applied (Adam's bias correction continues from
+ * there).  d_cost_history (may be NULL) [num_iters][P]: data-set cost BEFORE each update.
+ * d_status (may be NULL) [P]: OR over all iterations.  d_workspace: as mbqc_psr_grad_dataset. */
+#define MBQC_OPT_ADAM 1
+#define MBQC_OPT_SGD 2
+typedef struct mbqc_optimizer {
+    int32_t kind;     /* MBQC_OPT_* */
+    int32_t nesterov; /* SGD only */
+    double step_size;
+    double b1, b2, eps; /* Adam */
+    double momentum;    /* SGD */
+} mbqc_optimizer;
+int mbqc_train_dataset(const mbqc_plan* plan, double* d_x, const void* d_inputs, const void* d_targets,
+                       int64_t n_vectors, int64_t n_data, double shift, const mbqc_optimizer* opt,
+                       int32_t first_iteration, int32_t num_iters, double* d_state, double* d_cost_history,
+                       int32_t* d_status, void* d_workspace, void* stream);
+
 /* ---- streaming regime: one large window resident in HBM, one angle set -------------------------
  * Replaces NumpySimulatorSV.reset / measure / run for windows the reference cannot hold (it
  * materialises 2^w x 2^w operators: np_simulator_sv.py:103-128, :164-225, :286-297).  The state is

@@ -26,6 +26,14 @@ class Step(C.Structure):
                 ("nbr_mask", C.c_uint64)]
 
 
+class Optimizer(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nesterov", C.c_int32), ("step_size", C.c_double), ("b1", C.c_double),
+                ("b2", C.c_double), ("eps", C.c_double), ("momentum", C.c_double)]
+
+
+OPT_ADAM, OPT_SGD = 1, 2
+
+
 class FeedForwardC(C.Structure):
     _fields_ = [("xdep", C.c_uint32), ("zdep", C.c_uint32), ("outx", C.c_uint32), ("outz", C.c_uint32)]
 
@@ -87,6 +95,9 @@ _SIGNATURES = {
     "mbqc_psr_grad_dataset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mbqc_train_dataset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
+                                     C.POINTER(Optimizer), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_stream_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_void_p, C.c_double, C.c_void_p]),
     "mbqc_stream_steps": (C.c_int, [C.c_void_p, C.POINTER(StreamDesc), C.c_void_p]),

@@ -214,9 +214,39 @@ __global__ void __launch_bounds__(128) sv_reg_grad_prefix_kernel(const __grid_co
 // fixed order (deterministic result), lanes are combined through shared memory.
 constexpr int kReduceThreads = 256;
 
+// optimiser update fused into the reduction (device-resident training loop, mbqc_train_dataset);
+// formulas and operation order of mentpy/optimizers/adam.py:54-66 and sgd.py:49-59
+struct OptimDev {
+    int32_t kind;  // 0: none (plain gradient), MBQC_OPT_ADAM, MBQC_OPT_SGD
+    int32_t nesterov;
+    double step_size, b1, b2, eps, momentum;
+    double bias1, bias2;  // Adam: 1 - b1^t, 1 - b2^t of this iteration
+    double* x;            // [P][T] parameters, updated in place
+    double* s0;           // Adam m / SGD velocity
+    double* s1;           // Adam v
+};
+
+__device__ __forceinline__ void optimiser_update(const OptimDev& o, int64_t e, double g) {
+    // explicit _rn operations: no FMA contraction, so the trajectory matches the host formulas
+    if (o.kind == MBQC_OPT_ADAM) {
+        const double m = __dadd_rn(__dmul_rn(o.b1, o.s0[e]), __dmul_rn(1.0 - o.b1, g));
+        const double v = __dadd_rn(__dmul_rn(o.b2, o.s1[e]), __dmul_rn(__dmul_rn(1.0 - o.b2, g), g));
+        o.s0[e] = m;
+        o.s1[e] = v;
+        const double m_hat = m / o.bias1, v_hat = v / o.bias2;
+        o.x[e] = o.x[e] - __dmul_rn(o.step_size, m_hat) / (sqrt(v_hat) + o.eps);
+    } else if (o.kind == MBQC_OPT_SGD) {
+        const double vel = __dadd_rn(__dmul_rn(o.momentum, o.s0[e]), -__dmul_rn(o.step_size, g));
+        o.s0[e] = vel;
+        o.x[e] = o.nesterov ? __dadd_rn(__dadd_rn(o.x[e], __dmul_rn(o.momentum, vel)), -__dmul_rn(o.step_size, g))
+                            : __dadd_rn(o.x[e], vel);
+    }
+}
+
 __global__ void __launch_bounds__(kReduceThreads) grad_dataset_reduce_kernel(
     const double* __restrict__ ws_grad, const double* __restrict__ ws_cost, const int32_t* __restrict__ ws_status,
-    int64_t S, int T, double* __restrict__ grad, double* __restrict__ cost, int32_t* __restrict__ status) {
+    int64_t S, int T, double* __restrict__ grad, double* __restrict__ cost, int32_t* __restrict__ status,
+    int accumulate_status, const __grid_constant__ OptimDev opt) {
     __shared__ double part[kReduceThreads];
     __shared__ int32_t st_any;
     const int64_t p = blockIdx.x;
@@ -237,7 +267,9 @@ __global__ void __launch_bounds__(kReduceThreads) grad_dataset_reduce_kernel(
         __syncthreads();
         if (lane == 0 && col < T) {
             for (int j = 1; j < L; ++j) sum += part[j * Tc + c0];
-            grad[p * T + col] = sum * inv;
+            const double g = sum * inv;
+            if (grad) grad[p * T + col] = g;
+            if (opt.kind) optimiser_update(opt, p * T + col, g);
         }
         __syncthreads();
     }
@@ -253,7 +285,7 @@ __global__ void __launch_bounds__(kReduceThreads) grad_dataset_reduce_kernel(
     if (tid == 0) {
         for (int j = 1; j < kReduceThreads; ++j) csum += part[j];
         if (cost) cost[p] = csum * inv;
-        if (status) status[p] = st_any;
+        if (status) status[p] = accumulate_status ? (status[p] | st_any) : st_any;
     }
 }
 

