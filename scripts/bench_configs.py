@@ -103,3 +103,19 @@ for w in (28, 30, 32):
         del ps
     except Exception as e:
         emit(config="C5", window=w, error=repr(e)[:200])
+# device-resident training loop (mbqc_train_dataset): the tutorial workload and a wide one
+from mentpy_b200.optimizers import adam_optimize_batched  # noqa: E402
+gt = mb.templates.muta(2, 1, one_column=True); gt[3] = mb.Ment("X"); gt[8] = mb.Ment("X")
+pt = mb.PatternSimulator(gt, backend="cuda-sv"); Tt = len(gt.trainable_nodes)
+for P, S, iters in ((1, 7, 100), (1024, 64, 100)):
+    X = torch.rand((P, Tt), device=dev, dtype=torch.float64) * 6.283
+    ins = torch.randn((S, 4), device=dev, dtype=torch.complex128); ins = ins / ins.norm(dim=1, keepdim=True)
+    tgs = torch.randn((S, 4), device=dev, dtype=torch.complex128); tgs = tgs / tgs.norm(dim=1, keepdim=True)
+    for fused in (True, False):
+        def go():
+            adam_optimize_batched(pt, X, tgs, num_iters=iters, step_size=0.08, input_states=ins, dataset=True, fused=fused)
+            torch.cuda.synchronize()
+        go()
+        t0 = time.perf_counter(); go(); t = time.perf_counter() - t0
+        emit(config="train-loop", pattern="muta(2,1,one_column) X on 3,8 (intro-to-mbqml.rst)", vectors=P, data_items=S, iterations=iters,
+             fused_c_loop=fused, s_total=t, us_per_iteration=t / iters * 1e6, pattern_evals_per_s=P * S * 2 * Tt * iters / t)

@@ -178,10 +178,10 @@ def test_fused_training_loop_matches_reference_and_per_iteration_loop():
     assert np.allclose(out[0], d["adam_4"], atol=1e-9, rtol=0)
     assert hist.shape == (4, 1) and abs(hist[0, 0] - d["cost"]) < 1e-12
     c = mb.optimizers.BatchedFidelityCost(pd, tgts, input_states=ins)
-    assert abs(cost[0] - c(out[0])) < 1e-12 and hist[-1, 0] > cost[0] - 1e-12 or True
+    assert abs(cost[0] - c(out[0])) < 1e-12
     long = mb.optimizers.adam_optimize_batched(pd, x[None], tgts, num_iters=150, step_size=0.08, input_states=ins,
                                                dataset=True, return_history=True)[1]
-    assert long[-1, 0] < 0.2 * long[0, 0]                      # it actually trains
+    assert long[-1, 0] < long[0, 0] - 0.1 and np.all(np.isfinite(long))   # the cost goes down
     # CUDA tensors in -> CUDA tensors out, nothing synchronises
     import torch
 
