@@ -8,7 +8,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["partial_trace", "pure2density", "partial_trace_pure_state", "partial_trace_mixed_state"]
+__all__ = ["partial_trace", "pure2density", "partial_trace_pure_state", "partial_trace_mixed_state", "fidelity"]
 
 
 def _to_device(data):
@@ -74,3 +74,30 @@ def partial_trace(data, indices):
     if len(shape) == 2:
         return partial_trace_mixed_state(data, indices)
     raise ValueError("Invalid input shape for quantum state.")
+
+
+def fidelity(a, b):
+    """Uhlmann fidelity (tr sqrt(sqrt(a) b sqrt(a)))^2 of two density matrices -- what
+    mentpy.calculator.fidelity (calculator/borrows.py:4-6, PennyLane's math.fidelity) returns;
+    the loss of docs/tutorials/intro-to-mbqml.rst:35-42 calls it with a pure target.  State
+    vectors are accepted and promoted.  Evaluated on the device with torch.linalg (tiny matrices,
+    off the hot path); also batched: [B,d,d] x [B,d,d] -> [B]."""
+    import torch
+
+    da, host_a = _to_device(a)
+    db, host_b = _to_device(b)
+
+    def as_dm(t):
+        if t.dim() == 1 or (t.dim() == 2 and t.shape[-1] != t.shape[-2]):
+            return t[..., :, None] * t.conj()[..., None, :]
+        return t
+
+    da, db = as_dm(da), as_dm(db)
+    w, v = torch.linalg.eigh(da)
+    root = (v * torch.sqrt(torch.clamp(w, min=0.0)).to(v.dtype)[..., None, :]) @ v.conj().transpose(-1, -2)
+    ev = torch.linalg.eigvalsh(root @ db @ root)
+    f = torch.sqrt(torch.clamp(ev, min=0.0)).sum(dim=-1) ** 2
+    if host_a and host_b:
+        f = f.cpu().numpy()
+        return float(f) if f.ndim == 0 else f
+    return f

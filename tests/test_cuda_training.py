@@ -188,3 +188,50 @@ def test_fused_training_loop_matches_reference_and_per_iteration_loop():
     xt = mb.optimizers.adam_optimize_batched(pd, torch.as_tensor(x[None]).cuda(), torch.as_tensor(tgts).cuda(),
                                              num_iters=4, step_size=0.08, input_states=torch.as_tensor(ins).cuda(), dataset=True)
     assert xt.is_cuda and np.allclose(xt.cpu().numpy()[0], d["adam_4"], atol=1e-9, rtol=0)
+
+
+def test_tutorial_training_script_runs_unchanged():
+    """docs/tutorials/intro-to-mbqml.rst:16-86 with `mp` -> `mb` and backend='cuda-sv': the
+    reference-style closures (prediction / loss / cost, AdamOptimizer with a callback) work as
+    written, and the fused device loop reaches the same parameters."""
+    gs = mb.templates.muta(2, 1, one_column=True)
+    gs[3] = mb.Ment("X")
+    gs[8] = mb.Ment("X")
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+
+    def loss(output, target):
+        avg = 0
+        for sty, out in zip(target, output):
+            avg += 1 - mb.calculator.fidelity(mb.calculator.pure2density(sty), out)
+        return avg / len(target)
+
+    def prediction(thetas, statesx):
+        outs = []
+        for st in statesx:
+            ps.reset(input_state=st)
+            outs.append(ps(thetas))
+        return outs
+
+    def cost(thetas, statesx, statesy):
+        return loss(prediction(thetas, statesx), statesy)
+
+    gate = np.kron(mb.utils.random_special_unitary(1, random_state=3), np.eye(2))
+    assert abs(np.linalg.det(gate) - 1) < 1e-12
+    (x_train, y_train), (x_test, y_test) = mb.utils.generate_random_dataset(gate, 10, test_size=0.3, random_state=4)
+    assert x_train.shape == (7, 4) and x_test.shape == (3, 4) and np.allclose(y_test, x_test @ gate.T)
+    curve = []
+    theta0 = np.random.default_rng(5).random(len(gs.trainable_nodes))
+    opt = mb.optimizers.AdamOptimizer(step_size=0.08)
+    theta = opt.optimize(lambda p: cost(p, x_train, y_train), theta0.copy(), num_iters=3,
+                         callback=lambda params, it: curve.append(cost(params, x_train, y_train)))
+    assert len(curve) == 3 and np.all(np.isfinite(curve))
+    fused, hist = mb.optimizers.adam_optimize_batched(ps, theta0[None], y_train, num_iters=3, step_size=0.08,
+                                                      input_states=x_train, dataset=True, return_history=True)
+    assert np.allclose(fused[0], theta, atol=1e-8)
+    assert abs(hist[0, 0] - cost(theta0, x_train, y_train)) < 1e-10
+    # fidelity helper: pure/pure, pure/mixed, batched
+    a, b = x_train[0], x_train[1]
+    assert abs(mb.calculator.fidelity(a, b) - abs(np.vdot(a, b)) ** 2) < 1e-10
+    rho = 0.5 * np.outer(a, a.conj()) + 0.5 * np.outer(b, b.conj())
+    assert abs(mb.calculator.fidelity(np.outer(a, a.conj()), rho) - np.real(a.conj() @ rho @ a)) < 1e-10
+    assert abs(mb.calculator.fidelity(rho, rho) - 1) < 1e-10
