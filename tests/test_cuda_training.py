@@ -234,4 +234,8 @@ def test_tutorial_training_script_runs_unchanged():
     assert abs(mb.calculator.fidelity(a, b) - abs(np.vdot(a, b)) ** 2) < 1e-10
     rho = 0.5 * np.outer(a, a.conj()) + 0.5 * np.outer(b, b.conj())
     assert abs(mb.calculator.fidelity(np.outer(a, a.conj()), rho) - np.real(a.conj() @ rho @ a)) < 1e-10
-    assert abs(mb.calculator.fidelity(rho, rho) - 1) < 1e-10
+    assert abs(mb.calculator.fidelity(rho, rho) - 1) < 1e-7      # general (Uhlmann) branch
+    sig = 0.3 * np.outer(a, a.conj()) + 0.7 * np.eye(4) / 4
+    from scipy.linalg import sqrtm
+    want = np.real(np.trace(sqrtm(sqrtm(rho) @ sig @ sqrtm(rho)))) ** 2
+    assert abs(mb.calculator.fidelity(rho, sig) - want) < 1e-7
