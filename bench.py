@@ -345,10 +345,13 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
         assert bool(torch.isfinite(gathered.real).all().item())
     launches = args.steps  # one kernel per step (graph replays execute `pool` kernel nodes each)
+    ms_per_rank = [ms]
     if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_per_rank = [float(v) for v in t.tolist()]
+        ms = max(ms_per_rank)  # the job is as slow as its slowest rank
     assert int(status.max().item()) == 0, "kernel reported a bad norm"
 
     # same K steps with plain stream launches (no graph), for the record
@@ -445,6 +448,7 @@ def run_gpu_arm(args):
                        "CTA-coalesced results straight into the mapped page-locked output buffer; consecutive calls on alternating stream sets)",
                 "blocking_call": {"value": world * BATCH * e2e_steps / e2e_sync_s, "ms_per_step": 1e3 * e2e_sync_s / e2e_steps,
                                   "api": "run_batch(pinned host angles, copy=False), one blocking call per step"}},
+            "ms_per_rank": [round(v, 4) for v in ms_per_rank],
             "value_stream_launch": world * BATCH * args.steps / (ms_nograph * 1e-3),
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
