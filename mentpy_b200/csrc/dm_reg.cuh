@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
                                                      const __grid_constant__ SampleParams sp) {
     constexpr int N = 1 << W;           // lanes per sample = columns per lane
     constexpr int SPW = 32 / N;         // samples per warp
-    constexpr int SPB = 4 * SPW;        // samples per CTA (4 warps)
+    const int SPB = (int)(blockDim.x >> 5) * SPW;  // samples per CTA (1..4 warps, chosen by the launcher)
     extern __shared__ double2 stage[];  // [SPB][N][N] rows of rho for the output phase
     const PlanTables& t = p.tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -572,6 +572,16 @@ int mbqc_run_batch_sv_f32(const mbqc_plan* plan, const double* d_angles, int64_t
     }
 }
 
+// CTA size of the DM register kernel: small batches get 2-warp CTAs so that the warps spread
+// evenly over the SMs (a 4096-sample C3 batch is 2048 warps = 0.86 waves of 4-warp CTAs, with
+// SMs holding 3 or 4 of them; 2-warp CTAs level that to 13-14 warps per SM)
+static int dm_reg_threads(int64_t batch, int n) {
+    static const int forced = []() { const char* e = getenv("MBQC_DM_CTA"); return e ? atoi(e) : 0; }();
+    if (forced == 32 || forced == 64 || forced == 128) return forced;
+    const int64_t warps = (batch * n + 31) / 32;
+    return warps < 148 * 16 * 2 ? 64 : 128;
+}
+
 static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                              const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
                              int8_t* d_outcomes, double* d_expect, bool expect_mode, int32_t* d_status, void* stream) {
@@ -606,20 +616,22 @@ static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int6
     // w <= 5: one lane per row of rho, registers + shuffles; w = 6: rho in shared memory
     const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
     if (w <= 5 && (has_z || !(force && !strcmp(force, "smem")))) {
-        const int n = 1 << w, spb = 4 * (32 / n);
+        const int n = 1 << w;
+        const int threads = dm_reg_threads(batch, n);
+        const int spb = (threads / 32) * (32 / n);
         const size_t smem = (size_t)spb * n * n * sizeof(double2);
         const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
         cudaStream_t st = (cudaStream_t)stream;
         SampleParams sp;
         memset(&sp, 0, sizeof(sp));
         switch (w) {
-            case 1: dm_reg_kernel<1, false><<<blocks, 128, smem, st>>>(p, sp); break;
-            case 2: dm_reg_kernel<2, false><<<blocks, 128, smem, st>>>(p, sp); break;
-            case 3: dm_reg_kernel<3, false><<<blocks, 128, smem, st>>>(p, sp); break;
-            case 4: dm_reg_kernel<4, false><<<blocks, 128, smem, st>>>(p, sp); break;
+            case 1: dm_reg_kernel<1, false><<<blocks, threads, smem, st>>>(p, sp); break;
+            case 2: dm_reg_kernel<2, false><<<blocks, threads, smem, st>>>(p, sp); break;
+            case 3: dm_reg_kernel<3, false><<<blocks, threads, smem, st>>>(p, sp); break;
+            case 4: dm_reg_kernel<4, false><<<blocks, threads, smem, st>>>(p, sp); break;
             default:
                 CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                dm_reg_kernel<5, false><<<blocks, 128, smem, st>>>(p, sp);
+                dm_reg_kernel<5, false><<<blocks, threads, smem, st>>>(p, sp);
                 break;
         }
         return after_launch("dm_reg_kernel");
@@ -817,18 +829,20 @@ int mbqc_run_batch_dm_sampled(const mbqc_plan* plan, const double* d_angles, int
     p.batch = batch;
     p.out = (double2*)d_out;
     p.status = d_status;
-    const int n = 1 << w, spb = 4 * (32 / n);
+    const int n = 1 << w;
+    const int threads = dm_reg_threads(batch, n);
+    const int spb = (threads / 32) * (32 / n);
     const size_t smem = (size_t)spb * n * n * sizeof(double2);
     const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
     cudaStream_t st = (cudaStream_t)stream;
     switch (w) {
-        case 1: dm_reg_kernel<1, true><<<blocks, 128, smem, st>>>(p, sp); break;
-        case 2: dm_reg_kernel<2, true><<<blocks, 128, smem, st>>>(p, sp); break;
-        case 3: dm_reg_kernel<3, true><<<blocks, 128, smem, st>>>(p, sp); break;
-        case 4: dm_reg_kernel<4, true><<<blocks, 128, smem, st>>>(p, sp); break;
+        case 1: dm_reg_kernel<1, true><<<blocks, threads, smem, st>>>(p, sp); break;
+        case 2: dm_reg_kernel<2, true><<<blocks, threads, smem, st>>>(p, sp); break;
+        case 3: dm_reg_kernel<3, true><<<blocks, threads, smem, st>>>(p, sp); break;
+        case 4: dm_reg_kernel<4, true><<<blocks, threads, smem, st>>>(p, sp); break;
         default:
             CUDA_TRY(cudaFuncSetAttribute(dm_reg_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dm_reg_kernel<5, true><<<blocks, 128, smem, st>>>(p, sp);
+            dm_reg_kernel<5, true><<<blocks, threads, smem, st>>>(p, sp);
             break;
     }
     return after_launch("dm_reg_kernel<sampled>");
