@@ -1,15 +1,16 @@
 """Pattern generators used by the benchmark configs and the parity tests.
 
-Host-side mirror of mentpy/mbqc/templates.py:16-216 (linear_cluster, many_wires, grid_cluster,
-muta).  Node numbering is row-major (wire after wire), inputs are the first node of every wire and
+Host-side mirror of mentpy/mbqc/templates.py:16-295 (linear_cluster, many_wires, grid_cluster,
+muta, spturb).  Node numbering is row-major (wire after wire), inputs are the first node of every wire and
 outputs the last -- which is what fixes `measurement_order` and `trainable_nodes` for
-BASELINE.json's configs.  spturb / from_pauli need the GF(2)
-Pauli algebra (galois) and are out of scope.
+BASELINE.json's configs.  from_pauli needs the GF(2) Pauli
+algebra (galois) and is out of scope.
 """
 from typing import List
 
-from .circuit import MBQCircuit, hstack
+from .circuit import MBQCircuit, hstack, merge
 from .graph import GraphState
+from .measurement import Ment
 
 TRIANGLE_WIRE = 5  # nodes per wire in one MuTA block
 
@@ -90,3 +91,39 @@ def muta(n_wires: int, n_layers: int, **kwargs) -> MBQCircuit:
     for _ in range(1, n_layers):
         stacked = hstack((stacked, column))
     return stacked
+
+
+def spturb(n_qubits: int, n_layers: int, periodic: bool = False, **kwargs) -> MBQCircuit:
+    """Symmetry-protected-topological perturbator ansatz (mentpy/mbqc/templates.py:219-295).
+
+    Every layer is a column of 3-node wires whose middle node is trainable (the rest measured in
+    X), followed by two sweeps of two-wire "symmetry blocks" glued onto the outputs of wires i and
+    i + 2: a 5-2-5 wire triple whose middle wire is tied to node 2 of the outer wires and carries
+    the block's one trainable node; the second sweep measures the odd nodes of the outer wires in Y.
+    n_qubits * n_layers + 2 * n_layers * (n_qubits if periodic else n_qubits - 2) trainable nodes."""
+    if n_qubits < 4:
+        raise ValueError("n_qubits must be greater than 4")
+    frame = many_wires([5, 2, 5]).graph
+    frame.add_edge(2, 6)
+    frame.add_edge(9, 6)
+    y_nodes = {v: Ment(plane="Y") for v in (1, 3, 8, 10)}
+    blocks = [
+        MBQCircuit(frame, input_nodes=[0, 7], output_nodes=[4, 11], measurements={5: Ment(plane="XY")},
+                   default_measurement=Ment(plane="X")),
+        MBQCircuit(frame, input_nodes=[0, 7], output_nodes=[4, 11], measurements={5: Ment(plane="XY"), **y_nodes},
+                   default_measurement=Ment(plane="X")),
+    ]
+
+    def column():
+        return many_wires([3] * n_qubits, measurements={3 * i + 1: Ment() for i in range(n_qubits)},
+                          default_measurement=Ment(plane="X"))
+
+    n_blocks = n_qubits if periodic else n_qubits - 2
+    ansatz = None
+    for _layer in range(n_layers):
+        ansatz = column() if ansatz is None else hstack((ansatz, column()))
+        for block in blocks:
+            for i in range(n_blocks):
+                first, second = ansatz.output_nodes[i], ansatz.output_nodes[(i + 2) % n_qubits]
+                ansatz = merge(ansatz, block, [(first, 0), (second, 7)])
+    return ansatz

@@ -48,6 +48,9 @@ def template_specs():
     specs.append(("muta", [2, 2], {"one_column": True}))
     specs.append(("muta", [3, 1], {"one_column": True}))
     specs.append(("muta", [3, 1], {}))
+    specs.append(("spturb", [4, 1], {}))
+    specs.append(("spturb", [5, 1], {"periodic": True}))
+    specs.append(("spturb", [4, 2], {}))
     lin = lambda n: ["linear_cluster", [n], {}]
     grid = lambda r, c: ["grid_cluster", [r, c], {}]
     specs.append(("vstack", [lin(3), lin(4)], {}))

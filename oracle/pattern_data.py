@@ -40,7 +40,7 @@ class PatternData:
                 str(k): (None if v is None else [v[0], v[1]]) for k, v in self.measurements.items()
             },
             "trainable_nodes": list(self.trainable_nodes),
-            "measurement_order": list(self.measurement_order),
+            "measurement_order": None if self.measurement_order is None else list(self.measurement_order),
             "quantum_output_nodes": list(self.quantum_output_nodes),
         }
 
@@ -56,7 +56,7 @@ class PatternData:
             output_nodes=[int(x) for x in d["output_nodes"]],
             measurements=meas,
             trainable_nodes=[int(x) for x in d["trainable_nodes"]],
-            measurement_order=[int(x) for x in d["measurement_order"]],
+            measurement_order=None if d["measurement_order"] is None else [int(x) for x in d["measurement_order"]],
             quantum_output_nodes=[int(x) for x in d.get("quantum_output_nodes", [])],
         )
 

@@ -53,6 +53,10 @@ def test_lowering_matches_reference_window_bookkeeping():
     for rec in load_golden("structures.json")["records"]:
         gs = build_spec(rec["spec"])
         pat = PatternData.from_json(rec["pattern"])
+        if pat.measurement_order is None:   # no causal flow (spturb): nothing to lower without a user schedule
+            with pytest.raises(ValueError, match="Schedule must be provided"):
+                lower(gs)
+            continue
         n_meas = len(pat.measurement_order) - len(pat.output_nodes)
         for w in {len(pat.input_nodes) + 1, min(len(pat.input_nodes) + 3, n_meas)}:
             if w > n_meas or w < len(pat.input_nodes) or w == 1:

@@ -31,9 +31,12 @@ def test_structure_tables(rec):
     assert gs.inputc == rec["inputc"]
     assert {str(k): v for k, v in gs.planes.items()} == rec["planes"]
     assert list(gs.measurements.keys()) == [int(k) for k in pat["measurements"].keys()]
-    assert {str(v): gs.flow(v) for v in gs.outputc} == rec["flow"]
-    assert gs.gflow.layers == rec["layers"]
-    assert gs.depth == rec["depth"]
+    if rec["flow"] is None:   # no causal flow (spturb)
+        assert gs.flow is None and gs.gflow.layers is None
+    else:
+        assert {str(v): gs.flow(v) for v in gs.outputc} == rec["flow"]
+        assert gs.gflow.layers == rec["layers"]
+        assert gs.depth == rec["depth"]
     assert len(gs) == pat["n_nodes"]
 
 
@@ -112,3 +115,16 @@ def test_ment_contract():
         assert np.array_equal(np.asarray(p0, dtype=complex), from_cplx(rec["p0"]))
         assert np.array_equal(np.asarray(p1, dtype=complex), from_cplx(rec["p1"]))
         assert mb.Ment(rec["plane"]).is_trainable() == rec["trainable"]
+
+
+@pytest.mark.parametrize("n_layer", [1, 2])
+@pytest.mark.parametrize("n_qubits", [4, 5])
+@pytest.mark.parametrize("periodic", [True, False])
+def test_spturb_trainable_nodes(n_layer, n_qubits, periodic):
+    """The reference's own template test (tests/mbqc/test_mbqc_templates.py:12-22)."""
+    spt = mb.templates.spturb(n_qubits, n_layer, periodic=periodic)
+    blocks = n_qubits if periodic else n_qubits - 2
+    assert len(spt.trainable_nodes) == n_qubits * n_layer + 2 * n_layer * blocks
+    assert spt.flow is None and spt.measurement_order is None   # no causal flow: needs a user schedule
+    with pytest.raises(ValueError):
+        mb.templates.spturb(3, 1)
