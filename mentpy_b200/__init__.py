@@ -5,7 +5,7 @@ that simulates needs the in-tree CUDA library and a CUDA device and raises other
 """
 from . import mbqc
 from .mbqc import (GraphState, MBQCircuit, Measurement, Ment, hstack, merge, templates, vstack)
-from . import calculator, gradients, optimizers, simulators, utils
+from . import calculator, gates, gradients, optimizers, simulators, utils
 from .simulators import BaseSimulator, CudaSimulatorDM, CudaSimulatorSV, PatternSimulator
 
 

@@ -105,6 +105,8 @@ def test_ment_contract():
         mb.Ment(0.3).matrix(0.4)
     with pytest.raises(TypeError):
         mb.Ment([0.1])
+    for plane, mat in (("X", mb.gates.PauliX), ("Y", mb.gates.PauliY), ("Z", mb.gates.PauliZ)):
+        assert np.allclose(mb.Ment(plane=plane).matrix(), mat)          # test_ment.py:58-61
     h = load_golden("helpers.json")
     from conftest import from_cplx
 
