@@ -1,5 +1,6 @@
 """CPU: the C-ABI library loads and exports every symbol the header declares (no compute calls),
 and the host-side plan lowering reproduces the reference's window bookkeeping."""
+import ctypes as C
 import os
 import re
 
@@ -195,3 +196,32 @@ def test_lowered_plan_emulation_matches_oracle_on_random_patterns(seed):
     else:
         want = matrix_free.run_sv_batch(pat, ang[None], input_states=inp[None], window_size=w)[0]
         assert 1 - abs(np.vdot(run_sv(pl, ang, inp), want)) ** 2 < 1e-10
+
+
+def test_entry_points_validate_arguments_before_touching_cuda():
+    """No GPU needed: every batch entry point rejects a NULL plan / bad sizes with MBQC_E_ARG and a
+    message, without making a CUDA call."""
+    lib = _lib.load()
+    null = None
+    calls = {
+        "mbqc_run_batch_sv": (null, null, 0, null, 0, 4, null, 0, null, null),
+        "mbqc_run_batch_sv_f32": (null, null, 0, null, 0, 4, null, 0, null, null),
+        "mbqc_run_batch_dm": (null, null, 0, null, 0, 4, null, null, null, null),
+        "mbqc_run_batch_dm_expect": (null, null, 0, null, 0, 4, null, null, null, null, null),
+        "mbqc_psr_grad_batch": (null, null, 0, null, 0, 4, null, 1.5, null, null, null, null),
+        "mbqc_psr_grad_dataset": (null, null, 0, null, null, 1, 1, 1.5, null, null, null, null, null),
+        "mbqc_run_batch_sv_sampled": (null, null, 0, null, 0, 4, 1, 0, 0, 1, null, null, null, null, null, null),
+        "mbqc_run_batch_dm_sampled": (null, null, 0, null, 0, 4, 1, 0, 0, 1, null, null, null, null, null, null),
+        "mbqc_train_dataset": (null, null, null, null, 1, 1, 1.5, null, 0, 1, null, null, null, null, null),
+        "mbqc_plan_set_feedforward": (null, null, 0),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc == _lib.MBQC_E_ARG, name
+        assert b"NULL" in lib.mbqc_last_error() or b"plan" in lib.mbqc_last_error(), name
+    ticket = C.c_int32(-1)
+    rc = lib.mbqc_run_batch_sv_host_submit(null, null, 0, null, 0, 4, null, 0, null, 0, 0, C.byref(ticket))
+    assert rc == _lib.MBQC_E_ARG
+    assert lib.mbqc_host_wait(10**6, None) == _lib.MBQC_E_ARG
+    assert lib.mbqc_psr_grad_dataset_workspace_bytes(None, 1, 1) == -1
+    assert lib.mbqc_host_workspace_bytes(None, 1, 0) == -1
