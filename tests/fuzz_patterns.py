@@ -64,3 +64,20 @@ def random_pattern(lib, seed: int, mixed: bool):
     if seed % 5 == 0:  # the default |+> input (pattern_simulator.py:58-61)
         inp = np.full(2**n_in, 2.0 ** (-n_in / 2), dtype=complex)
     return gs, window, angles, inp
+
+
+def random_schedule(gs, seed: int, mixed: bool):
+    """A user schedule (the `schedule=` kwarg of the simulators): the default measurement order with
+    a few random adjacent transpositions among the measured non-input nodes; inputs stay first and
+    the unmeasured outputs last, as both simulators require."""
+    rng = np.random.default_rng(10_000 + seed)
+    order = list(gs.measurement_order)
+    keep_last = list(gs.quantum_output_nodes if mixed else gs.output_nodes)
+    n_in = len(gs.input_nodes)
+    head, tail = order[:n_in], [v for v in order[n_in:] if v in keep_last]
+    mid = [v for v in order[n_in:] if v not in keep_last]
+    for _ in range(int(rng.integers(1, 4))):
+        if len(mid) >= 2:
+            i = int(rng.integers(0, len(mid) - 1))
+            mid[i], mid[i + 1] = mid[i + 1], mid[i]
+    return head + mid + tail

@@ -108,3 +108,29 @@ def test_gradients_equal_shifted_oracle_evaluations_on_random_patterns(seed):
     for i in range(T):
         e = np.zeros(T); e[i] = 1.5
         assert np.allclose(g[:, i], (cost(X + e) - cost(X - e)) / 3.0, atol=1e-10)
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_user_schedules_equal_oracle(seed):
+    """The `schedule=` kwarg on the CUDA backends (incl. streaming) on perturbed measurement orders;
+    the oracle is pinned against the live reference on the same seeds (CPU suite)."""
+    from fuzz_patterns import random_schedule
+
+    mixed = seed % 2 == 1
+    gs, w, ang, inp = random_pattern(mb, seed, mixed)
+    sched = random_schedule(gs, seed, mixed)
+    pat = PatternData.from_circuit(gs)
+    A = np.vstack([ang[None], np.random.default_rng(5000 + seed).uniform(0, 2 * np.pi, (12, len(ang)))])
+    if mixed:
+        ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=w, schedule=sched)
+        got, oc = ps.run_batch(A, return_outcomes=True)
+        want, woc = matrix_free.run_dm_batch(pat, A, input_states=inp[None], window_size=w, schedule=sched, return_outcomes=True)
+        assert dm_distance(got, want) < 1e-10 and np.array_equal(oc, woc)
+    else:
+        ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=w, schedule=sched)
+        got = ps.run_batch(A)
+        want = matrix_free.run_sv_batch(pat, A, input_states=inp[None], window_size=w, schedule=sched)
+        assert np.max(1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2) < 1e-10
+        assert np.allclose(got, want, atol=1e-9)
+        st = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv-stream", window_size=w, schedule=sched)
+        assert 1 - abs(np.vdot(st.run(ang, output_form="sv"), want[0])) ** 2 < 1e-10

@@ -68,3 +68,39 @@ def test_host_indexing_equals_live_reference(seed):
         assert (sa.node, sa.slot, sa.angle_idx, sa.plane, sa.append, sa.new_node, sa.nbr_mask) == \
                (sb.node, sb.slot, sb.angle_idx, sb.plane, sb.append, sb.new_node, sb.nbr_mask)
         assert sa.fixed_cos == sb.fixed_cos and sa.fixed_sin == sb.fixed_sin
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_user_schedules_equal_live_reference(seed):
+    """`schedule=` kwarg: a perturbed measurement order through the live reference, the oracle and
+    the numpy execution of the lowered plan (slot bookkeeping under non-default orders, including
+    the CZs the reference silently drops when a neighbour has already left the window)."""
+    import mentpy_b200 as mb
+    from fuzz_patterns import random_schedule
+    from mentpy_b200.plan import lower
+    from plan_emulator import run_dm, run_sv
+
+    mp = import_reference()
+    mixed = seed % 2 == 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, w, ang, inp = random_pattern(mp, seed, mixed)
+        mine, _, _, _ = random_pattern(mb, seed, mixed)
+        sched = random_schedule(ref, seed, mixed)
+        assert sched == random_schedule(mine, seed, mixed)
+        try:
+            ps = mp.PatternSimulator(ref, input_state=inp, backend="numpy-dm" if mixed else "numpy-sv",
+                                     window_size=w, schedule=sched)
+            want = ps.run(ang) if mixed else ps.run(ang, output_form="sv")
+        except Exception as e:
+            pytest.skip(f"reference rejects the schedule: {type(e).__name__}")
+    pat = PatternData.from_circuit(mine)
+    pl = lower(mine, window_size=w, schedule=sched, mixed=mixed)
+    if mixed:
+        got = matrix_free.run_dm_batch(pat, ang[None], input_states=inp[None], window_size=w, schedule=sched)[0]
+        assert dm_distance(got, want) < 1e-10
+        assert np.abs(run_dm(pl, ang, inp)[0] - want).max() < 1e-10
+    else:
+        got = matrix_free.run_sv_batch(pat, ang[None], input_states=inp[None], window_size=w, schedule=sched)[0]
+        assert infidelity_pure(got, want) < 1e-10
+        assert 1 - abs(np.vdot(run_sv(pl, ang, inp), want)) ** 2 < 1e-10
