@@ -19,6 +19,8 @@
 #include "calc.cuh"
 #include <vector>
 
+#include "host_util.h"
+
 using namespace mbqc;
 
 namespace {
@@ -48,6 +50,14 @@ int after_launch(const char* name) {
     return MBQC_OK;
 }
 
+}  // namespace
+
+// helpers shared with the other translation units of the library (host_util.h)
+int mbqc_set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+int mbqc_cuda_error(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+int mbqc_after_launch(const char* name) { return after_launch(name); }
+
+namespace {
 int ilog2_ceil(unsigned v) {
     int l = 0;
     while ((1u << l) < v) ++l;
@@ -200,6 +210,9 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
         delete pl;
         return cuda_fail(e, "plan upload");
     }
+    pl->lean = nullptr;
+    pl->lean_fixed = 0;
+    mbqc_lean_build_proto(pl);
     *out = pl;
     return MBQC_OK;
 }
@@ -209,6 +222,7 @@ void mbqc_plan_destroy(mbqc_plan* plan) {
     if (plan->d_steps) cudaFree(plan->d_steps);
     if (plan->d_reg_blob) cudaFree(plan->d_reg_blob);
     if (plan->d_ff) cudaFree(plan->d_ff);
+    mbqc_lean_free_proto(plan);
     delete[] plan->h_steps;
     delete plan;
 }
@@ -316,6 +330,11 @@ static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStre
 
 static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st, bool coalesced_out = false) {
     const int w = p.tab.window;
+    if (w <= MBQC_MAX_WINDOW_REG) {
+        int rc = 0;
+        const int out_mode = out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : (coalesced_out ? MBQC_LEAN_OUT_STAGED : MBQC_LEAN_OUT_DIRECT);
+        if (mbqc_lean_try_launch(p, plan, out_mode, st, &rc)) return rc;
+    }
     if (w <= MBQC_MAX_WINDOW_REG)
         return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, plan, st, true) : launch_sv_reg<false>(p, plan, st, coalesced_out);
     if (w > MBQC_MAX_WINDOW_SMEM_SV)

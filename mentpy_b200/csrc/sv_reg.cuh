@@ -18,8 +18,6 @@
 //   * CZ signs come as ready-made sign words (0 / 0x80000000) from shared memory and are applied
 //     with one LOP3 per word on the integer pipe, keeping the FP64 pipe for the FMAs.
 #pragma once
-#include <utility>
-
 #include "sv_batch.cuh"
 
 namespace mbqc {
@@ -92,15 +90,6 @@ struct AngleGlobal {
         sincos_cw(th, s, c);
     }
 };
-
-template <class F, int... U>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, U...>) {
-    (f(std::integral_constant<int, U>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
-    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
-}
 
 // ---- one measurement ---------------------------------------------------------------------------
 template <int W, int S>
