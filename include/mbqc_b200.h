@@ -323,6 +323,13 @@ int32_t mbqc_plan_window(const mbqc_plan* plan);
 int32_t mbqc_plan_num_steps(const mbqc_plan* plan);
 int32_t mbqc_plan_num_outputs(const mbqc_plan* plan);
 
+/* ---- measurement probes (bench.py's second roofline; not on the product path) -------------------
+ * fp64_fma: `blocks` x `threads` (<= 256) threads run `iters` rounds of 8 independent DFMAs each;
+ * *flops receives the flop count of the launch (2 per FMA).  copy: grid-stride 16-byte copy of
+ * `bytes` (multiple of 16) from d_src to d_dst -- HBM traffic 2 * bytes. */
+int mbqc_probe_fp64_fma(int64_t iters, int32_t blocks, int32_t threads, double* d_out, int64_t* flops, void* stream);
+int mbqc_probe_copy(const void* d_src, void* d_dst, int64_t bytes, int32_t blocks, void* stream);
+
 /* number of kernels this library has launched in the calling process (bench gpu_launches) */
 int64_t mbqc_launch_count(void);
 

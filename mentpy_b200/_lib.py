@@ -119,6 +119,8 @@ _SIGNATURES = {
     "mbqc_plan_window": (C.c_int32, [C.c_void_p]),
     "mbqc_plan_num_steps": (C.c_int32, [C.c_void_p]),
     "mbqc_plan_num_outputs": (C.c_int32, [C.c_void_p]),
+    "mbqc_probe_fp64_fma": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]),
+    "mbqc_probe_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "mbqc_launch_count": (C.c_int64, []),
     "mbqc_last_error": (C.c_char_p, []),
     "mbqc_version": (C.c_char_p, []),

@@ -40,6 +40,13 @@ def gather_slices(local, total: int, group=None):
         return local
     sizes = [slice_bounds(total, r, world) for r in range(world)]
     biggest = max(hi - lo for lo, hi in sizes)
+    if total % world == 0 and local.is_contiguous():
+        # even split: the collective writes straight into the result, no padding or re-assembly
+        out = torch.empty((total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        flat_in = torch.view_as_real(local).reshape(-1) if local.is_complex() else local.reshape(-1)
+        flat_out = torch.view_as_real(out).reshape(-1) if out.is_complex() else out.reshape(-1)
+        dist.all_gather_into_tensor(flat_out, flat_in, group=group)
+        return out
     pad = torch.zeros((biggest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world, biggest) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
