@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OUT=${MBQC_BUILD_OUT:-mentpy_b200/_mbqc_b200.so}
 OBJ=${MBQC_BUILD_OBJ:-build/obj}
 mkdir -p "$OBJ"
-SRCS="mbqc_b200 sv_lean_host probes"
+SRCS="mbqc_b200 sv_lean_host sv_jit_host probes"
 ONLY=${1:-$SRCS}
 pids=""
 for s in $ONLY; do
@@ -18,5 +18,5 @@ done
 for p in $pids; do wait $p; done
 objs=""
 for s in $SRCS; do objs="$objs $OBJ/$s.o"; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" $objs -ldl
 echo "built $OUT"

@@ -110,6 +110,27 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
                      const mbqc_noise* noise, mbqc_plan** out);
 void mbqc_plan_destroy(mbqc_plan* plan);
 
+/* Same lowering tables WITHOUT any device allocation (no CUDA call): such a plan cannot be run; it
+ * exists so that the run-time specialised kernel of a pattern can be generated and compiled where
+ * there is no GPU (mbqc_jit_compile_check: build boxes, the CPU test suite). */
+int mbqc_plan_create_hostonly(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                              int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                              const uint64_t* init_cz_mask, const int32_t* output_slot,
+                              const mbqc_noise* noise, mbqc_plan** out);
+
+/* Run-time specialisation of mbqc_run_batch_sv (window <= MBQC_MAX_WINDOW_REG, reference schedules):
+ * for calls with batch >= 16384 (MBQC_JIT_MIN_BATCH; MBQC_JIT=0 disables, MBQC_JIT=force always)
+ * the library generates the pattern's kernel with its angle columns, CZ signs and step count as
+ * compile-time constants, compiles it once with NVRTC (dlopen'ed; cubins are cached under
+ * MBQC_JIT_CACHE, default ~/.cache/mentpy_b200) and launches that instead of the general kernels.
+ * Without NVRTC the general CUDA kernels run.  compile_check: generate + compile only; returns the
+ * cubin size in bytes, 0 if the plan is outside the specialised kernel's scope, < 0 on error.
+ * info: where NVRTC was found, kernels compiled / loaded from the file cache, last error. */
+int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t cta);
+const char* mbqc_jit_info(void);
+/* 0 = never, 1 = by batch size (default), 2 = every eligible call; returns the previous mode */
+int32_t mbqc_jit_set_mode(int32_t mode);
+
 /* NumpySimulatorSV.run over a batch (np_simulator_sv.py:227-297): angles [B][T] (row stride
  * `angle_stride` doubles) -> out.  Amplitudes carry the reference's global phase
  * prod_j (1+e^{i th_j})/|1+e^{i th_j}| so that 'sv' outputs compare amplitude by amplitude.

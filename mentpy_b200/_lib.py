@@ -64,6 +64,12 @@ _SIGNATURES = {
     "mbqc_plan_create": (C.c_int, [C.POINTER(Step), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
                                    C.POINTER(C.c_int32), C.POINTER(Noise), C.POINTER(C.c_void_p)]),
+    "mbqc_plan_create_hostonly": (C.c_int, [C.POINTER(Step), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64),
+                                   C.POINTER(C.c_int32), C.POINTER(Noise), C.POINTER(C.c_void_p)]),
+    "mbqc_jit_compile_check": (C.c_int64, [C.c_void_p, C.c_int32, C.c_int32]),
+    "mbqc_jit_info": (C.c_char_p, []),
+    "mbqc_jit_set_mode": (C.c_int32, [C.c_int32]),
     "mbqc_plan_destroy": (None, [C.c_void_p]),
     "mbqc_run_batch_sv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                     C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

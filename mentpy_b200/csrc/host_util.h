@@ -18,3 +18,7 @@ void mbqc_lean_build_proto(mbqc_plan* plan);  // sets plan->lean (or leaves it n
 void mbqc_lean_free_proto(mbqc_plan* plan);
 // 0 = not eligible (caller falls back to sv_reg_kernel), 1 = launched (*rc holds the result)
 int mbqc_lean_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st, int* rc);
+
+// ---- run-time specialised kernel (sv_jit_src.inc, sv_jit_host.cu): same return convention ----
+void mbqc_jit_free(mbqc_plan* plan);
+int mbqc_jit_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st, int* rc);

@@ -71,10 +71,10 @@ const char* mbqc_last_error(void) { return g_err; }
 const char* mbqc_version(void) { return "mentpy_b200 0.1 (sm_100a)"; }
 int64_t mbqc_launch_count(void) { return (int64_t)g_launches.load(); }
 
-int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
-                     int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
-                     const uint64_t* init_cz_mask, const int32_t* output_slot,
-                     const mbqc_noise* noise, mbqc_plan** out) {
+static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                            int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                            const uint64_t* init_cz_mask, const int32_t* output_slot,
+                            const mbqc_noise* noise, mbqc_plan** out, bool upload) {
     if (!out) return fail(MBQC_E_ARG, "out is NULL");
     *out = nullptr;
     if (window < 1 || window > MBQC_MAX_WINDOW) return fail(MBQC_E_ARG, "window %d out of range [1,%d]", window, MBQC_MAX_WINDOW);
@@ -152,9 +152,11 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
                 if (((i >> s.slot) & 1u) && parity64((uint64_t)i & d.nbr_mask)) d.flipmask |= 1u << i;
     }
     pl->d_steps = nullptr;
-    cudaError_t e = cudaGetDevice(&pl->device);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(StepDev) * (n_steps > 0 ? n_steps : 1));
-    if (e == cudaSuccess && n_steps > 0)
+    pl->device = -1;
+    cudaError_t e = cudaSuccess;
+    if (upload) e = cudaGetDevice(&pl->device);
+    if (upload && e == cudaSuccess) e = cudaMalloc(&pl->d_steps, sizeof(StepDev) * (n_steps > 0 ? n_steps : 1));
+    if (upload && e == cudaSuccess && n_steps > 0)
         e = cudaMemcpy(pl->d_steps, pl->h_steps, sizeof(StepDev) * n_steps, cudaMemcpyHostToDevice);
     pl->d_reg_blob = nullptr;
     pl->d_reg_cols = pl->d_reg_signs = nullptr;
@@ -189,8 +191,11 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
         }
         if (n_angles + (int)fixed.size() > 0xffff) periodic = 0;  // (never for w <= 5 patterns in practice)
         const size_t b_signs = signs.size() * 4, b_cols = cols.size() * 4, b_fixed = (fixed.size() ? fixed.size() : 1) * 16;
-        e = cudaMalloc(&pl->d_reg_blob, b_signs + b_cols + b_fixed);
-        if (e == cudaSuccess) {
+        pl->reg_n_fixed = (int)fixed.size();
+        pl->reg_sign_pitch = sp;
+        pl->reg_periodic = periodic;
+        if (upload) e = cudaMalloc(&pl->d_reg_blob, b_signs + b_cols + b_fixed);
+        if (upload && e == cudaSuccess) {
             char* base = (char*)pl->d_reg_blob;
             e = cudaMemcpy(base, signs.data(), b_signs, cudaMemcpyHostToDevice);
             if (e == cudaSuccess) e = cudaMemcpy(base + b_signs, cols.data(), b_cols, cudaMemcpyHostToDevice);
@@ -198,9 +203,6 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
             pl->d_reg_signs = (const uint32_t*)base;
             pl->d_reg_cols = (const uint32_t*)(base + b_signs);
             pl->d_reg_fixed = (const double2*)(base + b_signs + b_cols);
-            pl->reg_n_fixed = (int)fixed.size();
-            pl->reg_sign_pitch = sp;
-            pl->reg_periodic = periodic;
         }
     }
     if (e != cudaSuccess) {
@@ -212,9 +214,26 @@ int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, in
     }
     pl->lean = nullptr;
     pl->lean_fixed = 0;
+    pl->jit = nullptr;
     mbqc_lean_build_proto(pl);
     *out = pl;
     return MBQC_OK;
+}
+
+int mbqc_plan_create(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                     int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                     const uint64_t* init_cz_mask, const int32_t* output_slot,
+                     const mbqc_noise* noise, mbqc_plan** out) {
+    return plan_create_impl(steps, n_steps, window, n_inputs, n_outputs, n_angles, input_slot, init_cz_mask, output_slot,
+                            noise, out, true);
+}
+
+int mbqc_plan_create_hostonly(const mbqc_step* steps, int32_t n_steps, int32_t window, int32_t n_inputs,
+                              int32_t n_outputs, int32_t n_angles, const int32_t* input_slot,
+                              const uint64_t* init_cz_mask, const int32_t* output_slot,
+                              const mbqc_noise* noise, mbqc_plan** out) {
+    return plan_create_impl(steps, n_steps, window, n_inputs, n_outputs, n_angles, input_slot, init_cz_mask, output_slot,
+                            noise, out, false);
 }
 
 void mbqc_plan_destroy(mbqc_plan* plan) {
@@ -222,6 +241,7 @@ void mbqc_plan_destroy(mbqc_plan* plan) {
     if (plan->d_steps) cudaFree(plan->d_steps);
     if (plan->d_reg_blob) cudaFree(plan->d_reg_blob);
     if (plan->d_ff) cudaFree(plan->d_ff);
+    mbqc_jit_free(plan);
     mbqc_lean_free_proto(plan);
     delete[] plan->h_steps;
     delete plan;
@@ -261,6 +281,7 @@ int32_t mbqc_plan_num_outputs(const mbqc_plan* plan) { return plan ? plan->tab.n
 static int check_batch_args(const mbqc_plan* plan, const double* d_angles, int64_t stride,
                             const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out) {
     if (!plan) return fail(MBQC_E_ARG, "plan is NULL");
+    if (plan->device < 0) return fail(MBQC_E_ARG, "host-only plan (mbqc_plan_create_hostonly) cannot be run");
     if (batch < 0) return fail(MBQC_E_ARG, "batch < 0");
     if (plan->tab.n_angles > 0 && !d_angles) return fail(MBQC_E_ARG, "d_angles is NULL");
     if (stride < plan->tab.n_angles) return fail(MBQC_E_ARG, "angle_stride %lld < n_angles %d", (long long)stride, plan->tab.n_angles);
@@ -333,6 +354,7 @@ static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form
     if (w <= MBQC_MAX_WINDOW_REG) {
         int rc = 0;
         const int out_mode = out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : (coalesced_out ? MBQC_LEAN_OUT_STAGED : MBQC_LEAN_OUT_DIRECT);
+        if (mbqc_jit_try_launch(p, plan, out_mode, st, &rc)) return rc;
         if (mbqc_lean_try_launch(p, plan, out_mode, st, &rc)) return rc;
     }
     if (w <= MBQC_MAX_WINDOW_REG)

@@ -107,8 +107,8 @@ int mbqc_lean_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_
     if (p.stride != T || ((uintptr_t)p.angles & 15u)) return 0;
     int cta = 128;
     if (!plan->lean_fixed && out_mode == kLeanOutDirect) {
-        // small batches: 64-thread CTAs spread the batch evenly over the 148 SMs
-        if (cta_env == 64 || (cta_env == 0 && p.batch < (int64_t)148 * 1024)) cta = 64;
+        // MBQC_LEAN_CTA=64: 64-thread CTAs (measured equal to 128 on B200 at 65,536 .. 4M samples)
+        if (cta_env == 64) cta = 64;
     }
     size_t smem = (size_t)cta * T * sizeof(double);
     if (out_mode != kLeanOutDirect) {

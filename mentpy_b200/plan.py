@@ -334,7 +334,9 @@ class DevicePlan:
     """Owns the opaque mbqc_plan* created on the current CUDA device."""
 
     def __init__(self, plan: LoweredPlan, noise: Optional["_lib.Noise"] = None,
-                 n_steps: Optional[int] = None, output_slot: Optional[List[int]] = None):
+                 n_steps: Optional[int] = None, output_slot: Optional[List[int]] = None, host_only: bool = False):
+        """host_only: lowering tables without device allocations (mbqc_plan_create_hostonly) -- such
+        a plan cannot be run, only inspected and passed to `jit_compile_check` (no GPU needed)."""
         lib = _lib.load()
         steps = plan.steps if n_steps is None else plan.steps[:n_steps]
         arr = (_lib.Step * max(len(steps), 1))()
@@ -348,16 +350,25 @@ class DevicePlan:
         cz_arr = (C.c_uint64 * plan.window)(*plan.init_cz_mask)
         out_arr = (C.c_int32 * max(len(out_slot), 1))(*out_slot)
         handle = C.c_void_p()
-        _lib.check(lib.mbqc_plan_create(arr, len(steps), plan.window, len(plan.input_slot),
-                                        len(out_slot), plan.n_angles, in_arr, cz_arr, out_arr,
-                                        C.byref(noise) if noise is not None else None,
-                                        C.byref(handle)))
+        create = lib.mbqc_plan_create_hostonly if host_only else lib.mbqc_plan_create
+        _lib.check(create(arr, len(steps), plan.window, len(plan.input_slot),
+                          len(out_slot), plan.n_angles, in_arr, cz_arr, out_arr,
+                          C.byref(noise) if noise is not None else None,
+                          C.byref(handle)))
         self.handle = handle
         self.n_out = len(out_slot)
         self.n_in = len(plan.input_slot)
         self.n_steps = len(steps)
         self._lib = lib
         self.has_feedforward = False
+
+    def jit_compile_check(self, out_form: int = 0, cta: int = 128) -> int:
+        """Generate and compile (NVRTC, offline) the run-time specialised state-vector kernel of this
+        plan; returns the cubin size, 0 when the plan is outside that kernel's scope."""
+        n = int(self._lib.mbqc_jit_compile_check(self.handle, out_form, cta))
+        if n < 0:
+            _lib.check(n)
+        return n
 
     def set_feedforward(self, ff: Sequence[FeedForward]):
         """Attach the correction masks (once, before the plan is used for sampled runs)."""

@@ -7,7 +7,9 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {"reg": {"MBQC_SV_KERNEL_REG": "1"}, "lean128": {"MBQC_LEAN_CTA": "128"}, "lean64": {"MBQC_LEAN_CTA": "64"},
+VARIANTS = {"reg": {"MBQC_SV_KERNEL_REG": "1", "MBQC_JIT": "0"}, "lean128": {"MBQC_LEAN_CTA": "128", "MBQC_JIT": "0"},
+            "lean64": {"MBQC_LEAN_CTA": "64", "MBQC_JIT": "0"},
+            "jit128": {"MBQC_LEAN_CTA": "128", "MBQC_JIT": "force"}, "jit64": {"MBQC_LEAN_CTA": "64", "MBQC_JIT": "force"},
             # alternative builds of the library (build.sh with MBQC_BUILD_OUT=build/_mbqc_<name>.so)
             "notab": {"MBQC_LIB_PATH": os.path.join(ROOT, "build", "_mbqc_notab.so"), "MBQC_LEAN_CTA": "128"},
             "alt": {"MBQC_LIB_PATH": os.path.join(ROOT, "build", "_mbqc_alt.so")}}

@@ -1,0 +1,156 @@
+"""GPU: the three state-vector kernels behind mbqc_run_batch_sv -- run-time specialised
+(sv_jit_src.inc), lean (sv_lean.cuh) and general register kernel (sv_reg.cuh) -- against the
+reference's golden vectors and against each other on seeded batches (ragged sizes, Haar inputs,
+fixed-angle nodes, both output forms).  Tolerance: infidelity <= 1e-10, amplitudes 1e-9."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import mentpy_b200 as mb
+from conftest import ROOT, from_cplx, infidelity_pure, load_golden
+from mentpy_b200 import _lib
+from oracle import matrix_free
+from oracle.pattern_data import PatternData
+
+pytestmark = pytest.mark.gpu
+
+CASES = [c for c in load_golden("sim_cases.json")["cases"] if c["backend"] == "numpy-sv" and c["window_size"] <= 5]
+
+
+def _circuit(case):
+    name, args, kwargs = case["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    for v in case["x_nodes"]:
+        gs[v] = mb.Ment("X")
+    for v, (ang, plane) in case["fixed"].items():
+        gs[int(v)] = mb.Ment(ang, plane)
+    return gs
+
+
+@pytest.fixture
+def jit_forced():
+    lib = _lib.load()
+    prev = lib.mbqc_jit_set_mode(2)
+    yield lib
+    lib.mbqc_jit_set_mode(prev)
+
+
+@pytest.fixture
+def jit_off():
+    lib = _lib.load()
+    prev = lib.mbqc_jit_set_mode(0)
+    yield lib
+    lib.mbqc_jit_set_mode(prev)
+
+
+def _launched(lib):
+    return lib.mbqc_jit_info().decode()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"{c['spec'][0]}{c['spec'][1]}-w{c['window_size']}-s{c['seed']}-{c['output_form']}" for c in CASES])
+def test_specialised_kernel_reproduces_reference_goldens(case, jit_forced):
+    gs = _circuit(case)
+    inp = from_cplx(case["input_state"])
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-sv", window_size=case["window_size"])
+    ang = np.asarray(case["angles"])
+    want = from_cplx(case["output"])
+    B = 67  # ragged: two full warps + 3 rows; row 5 carries the golden angles
+    rows = np.random.default_rng(case["seed"]).uniform(0, 2 * np.pi, (B, len(ang)))
+    rows[5] = ang
+    before = _launched(jit_forced)
+    got = ps.run_batch(torch.from_numpy(rows).cuda(), output_form=case["output_form"]).cpu().numpy()
+    after = _launched(jit_forced)
+    assert "failures=0" in after, after
+    assert before != after or "compiled=0" not in after  # a specialised kernel was built or re-used
+    if case["output_form"] == "sv":
+        assert infidelity_pure(got[5], want) < 1e-10
+        assert np.allclose(got[5], want, atol=1e-9, rtol=0)
+    else:
+        assert np.abs(got[5] - want).max() < 1e-10
+    # the whole batch against the general kernels
+    jit_forced.mbqc_jit_set_mode(0)
+    ref = ps.run_batch(torch.from_numpy(rows).cuda(), output_form=case["output_form"]).cpu().numpy()
+    jit_forced.mbqc_jit_set_mode(2)
+    assert np.abs(got - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("spec", [("linear_cluster", [5]), ("grid_cluster", [2, 6]), ("grid_cluster", [3, 5]),
+                                  ("grid_cluster", [4, 5]), ("linear_cluster", [40]), ("muta", [2, 1])])
+@pytest.mark.parametrize("B", [1, 31, 128, 4099])
+def test_three_kernels_agree_with_the_oracle(spec, B, jit_forced):
+    gs = getattr(mb.templates, spec[0])(*spec[1])
+    T = len(gs.trainable_nodes)
+    rng = np.random.default_rng(B + T)
+    ang = rng.uniform(-7, 7, (B, T))
+    want = matrix_free.run_sv_batch(PatternData.from_circuit(gs), ang)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    a = torch.from_numpy(ang).cuda()
+    outs = {}
+    jit_forced.mbqc_jit_set_mode(2)
+    outs["jit"] = ps.run_batch(a).cpu().numpy()
+    jit_forced.mbqc_jit_set_mode(0)
+    outs["lean"] = ps.run_batch(a).cpu().numpy()
+    assert "failures=0" in _launched(jit_forced)
+    for name, got in outs.items():
+        infid = np.abs(1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2)
+        assert infid.max() < 1e-10, (name, infid.max())
+    assert np.abs(outs["jit"] - outs["lean"]).max() < 1e-12
+
+
+def test_general_register_kernel_still_matches(jit_off):
+    """MBQC_SV_KERNEL_REG=1 routes everything through sv_reg_kernel (read once per process)."""
+    code = (
+        "import numpy as np, torch, mentpy_b200 as mb\n"
+        "gs = mb.templates.grid_cluster(2, 6)\n"
+        "ang = np.random.default_rng(3).uniform(0, 6.28, (1000, 10))\n"
+        "ps = mb.PatternSimulator(gs, backend='cuda-sv')\n"
+        "np.save('/tmp/_mbqc_reg_out.npy', ps.run_batch(torch.from_numpy(ang).cuda()).cpu().numpy())\n")
+    env = dict(os.environ, MBQC_SV_KERNEL_REG="1", MBQC_JIT="0", PYTHONPATH=ROOT)
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, cwd=ROOT, timeout=300)
+    reg = np.load("/tmp/_mbqc_reg_out.npy")
+    gs = mb.templates.grid_cluster(2, 6)
+    ang = np.random.default_rng(3).uniform(0, 6.28, (1000, 10))
+    lean = mb.PatternSimulator(gs, backend="cuda-sv").run_batch(torch.from_numpy(ang).cuda()).cpu().numpy()
+    assert np.abs(reg - lean).max() < 1e-12
+
+
+def test_inputs_per_sample_and_shared_and_dm_form(jit_forced):
+    from scipy.stats import unitary_group
+
+    gs = mb.templates.grid_cluster(2, 5)
+    T = len(gs.trainable_nodes)
+    B = 300
+    rng = np.random.default_rng(11)
+    ang = rng.uniform(0, 2 * np.pi, (B, T))
+    ins = np.stack([unitary_group.rvs(4, random_state=s)[:, 0] for s in range(B)])
+    pat = PatternData.from_circuit(gs)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    got = ps.run_batch(torch.from_numpy(ang).cuda(), input_states=torch.from_numpy(ins).cuda()).cpu().numpy()
+    want = matrix_free.run_sv_batch(pat, ang, input_states=ins)
+    assert np.abs(1 - np.abs(np.sum(got.conj() * want, axis=1)) ** 2).max() < 1e-10
+    assert np.allclose(got, want, atol=1e-9, rtol=0)
+    ps1 = mb.PatternSimulator(gs, input_state=ins[3], backend="cuda-sv")
+    got1 = ps1.run_batch(torch.from_numpy(ang).cuda(), output_form="dm").cpu().numpy()
+    want1 = matrix_free.run_sv_batch(pat, ang, input_states=np.tile(ins[3], (B, 1)))
+    assert np.abs(got1 - want1[:, :, None] * want1.conj()[:, None, :]).max() < 1e-10
+
+
+def test_out_of_range_angles_are_reported(jit_forced):
+    gs = mb.templates.grid_cluster(2, 6)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    ang = np.random.default_rng(0).uniform(0, 2 * np.pi, (64, 10))
+    big = ang.copy()
+    big[:, 3] += 2 * np.pi * 1e5  # far outside one turn, still inside the kernels' range (|x| < 2^31)
+    a = ps.run_batch(torch.from_numpy(ang).cuda()).cpu().numpy()
+    b = ps.run_batch(torch.from_numpy(big).cuda()).cpu().numpy()
+    assert np.abs(a - b).max() < 1e-8  # the angle itself carries ~1e-10 of rounding at 6e5
+    bad = ang.copy()
+    bad[7, 2] = 3e9
+    bad[9, 0] = np.inf
+    ps.run_batch(torch.from_numpy(bad).cuda())
+    st = ps.simulator.last_status.cpu().numpy()
+    assert st[7] == _lib.STATUS_BAD_NORM and st[9] == _lib.STATUS_BAD_NORM and st[[0, 1, 8, 10]].max() == 0
