@@ -702,6 +702,11 @@ def run_gpu_arm(args):
         step(i, stream.cuda_stream)
     ctx.barrier()
     launches_per_step = (_lib.launch_count() - launches_before) // W
+    jit_info = lib.mbqc_jit_info().decode()
+    jit_on = "compiled=0 from_disk=0" not in jit_info and "failures=0" in jit_info
+    kernel_name = ("mbqc_jit_sv (mentpy_b200/csrc/sv_jit_src.inc: the pattern's kernel, specialised and compiled at plan time with NVRTC)"
+                   if jit_on else "sv_lean_kernel<3,128,false,0> (mentpy_b200/csrc/sv_lean.cuh)")
+    facts_key = "mbqc_jit_sv_c2" if jit_on else "sv_lean_kernel_c2"
 
     # the K-step block: launch-bound (one ~3 us kernel per step), so it is captured once as a CUDA
     # graph (independent batches in parallel branches) and replayed; --no-graph launches directly
@@ -825,12 +830,17 @@ def run_gpu_arm(args):
         value = world * BATCH * K / (ms * 1e-3)
         achieved = BATCH * ALGO_BYTES_PER_EVAL / (ms_per_step * 1e-3) / 1e9
         facts = ncu_facts()
-        fp64_inst = facts.get("sv_lean_kernel_c2_fp64_inst_per_eval")
-        total_inst = facts.get("sv_lean_kernel_c2_inst_per_eval")
+        fp64_inst = facts.get(facts_key + "_fp64_inst_per_eval")
+        total_inst = facts.get(facts_key + "_inst_per_eval")
         evals_per_gpu = BATCH / (ms_per_step * 1e-3)
         fp64 = {"peak_measured_tflops": fp64_peak,
                 "peak_how": "own DFMA microbenchmark (mbqc_probe_fp64_fma: 8 independent chains per thread, CUDA events, best of 5)"}
-        binds = "issue"
+        binds = "fp64" if jit_on else "issue"
+        binds_note = ("FP64 pipe: the specialised kernel is ~63 % FP64 instructions (393 of 621 per evaluation) and ncu shows the FP64 "
+                      "pipe as the busiest unit (70.9 % at B = 2^20, DRAM 37 %); HBM traffic is I/O only -- profiles/README.md"
+                      if jit_on else
+                      "neither roof: the general kernels are bound by instruction issue (an FP64 warp instruction holds the dispatch "
+                      "port 2 cycles: cycles per warp ~= non-FP64 + 2 x FP64 instructions); HBM traffic is I/O only -- profiles/README.md")
         if fp64_inst:
             # every FP64 warp instruction counted as one FMA (2 flops per lane): pipe occupancy, not useful flops
             fp64["achieved_tflops"] = evals_per_gpu * fp64_inst * 2 / 1e12
@@ -861,13 +871,10 @@ def run_gpu_arm(args):
             "ms_per_rank": [round(v, 5) for v in ms_per_rank],
             "gpu_launches": int(K * launches_per_step),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": facts.get("sv_lean_kernel_c2_bytes_per_launch"),
-                         "peak_source": peak_src, "kernel": "sv_lean_kernel<3,...> (mentpy_b200/csrc/sv_lean.cuh)",
+                         "frac": achieved / peak, "traffic": facts.get(facts_key + "_bytes_per_launch"),
+                         "peak_source": peak_src, "kernel": kernel_name, "jit": jit_info,
                          "algorithmic_bytes_per_launch": BATCH * ALGO_BYTES_PER_EVAL,
-                         "fp64": fp64, "binds": binds,
-                         "binds_note": "neither roof: the register-resident batched regime is bound by instruction issue "
-                                       "(an FP64 warp instruction holds the dispatch port 2 cycles: cycles per warp ~= non-FP64 + 2 x FP64 "
-                                       "instructions); HBM traffic is I/O only -- ncu counters in profiles/README.md"},
+                         "fp64": fp64, "binds": binds, "binds_note": binds_note},
             "cpu_baseline": {"value": cpu_rate, "unit": "evals/s", "cores": cores, "kind": "port",
                              "sample": f"{2048 * cores} angle sets of the same workload, one single-threaded process per core, "
                                        f"{cpu_s:.1f} s (oracle/dense_port.py: reference algorithm incl. dense kron operators)"},

@@ -21,4 +21,5 @@ int mbqc_lean_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, in
 
 // ---- run-time specialised kernel (sv_jit_src.inc, sv_jit_host.cu): same return convention ----
 void mbqc_jit_free(mbqc_plan* plan);
-int mbqc_jit_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st, int* rc);
+int mbqc_jit_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st,
+                        int64_t call_batch, int* rc);

@@ -349,12 +349,15 @@ static int launch_sv_reg(const SvBatchParams& p, const mbqc_plan* plan, cudaStre
     }
 }
 
-static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st, bool coalesced_out = false) {
+// call_batch: size of the API call this launch is a piece of (the host pipeline launches chunks);
+// the choice of kernel depends on the call, not on how it was cut up.
+static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form, cudaStream_t st, bool coalesced_out = false,
+                     int64_t call_batch = -1) {
     const int w = p.tab.window;
     if (w <= MBQC_MAX_WINDOW_REG) {
         int rc = 0;
         const int out_mode = out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : (coalesced_out ? MBQC_LEAN_OUT_STAGED : MBQC_LEAN_OUT_DIRECT);
-        if (mbqc_jit_try_launch(p, plan, out_mode, st, &rc)) return rc;
+        if (mbqc_jit_try_launch(p, plan, out_mode, st, call_batch < 0 ? p.batch : call_batch, &rc)) return rc;
         if (mbqc_lean_try_launch(p, plan, out_mode, st, &rc)) return rc;
     }
     if (w <= MBQC_MAX_WINDOW_REG)
@@ -523,7 +526,7 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
         double2* dst = dev_view_of_host_out ? dev_view_of_host_out + lo * out_elems : d_out + lo * out_elems;
         fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, dst, nullptr);
         p.status_any = d_any + (c % kPipeStreams);
-        rc = launch_sv(p, plan, out_form, st, dev_view_of_host_out != nullptr);
+        rc = launch_sv(p, plan, out_form, st, dev_view_of_host_out != nullptr, batch);
         if (rc) return rc;
         if (!dev_view_of_host_out)
             CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),

@@ -352,7 +352,8 @@ void mbqc_jit_free(mbqc_plan* plan) {
 }
 
 // 0 = not taken (caller continues with the ahead-of-time kernels), 1 = launched (*rc holds the result)
-int mbqc_jit_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st, int* rc) {
+int mbqc_jit_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st, int64_t call_batch,
+                        int* rc) {
     static const long long min_batch = [] {
         const char* e = getenv("MBQC_JIT_MIN_BATCH");
         return (e && *e) ? atoll(e) : 16384ll;
@@ -363,7 +364,7 @@ int mbqc_jit_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_m
     }();
     const int mode = jit_mode();
     if (mode == 0 || !plan->lean) return 0;
-    if (mode == 1 && p.batch < min_batch) return 0;
+    if (mode == 1 && call_batch < min_batch) return 0;
     const int T = p.tab.n_angles;
     if (p.stride != T || ((uintptr_t)p.angles & 15u)) return 0;
     Variant v{out_mode, 128};
