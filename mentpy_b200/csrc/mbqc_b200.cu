@@ -715,6 +715,7 @@ namespace {
 // Shared by the per-sample and the data-set entry points: p.batch samples, p.grad [batch][T].
 int launch_psr_grad(const mbqc_plan* plan, const SvBatchParams& p, cudaStream_t st) {
     int rc = MBQC_OK;
+    if (mbqc_jit_grad_try_launch(plan, p, st, &rc)) return rc;  // pattern-specialised kernel (sv_jit_grad_src.inc)
     const int w = plan->tab.window;
     const int64_t batch = p.batch;
     const int T = plan->tab.n_angles;

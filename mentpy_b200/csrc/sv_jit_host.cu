@@ -13,6 +13,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,10 @@ namespace {
 const char* kJitSource =
 #include "sv_jit_src.inc"
     ;
+const char* kJitGradSource =
+#include "sv_jit_grad_src.inc"
+    ;
+constexpr int kKindRun = 0, kKindGrad = 1;
 
 // ---- NVRTC through dlopen --------------------------------------------------------------------
 struct Nvrtc {
@@ -94,7 +99,11 @@ Nvrtc& nvrtc() {
 // ---- source generation ---------------------------------------------------------------------------
 struct Variant {
     int out_mode, cta;
-    bool operator<(const Variant& o) const { return out_mode != o.out_mode ? out_mode < o.out_mode : cta < o.cta; }
+    int kind = kKindRun;  // kKindRun: mbqc_jit_sv, kKindGrad: mbqc_jit_grad
+    bool operator<(const Variant& o) const {
+        if (kind != o.kind) return kind < o.kind;
+        return out_mode != o.out_mode ? out_mode < o.out_mode : cta < o.cta;
+    }
 };
 
 void appendf(std::string& s, const char* fmt, ...) {
@@ -110,7 +119,8 @@ void appendf(std::string& s, const char* fmt, ...) {
 std::string make_preamble(const mbqc_plan* plan, Variant v) {
     const LeanParams& lp = *plan->lean;
     const int w = plan->tab.window, M = lp.n_steps, np = 1 << (w - 1), n = 1 << w;
-    const int minblocks = (w <= 3) ? 1024 / v.cta : (w == 4 ? 640 / v.cta : 384 / v.cta);
+    int minblocks = (w <= 3) ? 1024 / v.cta : (w == 4 ? 640 / v.cta : 384 / v.cta);
+    if (v.kind == kKindGrad) minblocks = (w <= 3) ? 1024 / v.cta : (w == 4 ? 640 / v.cta : 384 / v.cta);  // two working buffers
     std::string s;
     appendf(s, "#define JW %d\n#define JM %d\n#define JNFULL %d\n#define JT %d\n#define JNOUT %d\n#define JNIN %d\n", w, M,
             lp.n_full, lp.n_angles, lp.n_out, lp.n_in);
@@ -147,9 +157,91 @@ std::string make_preamble(const mbqc_plan* plan, Variant v) {
         appendf(dst, "%d,", (int)lp.out_dst[i]);
     }
     s += src + "};\n" + dst + "};\n";
-    std::string steps = "#define JSTEPS";
-    for (int m = 0; m < M; ++m) appendf(steps, " jit_renorm<%d>(re, im, zr, zi); jit_step<%d>(row, s_trig, re, im, zr, zi, big);", m, m);
-    s += steps + "\n";
+    if (v.kind == kKindRun) {
+        std::string steps = "#define JSTEPS";
+        for (int m = 0; m < M; ++m) appendf(steps, " jit_renorm<%d>(re, im, zr, zi); jit_step<%d>(row, s_trig, re, im, zr, zi, big);", m, m);
+        s += steps + "\n";
+    } else {
+        // run-time indexable copies of two tables + the switch bodies of the gradient kernel
+        std::string fx = "__constant__ int kFixedIdxRt[JM] = {", cl = "__constant__ int kColRt[JM] = {";
+        // measurement m reads the buffer m & 1 (E = even, O = odd) and writes the other one; the
+        // power-of-two damping every 8 measurements is part of the case body.  STEP: working state;
+        // YSTEP: prefix (shared memory) -> u-part in the working state; PSTEP: prefix -> prefix.
+        std::string cs = "#define JCASES_STEP", cy = "#define JCASES_YSTEP", cp = "#define JCASES_PSTEP";
+        int nf = 0;
+        for (int m = 0; m < M; ++m) {
+            const bool fixed = (lp.colofs[m] & kLeanFixedBit) != 0;
+            appendf(fx, "%d,", fixed ? nf++ : -1);
+            appendf(cl, "%d,", fixed ? 0 : (int)(lp.colofs[m] / 8));
+            if (m == 0) continue;  // measurement 0 reads the full seed state: handled outside the switches
+            const bool odd = m & 1;
+            const char* src = odd ? "wOr, wOi" : "wEr, wEi";
+            const char* dst = odd ? "wEr, wEi" : "wOr, wOi";
+            std::string damp = ((m & 7) == 7) ? std::string(" damp(") + dst + ");" : std::string();
+            appendf(cs, " case %d: step_angle<%d>(cs, c, s); jit_cstep<%d, false>(%s, %s, c, s);%s break;", m, m, m, src, dst, damp.c_str());
+            if (!fixed)
+                appendf(cy, " case %d: load_prefix(pfx, %s); step_angle<%d>(cs, c, s); jit_cstep<%d, true>(%s, %s, c, s);%s break;", m, src,
+                        m, m, src, dst, damp.c_str());
+            appendf(cp, " case %d: load_prefix(pfx, %s); step_angle<%d>(cs, c, s); jit_cstep<%d, false>(%s, %s, c, s);%s store_prefix(pfx, %s); break;",
+                    m, src, m, m, src, dst, damp.c_str(), dst);
+        }
+        s += cp + "\n";
+        s += fx + "};\n" + cl + "};\n" + cs + "\n" + cy + "\n";
+        // compressed-state bookkeeping: which register-index bit holds the slot measured at step m,
+        // and the pending CZ signs of step m-1 seen from the register pairs of step m
+        std::vector<int> pos2slot;
+        const int s0 = w - 1;
+        for (int sl = 0; sl < w; ++sl)
+            if (sl != s0) pos2slot.push_back(sl);
+        auto full_index = [&](int r) {
+            int i = 0;
+            for (int q = 0; q < w - 1; ++q)
+                if ((r >> q) & 1) i |= 1 << pos2slot[q];
+            return i;
+        };
+        auto pending_mask = [&](int m) -> uint64_t {  // CZ neighbours of the qubit appended at step m
+            return (plan->h_steps[m].flags & MBQC_STEP_APPEND) ? plan->h_steps[m].nbr_mask : 0ull;
+        };
+        std::string qb = "constexpr int kQBit[JM] = {0,", sa = "constexpr unsigned kSA[JM] = {0u,", sb = "constexpr unsigned kSB[JM] = {0u,";
+        const int groups = (1 << (w - 1)) / 2;
+        for (int m = 1; m < M; ++m) {
+            const int sm = w - 1 - (m % w), sprev = w - 1 - ((m - 1) % w);
+            int q = -1;
+            for (int t = 0; t < w - 1; ++t)
+                if (pos2slot[t] == sm) q = t;
+            const uint64_t mask = pending_mask(m - 1);
+            unsigned ma = 0, mb = 0;
+            for (int g = 0; g < groups; ++g) {
+                const int r0 = ((g >> q) << (q + 1)) | (g & ((1 << q) - 1)), r1 = r0 | (1 << q);
+                if (__builtin_parityll((uint64_t)full_index(r0) & mask)) ma |= 1u << g;
+                if (__builtin_parityll((uint64_t)full_index(r1) & mask)) mb |= 1u << g;
+            }
+            appendf(qb, "%d,", q);
+            appendf(sa, "%uu,", ma);
+            appendf(sb, "%uu,", mb);
+            pos2slot[q] = sprev;
+        }
+        s += qb + "};\n" + sa + "};\n" + sb + "};\n";
+        // outputs: register and pending sign of output index d in the final compressed state
+        const int slast = w - 1 - ((M - 1) % w);
+        const uint64_t mlast = pending_mask(M - 1);
+        std::vector<int> oreg(1 << lp.n_out, 0), oneg(1 << lp.n_out, 0);
+        for (int i = 0; i < n; ++i) {
+            const int d = lp.out_dst[i];
+            if (d < 0) continue;
+            int r = 0;
+            for (int t = 0; t < w - 1; ++t)
+                if ((i >> pos2slot[t]) & 1) r |= 1 << t;
+            oreg[d] = r;
+            oneg[d] = ((i >> slast) & 1) ? __builtin_parityll((uint64_t)(i & ~(1 << slast)) & mlast) : 0;
+        }
+        std::string orr = "constexpr int kOutReg[] = {", onn = "constexpr bool kOutNeg[] = {";
+        for (size_t d = 0; d < oreg.size(); ++d) {
+            appendf(orr, "%d,", oreg[d]);
+            appendf(onn, "%s,", oneg[d] ? "true" : "false");
+        }
+        s += orr + "};\n" + onn + "};\n";
+    }
     return s;
 }
 
@@ -253,7 +345,7 @@ bool compile_cubin(const std::string& source, std::vector<char>& cubin, std::str
 
 // kernel for (plan, variant) on the current device, or nullptr (reason in state().last_error)
 cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
-    const std::string source = make_preamble(plan, v) + kJitSource;
+    const std::string source = make_preamble(plan, v) + (v.kind == kKindGrad ? kJitGradSource : kJitSource);
     const uint64_t h = fnv1a(source);
     int device = 0;
     cudaGetDevice(&device);
@@ -265,7 +357,8 @@ cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
     std::vector<char> cubin;
     const std::string dir = cache_dir();
     char name[64];
-    snprintf(name, sizeof(name), "/sv_%016llx_nvrtc%d%d.cubin", (unsigned long long)h, nvrtc().major, nvrtc().minor);
+    snprintf(name, sizeof(name), "/%s_%016llx_nvrtc%d%d.cubin", v.kind == kKindGrad ? "grad" : "sv", (unsigned long long)h,
+             nvrtc().major, nvrtc().minor);
     bool have = !dir.empty() && read_file(dir + name, cubin);
     if (have) ++st.from_disk;
     if (!have) {
@@ -281,7 +374,7 @@ cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
         if (!dir.empty()) write_file_atomic(dir + name, cubin);
     }
     cudaError_t e = cudaLibraryLoadData(&ld.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&ld.kernel, ld.lib, "mbqc_jit_sv");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&ld.kernel, ld.lib, v.kind == kKindGrad ? "mbqc_jit_grad" : "mbqc_jit_sv");
     if (e != cudaSuccess) {
         cudaGetLastError();
         st.last_error = std::string("loading the specialised kernel: ") + cudaGetErrorString(e);
@@ -377,7 +470,7 @@ int mbqc_jit_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_m
     if (smem > 96 * 1024) return 0;
     cudaKernel_t kern = get_kernel(plan, v);
     if (!kern) return 0;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {  // static shared memory (tables, barriers) counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             *rc = mbqc_cuda_error(e, "cudaFuncSetAttribute(mbqc_jit_sv)");
@@ -401,6 +494,68 @@ int mbqc_jit_try_launch(const SvBatchParams& p, const mbqc_plan* plan, int out_m
         return 1;
     }
     *rc = mbqc_after_launch("mbqc_jit_sv");
+    return 1;
+}
+
+struct JitGradArgsHost {  // mirrors JitGradArgs of sv_jit_grad_src.inc
+    const double* angles;
+    const double2* inputs;
+    const double2* target;
+    const double2* trig;
+    double* grad;
+    double* cost;
+    int* status;
+    long long stride, batch, data_count;
+    int input_mode;
+    double gr, gi, inv2s;
+};
+
+// Parameter-shift gradient through the specialised kernel: same return convention as above.
+int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cudaStream_t st, int* rc) {
+    static const long long min_batch = [] {
+        const char* e = getenv("MBQC_JIT_MIN_BATCH");
+        return (e && *e) ? atoll(e) : 16384ll;
+    }();
+    const int mode = jit_mode();
+    if (mode == 0 || !plan->lean) return 0;
+    if (mode == 1 && p.batch < min_batch) return 0;
+    const int T = p.tab.n_angles;
+    Variant v{0, 128, kKindGrad};
+    const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
+    if (smem > 200 * 1024 || T > 64) return 0;
+    cudaKernel_t kern = get_kernel(plan, v);
+    if (!kern) return 0;
+    if (smem > 40 * 1024) {  // static shared memory (tables, barriers) counts against the 48 KB default too
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            *rc = mbqc_cuda_error(e, "cudaFuncSetAttribute(mbqc_jit_grad)");
+            return 1;
+        }
+    }
+    JitGradArgsHost a;
+    a.angles = p.angles;
+    a.inputs = p.inputs;
+    a.target = p.target;
+    a.trig = trig_table_device();
+    a.grad = p.grad;
+    a.cost = p.cost;
+    a.status = p.status;
+    a.stride = p.stride;
+    a.batch = p.batch;
+    a.data_count = p.data_count;
+    a.input_mode = p.input_mode;
+    const double sh = sin(0.5 * p.shift);
+    a.gr = -2.0 * sh * sh;  // cos s - 1 without cancellation (finite differences use s = 1e-5)
+    a.gi = -sin(p.shift);
+    a.inv2s = 1.0 / (2.0 * p.shift);
+    void* args[] = {&a};
+    const unsigned blocks = (unsigned)((p.batch + v.cta - 1) / v.cta);
+    cudaError_t e = cudaLaunchKernel((const void*)kern, dim3(blocks), dim3(v.cta), args, smem, st);
+    if (e != cudaSuccess) {
+        *rc = mbqc_cuda_error(e, "cudaLaunchKernel(mbqc_jit_grad)");
+        return 1;
+    }
+    *rc = mbqc_after_launch("mbqc_jit_grad");
     return 1;
 }
 
@@ -432,8 +587,10 @@ int32_t mbqc_jit_set_mode(int32_t mode) {
 int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t cta) {
     if (!plan) return mbqc_set_error(MBQC_E_ARG, "plan is NULL");
     if (!plan->lean) return 0;
+    // out_form: MBQC_OUT_SV / MBQC_OUT_DM -> mbqc_jit_sv; 100 -> the gradient kernel mbqc_jit_grad
     Variant v{out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : MBQC_LEAN_OUT_DIRECT, cta == 64 ? 64 : 128};
-    const std::string source = make_preamble(plan, v) + kJitSource;
+    if (out_form == 100) v = Variant{0, 128, kKindGrad};
+    const std::string source = make_preamble(plan, v) + (v.kind == kKindGrad ? kJitGradSource : kJitSource);
     std::vector<char> cubin;
     std::string err;
     if (!compile_cubin(source, cubin, err)) return mbqc_set_error(MBQC_E_UNSUPPORTED, err.c_str());

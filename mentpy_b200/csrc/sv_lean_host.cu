@@ -67,7 +67,7 @@ void mbqc_lean_free_proto(mbqc_plan* plan) {
 template <int W, int CTA, bool FIXED, int OUT>
 static int launch_lean_inst(const LeanParams& lp, size_t smem, cudaStream_t st) {
     auto kern = sv_lean_kernel<W, CTA, FIXED, OUT>;
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {  // static shared memory (trig table, barriers) counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return mbqc_cuda_error(e, "cudaFuncSetAttribute(sv_lean_kernel)");
     }

@@ -154,3 +154,86 @@ def test_out_of_range_angles_are_reported(jit_forced):
     ps.run_batch(torch.from_numpy(bad).cuda())
     st = ps.simulator.last_status.cpu().numpy()
     assert st[7] == _lib.STATUS_BAD_NORM and st[9] == _lib.STATUS_BAD_NORM and st[[0, 1, 8, 10]].max() == 0
+
+
+# ---- specialised gradient kernel (sv_jit_grad_src.inc) -------------------------------------------
+GRAD = load_golden("gradients.json")
+
+
+def test_specialised_gradient_reproduces_the_reference_golden(jit_forced):
+    """grid_cluster(4,5): cost and parameter-shift gradient recorded from mentpy.gradients.get_gradient."""
+    from mentpy_b200.gradients import psr_gradient_batched
+
+    g = GRAD["c4"]
+    name, args, kwargs = g["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    x = np.asarray(g["x"])
+    tgt = from_cplx(g["target"]).reshape(-1)
+    rows = np.random.default_rng(0).uniform(0, 2 * np.pi, (37, len(x)))
+    rows[11] = x
+    grad, cost = psr_gradient_batched(ps, torch.from_numpy(rows).cuda(), tgt, return_cost=True)
+    assert "failures=0" in jit_forced.mbqc_jit_info().decode()
+    assert abs(cost[11].item() - g["cost"]) < 1e-12
+    assert np.abs(grad[11].cpu().numpy() - np.asarray(g["psr"])).max() < 1e-12
+    fd = psr_gradient_batched(ps, torch.from_numpy(rows).cuda(), tgt, shift=1e-5)
+    assert np.abs(fd[11].cpu().numpy() - np.asarray(g["fd"])).max() < 1e-8  # central difference, h = 1e-5
+
+
+@pytest.mark.parametrize("spec,w", [(("linear_cluster", [5]), None), (("grid_cluster", [2, 6]), None),
+                                    (("grid_cluster", [3, 5]), None), (("grid_cluster", [4, 5]), None),
+                                    (("grid_cluster", [2, 5]), 5), (("muta", [2, 1]), None),
+                                    (("linear_cluster", [40]), 3), (("many_wires", [[3, 4, 2]]), None)])
+def test_specialised_gradient_matches_general_kernels(spec, w, jit_forced):
+    """Random targets, Haar inputs per sample, fixed-angle nodes: specialised kernel vs the
+    ahead-of-time gradient kernels (which the round-1 suite pins to the reference)."""
+    from scipy.stats import unitary_group
+
+    from mentpy_b200.gradients import psr_gradient_batched
+
+    gs = getattr(mb.templates, spec[0])(*spec[1])
+    if spec[0] == "grid_cluster" and spec[1] == [2, 5]:
+        gs[1] = mb.Ment("X")
+        gs[7] = mb.Ment(0.3, "XY")
+    kw = {} if w is None else {"window_size": w}
+    ps = mb.PatternSimulator(gs, backend="cuda-sv", **kw)
+    T, k, n_in = len(gs.trainable_nodes), len(gs.output_nodes), len(gs.input_nodes)
+    B = 77
+    rng = np.random.default_rng(T)
+    ang = torch.from_numpy(rng.uniform(-4, 4, (B, T))).cuda()
+    tgt = unitary_group.rvs(2**k, random_state=1)[:, 0] if k > 0 else np.ones(1, complex)
+    ins = np.stack([unitary_group.rvs(2**n_in, random_state=s)[:, 0] for s in range(B)])
+    res = {}
+    for mode in (2, 0):
+        jit_forced.mbqc_jit_set_mode(mode)
+        g1, c1 = psr_gradient_batched(ps, ang, tgt, return_cost=True)
+        g2, c2 = psr_gradient_batched(ps, ang, tgt, input_states=ins, return_cost=True)
+        res[mode] = [x.cpu().numpy() for x in (g1, c1, g2, c2)]
+    jit_forced.mbqc_jit_set_mode(2)
+    assert "failures=0" in jit_forced.mbqc_jit_info().decode()
+    for a, b in zip(res[2], res[0]):
+        assert np.abs(a - b).max() < 1e-11
+
+
+def test_specialised_gradient_dataset_mode(jit_forced):
+    """Data-set averaged gradient (mbqc_psr_grad_dataset): sample p * S + s uses angle row p,
+    input / target s."""
+    from scipy.stats import unitary_group
+
+    from mentpy_b200.gradients import psr_gradient_dataset
+
+    gs = mb.templates.grid_cluster(2, 5)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    T = len(gs.trainable_nodes)
+    P, S = 5, 9
+    rng = np.random.default_rng(5)
+    X = torch.from_numpy(rng.uniform(0, 2 * np.pi, (P, T))).cuda()
+    ins = np.stack([unitary_group.rvs(4, random_state=s)[:, 0] for s in range(S)])
+    tgs = np.stack([unitary_group.rvs(4, random_state=100 + s)[:, 0] for s in range(S)])
+    out = {}
+    for mode in (2, 0):
+        jit_forced.mbqc_jit_set_mode(mode)
+        g, c = psr_gradient_dataset(ps, X, tgs, ins, return_cost=True)
+        out[mode] = (g.cpu().numpy(), c.cpu().numpy())
+    jit_forced.mbqc_jit_set_mode(2)
+    assert np.abs(out[2][0] - out[0][0]).max() < 1e-12 and np.abs(out[2][1] - out[0][1]).max() < 1e-12
