@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "common.cuh"
@@ -135,6 +136,10 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
         }
     }
     pl->h_steps = new (std::nothrow) StepDev[n_steps > 0 ? n_steps : 1];
+    if (!pl->h_steps) {
+        delete pl;
+        return fail(MBQC_E_CUDA, "out of host memory");
+    }
     for (int m = 0; m < n_steps; ++m) {
         StepDev& d = pl->h_steps[m];
         const mbqc_step& s = steps[m];
@@ -189,7 +194,13 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
                 ++pidx;
             }
         }
-        if (n_angles + (int)fixed.size() > 0xffff) periodic = 0;  // (never for w <= 5 patterns in practice)
+        if (n_angles + (int)fixed.size() > 0xffff) {
+            // the packed (slot << 16 | column) words of the register kernels cannot name the column
+            delete[] pl->h_steps;
+            delete pl;
+            return fail(MBQC_E_UNSUPPORTED, "window <= %d patterns are limited to 65535 angle columns (got %d)",
+                        MBQC_MAX_WINDOW_REG, n_angles + (int)fixed.size());
+        }
         const size_t b_signs = signs.size() * 4, b_cols = cols.size() * 4, b_fixed = (fixed.size() ? fixed.size() : 1) * 16;
         pl->reg_n_fixed = (int)fixed.size();
         pl->reg_sign_pitch = sp;
@@ -327,6 +338,9 @@ static int launch_sv_reg_w(const SvBatchParams& p, const mbqc_plan* plan, cudaSt
     SvRegParams rp;
     fill_reg_params(rp, p, plan);
     const size_t tables = reg_smem_tables_bytes(p.tab.n_steps, rp.reg.sign_pitch, rp.reg.n_fixed);
+    if (tables > 200 * 1024)
+        return fail(MBQC_E_UNSUPPORTED, "%d measurements at window %d: the step tables (%zu bytes) exceed the shared-memory budget of the register kernels",
+                    p.tab.n_steps, W, tables);
     const size_t tile = (size_t)per_cta * p.tab.n_angles * sizeof(double2);
     const int staged = (p.tab.n_angles > 0 && tables + tile <= 100 * 1024) ? 1 : 0;
     size_t smem = tables + (staged ? tile : 0);
@@ -409,6 +423,7 @@ struct PipeTicket {
     bool busy = false;
 };
 struct PipeState {  // created lazily, once per device
+    std::mutex mu;  // ctypes releases the GIL: two host threads may submit / wait on one device
     cudaStream_t s[kPipeSets][kPipeStreams];
     cudaEvent_t joined[kPipeSets][kPipeStreams];
     PipeTicket ticket[kPipeTickets];
@@ -420,6 +435,7 @@ PipeState g_pipe[64];
 int pipe_state(int device, PipeState** out) {
     if (device < 0 || device >= 64) return fail(MBQC_E_ARG, "device index %d out of range", device);
     PipeState& ps = g_pipe[device];
+    std::lock_guard<std::mutex> lock(ps.mu);
     if (!ps.ready) {
         for (int g = 0; g < kPipeSets; ++g)
             for (int i = 0; i < kPipeStreams; ++i) {
@@ -464,6 +480,7 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
     CUDA_TRY(cudaGetDevice(&device));
     rc = pipe_state(device, &ps);
     if (rc) return rc;
+    std::lock_guard<std::mutex> pipe_lock(ps->mu);
     const unsigned slot = ps->next % kPipeTickets;
     PipeTicket& tk = ps->ticket[slot];
     if (tk.busy) return fail(MBQC_E_ARG, "%d host calls already in flight on device %d: wait for the oldest first", kPipeTickets, device);
@@ -527,7 +544,11 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
         fill_sv_params(p, plan, d_angles + lo * Tw, Tw, din, input_mode, hi - lo, dst, nullptr);
         p.status_any = d_any + (c % kPipeStreams);
         rc = launch_sv(p, plan, out_form, st, dev_view_of_host_out != nullptr, batch);
-        if (rc) return rc;
+        if (rc) {
+            // chunks already queued still read the caller's buffers: drain them before reporting
+            for (int i = 0; i < kPipeStreams; ++i) cudaStreamSynchronize(str[i]);
+            return rc;
+        }
         if (!dev_view_of_host_out)
             CUDA_TRY(cudaMemcpyAsync((double2*)h_out + lo * out_elems, d_out + lo * out_elems, (size_t)(hi - lo) * out_elems * sizeof(double2),
                                      cudaMemcpyDeviceToHost, st));
@@ -549,9 +570,15 @@ extern "C" int mbqc_host_wait(int32_t ticket, int32_t* h_status_any) {
     PipeState& ps = g_pipe[ticket / kPipeTickets];
     if (!ps.ready) return fail(MBQC_E_ARG, "ticket %d: nothing was submitted on that device", ticket);
     PipeTicket& tk = ps.ticket[ticket % kPipeTickets];
-    if (!tk.busy) return fail(MBQC_E_ARG, "ticket %d is not in flight", ticket);
+    cudaEvent_t done;
+    {
+        std::lock_guard<std::mutex> lock(ps.mu);
+        if (!tk.busy) return fail(MBQC_E_ARG, "ticket %d is not in flight", ticket);
+        done = tk.done;
+    }
+    CUDA_TRY(cudaEventSynchronize(done));  // outside the lock: other threads keep submitting
+    std::lock_guard<std::mutex> lock(ps.mu);
     tk.busy = false;
-    CUDA_TRY(cudaEventSynchronize(tk.done));
     if (h_status_any) {
         int32_t any = 0;
         for (int i = 0; i < tk.used; ++i) any |= tk.h_flags[i];

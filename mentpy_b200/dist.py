@@ -137,6 +137,9 @@ def psr_gradient_dataset_distributed(simulator, angles, targets, input_states=No
     dev = sim._dev()
     a = angles if isinstance(angles, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(angles, dtype=np.float64))
     a = a.to(dev)
+    if input_states is None and getattr(sim, 'input_state', None) is not None and not sim._input_is_plus():
+        # differentiate the cost run_batch evaluates (the simulator's own input state)
+        input_states = np.tile(np.asarray(sim.input_state, dtype=np.complex128), (S, 1))
     if hi > lo:
         g, c = psr_gradient_dataset(sim, a, targets[lo:hi], None if input_states is None else input_states[lo:hi],
                                     shift=shift, return_cost=True)

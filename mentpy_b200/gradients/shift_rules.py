@@ -170,6 +170,10 @@ def psr_gradient_dataset(simulator, angles, targets, input_states=None, shift=1.
 
         tg = stage(targets, 2 ** dplan.n_out, "targets")
         S = tg.shape[0]
+        if input_states is None and not sim._input_is_plus():
+            # the cost is evaluated with the simulator's own input state (run_batch: INPUT_SHARED):
+            # differentiate that cost, not the |+> one
+            input_states = np.tile(np.asarray(sim.input_state, dtype=np.complex128), (S, 1))
         inp = None if input_states is None else stage(input_states, 2 ** dplan.n_in, "input_states")
         if inp is not None and inp.shape[0] != S:
             raise ValueError("need one target state per input state")

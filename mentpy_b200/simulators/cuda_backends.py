@@ -79,7 +79,10 @@ class PendingBatch:
 
     def __init__(self, lib, call, turn, ticket, check, keep):
         self._lib, self._call, self._turn, self._ticket, self._check = lib, call, turn, ticket, check
-        self._keep = keep  # the input buffer the copy engines are still reading
+        # what the queued work still reads: the angle buffer (copy engines), the input-state tensor
+        # (kernels), and -- through self._call -- the workspace / page-locked result buffers, which
+        # therefore outlive an eviction of the simulator's call cache
+        self._keep = keep
         self._done = False
         self.status_any = None
 
@@ -95,6 +98,15 @@ class PendingBatch:
                 raise ValueError("qstate has nan, you might want to increase the window size")
         res = self._call.views[self._turn]
         return res.copy() if copy else res
+
+    def __del__(self):
+        # a handle dropped without result() must still give its ticket back (four tickets per device)
+        if not getattr(self, "_done", True):
+            try:
+                self._lib.mbqc_host_wait(self._ticket, None)
+            except Exception:
+                pass
+            self._done = True
 
 
 class _ReadyBatch:
@@ -181,6 +193,12 @@ class _CudaPatternBase(BaseSimulator):
 
     def _noise_for_prefix(self):
         return None
+
+    def _input_is_plus(self) -> bool:
+        """True when the simulator's input state is the default |+>^|I| (pattern_simulator.py:58-61)."""
+        n = len(self.plan.input_nodes)
+        st = np.asarray(self.input_state)
+        return st.shape == (2 ** n,) and np.allclose(st, np.full(2 ** n, 2.0 ** (-n / 2)), rtol=0, atol=1e-15)
 
     def _device_input(self, dev):
         st = np.ascontiguousarray(self.input_state, dtype=np.complex128)
@@ -461,11 +479,16 @@ class CudaSimulatorSV(_CudaPatternBase):
         call = self._host_calls.get(key)
         if call is None:
             if len(self._host_calls) > 8:
+                # in-flight PendingBatch handles hold their own reference to their _HostCall, so the
+                # buffers of queued work stay alive; only idle entries are really dropped here
                 self._host_calls.clear()
             call = self._host_calls[key] = _HostCall(lib, dplan, dev, batch, T, code)
         inp, mode = self._stage_inputs(input_states, batch, dev)
-        if not self._input_synced:
-            torch.cuda.current_stream(dev).synchronize()  # the pipeline runs on its own streams
+        if input_states is not None or not self._input_synced:
+            # the pipeline reads `inp` on its own non-blocking streams: a tensor that was just
+            # uploaded on torch's current stream must be complete before the submit (a per-call
+            # input state is a fresh temporary every time; the cached default only once)
+            torch.cuda.current_stream(dev).synchronize()
             self._input_synced = True
         call.turn = (call.turn + 1) % call.DEPTH
         if batch * T >= (1 << 16) and not src.is_pinned():
@@ -479,7 +502,7 @@ class CudaSimulatorSV(_CudaPatternBase):
             if rc:
                 _lib.check(rc)
             self.last_status = None
-            return PendingBatch(lib, call, call.turn, call.ticket.value, check, src)
+            return PendingBatch(lib, call, call.turn, call.ticket.value, check, (src, inp))
         rc = lib.mbqc_run_batch_sv_host(dplan.handle, src.data_ptr(), max(T, 1), _ptr(inp), mode, batch,
                                         call.out_ptr[call.turn], code, call.work_ptr[call.turn], call.need,
                                         call.flag_ref, 0)

@@ -237,3 +237,46 @@ def test_specialised_gradient_dataset_mode(jit_forced):
         out[mode] = (g.cpu().numpy(), c.cpu().numpy())
     jit_forced.mbqc_jit_set_mode(2)
     assert np.abs(out[2][0] - out[0][0]).max() < 1e-12 and np.abs(out[2][1] - out[0][1]).max() < 1e-12
+
+
+# ---- regressions for the round-1 advisor findings -------------------------------------------------
+def test_dataset_gradient_uses_the_simulators_input_state():
+    """psr_gradient_dataset(input_states=None) must differentiate the cost that run_batch evaluates,
+    i.e. use the simulator's own (non-default) input state."""
+    from scipy.stats import unitary_group
+
+    from mentpy_b200.gradients import psr_gradient_dataset
+
+    gs = mb.templates.grid_cluster(2, 4)
+    st = unitary_group.rvs(4, random_state=3)[:, 0]
+    ps = mb.PatternSimulator(gs, input_state=st, backend="cuda-sv")
+    T = len(gs.trainable_nodes)
+    X = torch.from_numpy(np.random.default_rng(1).uniform(0, 2 * np.pi, (3, T))).cuda()
+    tgs = np.stack([unitary_group.rvs(4, random_state=20 + s)[:, 0] for s in range(5)])
+    g_none, c_none = psr_gradient_dataset(ps, X, tgs, None, return_cost=True)
+    g_expl, c_expl = psr_gradient_dataset(ps, X, tgs, np.tile(st, (5, 1)), return_cost=True)
+    assert np.abs((g_none - g_expl).cpu().numpy()).max() < 1e-14
+    # and the cost is the one run_batch gives
+    out = ps.run_batch(X).cpu().numpy()
+    want = np.array([[1 - abs(np.vdot(t, o)) ** 2 for t in tgs] for o in out]).mean(axis=1)
+    assert np.abs(c_none.cpu().numpy() - want).max() < 1e-12
+    assert np.abs(c_none.cpu().numpy() - c_expl.cpu().numpy()).max() < 1e-14
+
+
+def test_async_host_calls_with_per_call_input_state_and_dropped_handles():
+    from scipy.stats import unitary_group
+
+    gs = mb.templates.grid_cluster(2, 6)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    ang = np.random.default_rng(2).uniform(0, 2 * np.pi, (3000, 10))
+    for s in range(6):  # a fresh temporary input tensor per call: it must be complete before the pipeline reads it
+        st = unitary_group.rvs(4, random_state=s)[:, 0]
+        want = ps.run_batch(torch.from_numpy(ang).cuda(), input_states=torch.from_numpy(st).cuda()).cpu().numpy()
+        got = ps.run_batch_async(ang, input_states=st).result()
+        assert np.abs(got - want).max() < 1e-12
+    for _ in range(7):  # handles dropped without result(): their tickets must come back
+        ps.run_batch_async(ang)
+    import gc
+
+    gc.collect()
+    assert ps.run_batch_async(ang).result().shape == (3000, 4)
