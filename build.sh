@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 OUT=${MBQC_BUILD_OUT:-mentpy_b200/_mbqc_b200.so}
 OBJ=${MBQC_BUILD_OBJ:-build/obj}
 mkdir -p "$OBJ"
-SRCS="mbqc_b200 sv_lean_host sv_jit_host probes"
+SRCS="mbqc_b200 sv_lean_host sv_jit_host probes peer"
 ONLY=${1:-$SRCS}
 pids=""
 for s in $ONLY; do

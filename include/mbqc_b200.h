@@ -219,6 +219,17 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
                         const void* d_target, double shift, double* d_grad, double* d_cost,
                         int32_t* d_status, void* stream);
 
+/* The same gradient with a REPLICATED result: the `batch` rows of this call are rows
+ * first_row .. first_row + batch of a [total][T] float64 result that lives on n_results GPUs;
+ * d_results[0] is the local copy, d_results[1..] are the other GPUs' copies (peer-mapped: CUDA IPC,
+ * mbqc_ipc_import).  The kernel stores each finished tile of rows into every copy (NVLink peer
+ * stores overlap the remaining computation): the multi-GPU form of gradients/_parameter_shift.py:9-25
+ * where the final gather is part of the launch.  Follow with mbqc_peer_barrier before reading. */
+int mbqc_psr_grad_batch_push(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                             const void* d_inputs, int32_t input_mode, int64_t batch,
+                             const void* d_target, double shift, void* const* d_results, int32_t n_results,
+                             int64_t first_row, double* d_cost, int32_t* d_status, void* stream);
+
 /* Data-set averaged cost and its gradient in one call -- the S x 2T pattern evaluations of one
  * optimiser step of the reference's training loop (docs/tutorials/intro-to-mbqml.rst:35-86:
  * cost(x) = mean_s [1 - |<t_s|psi(x; in_s)>|^2], differentiated by gradients/_parameter_shift.py:9-25):
@@ -329,6 +340,13 @@ int mbqc_device_free(void* d_ptr);
 int mbqc_ipc_export(const void* d_ptr, void* handle64);
 int mbqc_ipc_import(const void* handle64, void** d_ptr);
 int mbqc_ipc_close(void* d_ptr);
+
+/* Stream-ordered barrier across the GPUs of one node through flag words in peer-mapped memory:
+ * d_flags[r] = rank r's array of 8 uint64 (zeroed once; entry `rank` is the caller's own
+ * allocation, the others are IPC imports).  `epoch` grows by one per call on every rank.  Work
+ * queued on `stream` after the call starts only when every rank's earlier work on its stream --
+ * including its peer stores -- has completed. */
+int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, uint64_t epoch, void* stream);
 
 /* ---- calculator helpers (mentpy/calculator/state_ops.py), single state, qubit 0 = MSB ------------
  * pure: SUM over the traced qubits then renormalise (:42-74 -- the reference's pure-state "partial

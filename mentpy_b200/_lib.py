@@ -88,6 +88,9 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                       C.c_int64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mbqc_psr_grad_batch_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                           C.c_int64, C.c_void_p, C.c_double, C.POINTER(C.c_void_p), C.c_int32,
+                                           C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_run_batch_dm_expect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_plan_set_feedforward": (C.c_int, [C.c_void_p, C.POINTER(FeedForwardC), C.c_int32]),
@@ -119,6 +122,7 @@ _SIGNATURES = {
     "mbqc_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mbqc_ipc_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mbqc_ipc_close": (C.c_int, [C.c_void_p]),
+    "mbqc_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
     "mbqc_partial_trace_pure": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "mbqc_partial_trace_mixed": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "mbqc_pure2density": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -15,22 +15,9 @@
 // optional single-qubit channel of the plan folded into the q coefficients.
 #pragma once
 #include "common.cuh"
+#include "dm_params.cuh"
 
 namespace mbqc {
-
-struct DmBatchParams {
-    PlanTables tab;
-    const StepDev* __restrict__ steps;
-    const double* __restrict__ angles;
-    int64_t stride;
-    const double2* __restrict__ inputs;
-    int32_t input_mode;
-    int64_t batch;
-    double2* __restrict__ out;      // [B][4^k]
-    int8_t* __restrict__ outcomes;  // [B][n_steps] or null
-    int32_t* __restrict__ status;
-    double* __restrict__ expect;    // [B][n_steps] prob1 of plane-Z steps (expectation mode) or null
-};
 
 struct MeasCoef {
     double q00, q11, q01r, q01i;

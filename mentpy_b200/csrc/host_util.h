@@ -24,3 +24,7 @@ void mbqc_jit_free(mbqc_plan* plan);
 int mbqc_jit_try_launch(const mbqc::SvBatchParams& p, const mbqc_plan* plan, int out_mode, cudaStream_t st,
                         int64_t call_batch, int* rc);
 int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const mbqc::SvBatchParams& p, cudaStream_t st, int* rc);
+namespace mbqc {
+struct DmBatchParams;  // dm_batch.cuh
+}
+int mbqc_jit_dm_try_launch(const mbqc_plan* plan, const mbqc::DmBatchParams& p, cudaStream_t st, int* rc);

@@ -686,6 +686,10 @@ static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int6
     if (d_expect) CUDA_TRY(cudaMemsetAsync(d_expect, 0, sizeof(double) * (size_t)batch * plan->tab.n_steps, (cudaStream_t)stream));
     // w <= 5: one lane per row of rho, registers + shuffles; w = 6: rho in shared memory
     const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
+    if (!has_z && !force) {  // pattern-specialised kernel on the compressed state (dm_jit_src.inc)
+        int jrc = MBQC_OK;
+        if (mbqc_jit_dm_try_launch(plan, p, (cudaStream_t)stream, &jrc)) return jrc;
+    }
     if (w <= 5 && (has_z || !(force && !strcmp(force, "smem")))) {
         const int n = 1 << w;
         const int threads = dm_reg_threads(batch, n);
@@ -935,6 +939,38 @@ int mbqc_psr_grad_batch(const mbqc_plan* plan, const double* d_angles, int64_t a
     p.grad = d_grad;
     p.cost = d_cost;
     return launch_psr_grad(plan, p, (cudaStream_t)stream);
+}
+
+int mbqc_psr_grad_batch_push(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                             const void* d_inputs, int32_t input_mode, int64_t batch,
+                             const void* d_target, double shift, void* const* d_results, int32_t n_results,
+                             int64_t first_row, double* d_cost, int32_t* d_status, void* stream) {
+    if (!d_results || n_results < 1 || n_results > 8) return fail(MBQC_E_ARG, "n_results %d not in [1, 8]", n_results);
+    for (int d = 0; d < n_results; ++d)
+        if (!d_results[d]) return fail(MBQC_E_ARG, "d_results[%d] is NULL", d);
+    if (first_row < 0) return fail(MBQC_E_ARG, "first_row < 0");
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_results[0]);
+    if (rc) return rc;
+    if ((rc = check_grad_plan(plan, d_target, shift))) return rc;
+    const int T = plan->tab.n_angles;
+    if (batch == 0 || T == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, nullptr, d_status);
+    p.target = (const double2*)d_target;
+    p.shift = shift;
+    p.cost = d_cost;
+    p.push_n = n_results;
+    p.push_row0 = first_row;
+    for (int d = 0; d < n_results; ++d) p.push_dst[d] = (double*)d_results[d];
+    if (mbqc_jit_grad_try_launch(plan, p, (cudaStream_t)stream, &rc)) return rc;  // stores from the kernel itself
+    // general kernels: local rows first, then one peer copy per replica (copy engines over NVLink)
+    p.push_n = 0;
+    p.grad = (double*)d_results[0] + first_row * T;
+    if ((rc = launch_psr_grad(plan, p, (cudaStream_t)stream))) return rc;
+    for (int d = 1; d < n_results; ++d)
+        CUDA_TRY(cudaMemcpyAsync((double*)d_results[d] + first_row * T, p.grad, sizeof(double) * (size_t)batch * T,
+                                 cudaMemcpyDefault, (cudaStream_t)stream));
+    return MBQC_OK;
 }
 
 int64_t mbqc_psr_grad_dataset_workspace_bytes(const mbqc_plan* plan, int64_t n_vectors, int64_t n_data) {

@@ -23,6 +23,7 @@
 #include <string>
 #include <vector>
 
+#include "dm_jit_gen.h"
 #include "host_util.h"
 #include "sv_lean.cuh"
 
@@ -36,7 +37,13 @@ const char* kJitSource =
 const char* kJitGradSource =
 #include "sv_jit_grad_src.inc"
     ;
-constexpr int kKindRun = 0, kKindGrad = 1;
+const char* kJitDmSource =
+#include "dm_jit_src.inc"
+    ;
+constexpr int kKindRun = 0, kKindGrad = 1, kKindDm = 2;
+const char* kind_source(int kind) { return kind == kKindGrad ? kJitGradSource : (kind == kKindDm ? kJitDmSource : kJitSource); }
+const char* kind_entry(int kind) { return kind == kKindGrad ? "mbqc_jit_grad" : (kind == kKindDm ? "mbqc_jit_dm" : "mbqc_jit_sv"); }
+const char* kind_tag(int kind) { return kind == kKindGrad ? "grad" : (kind == kKindDm ? "dm" : "sv"); }
 
 // ---- NVRTC through dlopen --------------------------------------------------------------------
 struct Nvrtc {
@@ -117,6 +124,11 @@ void appendf(std::string& s, const char* fmt, ...) {
 
 // everything the kernel needs to know about the plan, as preprocessor / constexpr definitions
 std::string make_preamble(const mbqc_plan* plan, Variant v) {
+    if (v.kind == kKindDm) {
+        DmJitShape sh;
+        if (!dm_jit_shape(plan, sh)) return std::string();
+        return dm_jit_preamble(plan, sh);
+    }
     const LeanParams& lp = *plan->lean;
     const int w = plan->tab.window, M = lp.n_steps, np = 1 << (w - 1), n = 1 << w;
     int minblocks = (w <= 3) ? 1024 / v.cta : (w == 4 ? 640 / v.cta : 384 / v.cta);
@@ -126,6 +138,7 @@ std::string make_preamble(const mbqc_plan* plan, Variant v) {
             lp.n_full, lp.n_angles, lp.n_out, lp.n_in);
     appendf(s, "#define JCTA %d\n#define JMINBLOCKS %d\n#define JOUT %d\n#define JPHASE %s\n", v.cta, minblocks, v.out_mode,
             v.out_mode == MBQC_LEAN_OUT_DM ? "false" : "true");
+    if (v.kind == kKindGrad) appendf(s, "#define JPUSH %d\n", v.out_mode == 1 ? 1 : 0);  // out_mode 1: replicated result
     appendf(s, "#define JTRIG_INV %a\n#define JTRIG_C1 %a\n#define JTRIG_C2 %a\n", (double)MBQC_TRIG128_INV, (double)MBQC_TRIG128_C1,
             (double)MBQC_TRIG128_C2);
     std::string col = "constexpr unsigned kColOfs[JM] = {", sgn = "constexpr unsigned kSignMask[JM] = {",
@@ -345,7 +358,7 @@ bool compile_cubin(const std::string& source, std::vector<char>& cubin, std::str
 
 // kernel for (plan, variant) on the current device, or nullptr (reason in state().last_error)
 cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
-    const std::string source = make_preamble(plan, v) + (v.kind == kKindGrad ? kJitGradSource : kJitSource);
+    const std::string source = make_preamble(plan, v) + kind_source(v.kind);
     const uint64_t h = fnv1a(source);
     int device = 0;
     cudaGetDevice(&device);
@@ -357,7 +370,7 @@ cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
     std::vector<char> cubin;
     const std::string dir = cache_dir();
     char name[64];
-    snprintf(name, sizeof(name), "/%s_%016llx_nvrtc%d%d.cubin", v.kind == kKindGrad ? "grad" : "sv", (unsigned long long)h,
+    snprintf(name, sizeof(name), "/%s_%016llx_nvrtc%d%d.cubin", kind_tag(v.kind), (unsigned long long)h,
              nvrtc().major, nvrtc().minor);
     bool have = !dir.empty() && read_file(dir + name, cubin);
     if (have) ++st.from_disk;
@@ -374,7 +387,7 @@ cudaKernel_t build_kernel(const mbqc_plan* plan, Variant v) {
         if (!dir.empty()) write_file_atomic(dir + name, cubin);
     }
     cudaError_t e = cudaLibraryLoadData(&ld.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-    if (e == cudaSuccess) e = cudaLibraryGetKernel(&ld.kernel, ld.lib, v.kind == kKindGrad ? "mbqc_jit_grad" : "mbqc_jit_sv");
+    if (e == cudaSuccess) e = cudaLibraryGetKernel(&ld.kernel, ld.lib, kind_entry(v.kind));
     if (e != cudaSuccess) {
         cudaGetLastError();
         st.last_error = std::string("loading the specialised kernel: ") + cudaGetErrorString(e);
@@ -508,6 +521,9 @@ struct JitGradArgsHost {  // mirrors JitGradArgs of sv_jit_grad_src.inc
     long long stride, batch, data_count;
     int input_mode;
     double gr, gi, inv2s;
+    double* dst[8];
+    long long row0;
+    int n_dst;
 };
 
 // Parameter-shift gradient through the specialised kernel: same return convention as above.
@@ -520,8 +536,10 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
     if (mode == 0 || !plan->lean) return 0;
     if (mode == 1 && p.batch < min_batch) return 0;
     const int T = p.tab.n_angles;
-    Variant v{0, 128, kKindGrad};
-    const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
+    const bool push = p.push_n > 0;
+    Variant v{push ? 1 : 0, 128, kKindGrad};
+    size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
+    if (push) smem += (size_t)(v.cta + 1) * T * sizeof(double);  // gradient stage of the CTA
     if (smem > 200 * 1024 || T > 64) return 0;
     cudaKernel_t kern = get_kernel(plan, v);
     if (!kern) return 0;
@@ -548,6 +566,9 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
     a.gr = -2.0 * sh * sh;  // cos s - 1 without cancellation (finite differences use s = 1e-5)
     a.gi = -sin(p.shift);
     a.inv2s = 1.0 / (2.0 * p.shift);
+    for (int d = 0; d < 8; ++d) a.dst[d] = d < p.push_n ? p.push_dst[d] : nullptr;
+    a.row0 = p.push_row0;
+    a.n_dst = p.push_n;
     void* args[] = {&a};
     const unsigned blocks = (unsigned)((p.batch + v.cta - 1) / v.cta);
     cudaError_t e = cudaLaunchKernel((const void*)kern, dim3(blocks), dim3(v.cta), args, smem, st);
@@ -556,6 +577,58 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
         return 1;
     }
     *rc = mbqc_after_launch("mbqc_jit_grad");
+    return 1;
+}
+
+struct DmJitArgsHost {  // mirrors DmJitArgs of dm_jit_src.inc
+    const double* angles;
+    long long stride;
+    const double2* inputs;
+    double2* out;
+    signed char* outcomes;
+    int* status;
+    long long batch;
+    int input_mode;
+};
+
+// Batched density-matrix run through the specialised kernel: same return convention as above.
+int mbqc_jit_dm_try_launch(const mbqc_plan* plan, const DmBatchParams& p, cudaStream_t st, int* rc) {
+    static const long long min_batch = [] {
+        const char* e = getenv("MBQC_JIT_DM_MIN_BATCH");
+        return (e && *e) ? atoll(e) : 1024ll;
+    }();
+    const int mode = jit_mode();
+    if (mode == 0 || p.expect) return 0;
+    if (mode == 1 && p.batch < min_batch) return 0;
+    DmJitShape sh;
+    if (!dm_jit_shape(plan, sh)) return 0;
+    cudaKernel_t kern = get_kernel(plan, Variant{0, sh.cta, kKindDm});
+    if (!kern) return 0;
+    if (sh.smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+        if (e != cudaSuccess) {
+            *rc = mbqc_cuda_error(e, "cudaFuncSetAttribute(mbqc_jit_dm)");
+            return 1;
+        }
+    }
+    DmJitArgsHost a;
+    a.angles = p.angles;
+    a.stride = p.stride;
+    a.inputs = p.inputs;
+    a.out = p.out;
+    a.outcomes = (signed char*)p.outcomes;
+    a.status = p.status;
+    a.batch = p.batch;
+    a.input_mode = p.input_mode;
+    void* args[] = {&a};
+    const int spb = sh.samples_per_cta();
+    const unsigned blocks = (unsigned)((p.batch + spb - 1) / spb);
+    cudaError_t e = cudaLaunchKernel((const void*)kern, dim3(blocks), dim3(sh.cta), args, sh.smem, st);
+    if (e != cudaSuccess) {
+        *rc = mbqc_cuda_error(e, "cudaLaunchKernel(mbqc_jit_dm)");
+        return 1;
+    }
+    *rc = mbqc_after_launch("mbqc_jit_dm");
     return 1;
 }
 
@@ -586,11 +659,19 @@ int32_t mbqc_jit_set_mode(int32_t mode) {
 // outside the specialised kernel's scope, or a negative MBQC_E_* code (message in mbqc_last_error).
 int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t cta) {
     if (!plan) return mbqc_set_error(MBQC_E_ARG, "plan is NULL");
-    if (!plan->lean) return 0;
-    // out_form: MBQC_OUT_SV / MBQC_OUT_DM -> mbqc_jit_sv; 100 -> the gradient kernel mbqc_jit_grad
+    // out_form: MBQC_OUT_SV / MBQC_OUT_DM -> mbqc_jit_sv; 100 -> the gradient kernel mbqc_jit_grad;
+    // 200 -> the density-matrix kernel mbqc_jit_dm
     Variant v{out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : MBQC_LEAN_OUT_DIRECT, cta == 64 ? 64 : 128};
     if (out_form == 100) v = Variant{0, 128, kKindGrad};
-    const std::string source = make_preamble(plan, v) + (v.kind == kKindGrad ? kJitGradSource : kJitSource);
+    if (out_form == 101) v = Variant{1, 128, kKindGrad};  // replicated-result form of the gradient kernel
+    if (out_form == 200) {
+        DmJitShape sh;
+        if (!dm_jit_shape(plan, sh)) return 0;
+        v = Variant{0, sh.cta, kKindDm};
+    } else if (!plan->lean) {
+        return 0;
+    }
+    const std::string source = make_preamble(plan, v) + kind_source(v.kind);
     std::vector<char> cubin;
     std::string err;
     if (!compile_cubin(source, cubin, err)) return mbqc_set_error(MBQC_E_UNSUPPORTED, err.c_str());

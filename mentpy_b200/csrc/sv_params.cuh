@@ -23,6 +23,12 @@ struct SvBatchParams {
     // data-set mode of the gradient kernels (data_count = S > 0): sample b = p * S + s uses angle
     // row p, input state s and target state s; 0 = every sample has its own row / input, one target
     int64_t data_count;
+    // replicated result (mbqc_psr_grad_batch_push): the rows of this launch are rows push_row0..
+    // of a [total][T] result held by push_n GPUs; push_dst[0] is the local copy, the others are
+    // peer-mapped.  push_n = 0: plain `grad` output.
+    double* push_dst[8];
+    int64_t push_row0;
+    int32_t push_n;
 };
 
 // (angle row, data item) of sample b

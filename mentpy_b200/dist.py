@@ -76,10 +76,134 @@ def run_batch_distributed(simulator, angles, group=None, gather: bool = True, **
     return gather_slices(local, B, group)
 
 
-def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, group=None, gather: bool = True):
-    """BASELINE config 4: parameter-shift gradients of B angle vectors split across the GPUs."""
+class ReplicatedResult:
+    """A [rows, cols] float64 result that every GPU of the node holds a full copy of, filled by
+    kernels that store their rows into ALL copies (peer-mapped memory, CUDA IPC over NVLink) --
+    the gather is part of the producing launch instead of a collective after it.  One process per
+    GPU; buffers come from plain cudaMalloc (IPC-exportable), handles travel once through
+    torch.distributed's object all_gather.  `barrier()` is the stream-ordered flag barrier that
+    makes the remote rows visible (mbqc_peer_barrier).  Two copies alternate (`next_copy`), so ONE
+    barrier per producing call is enough: a rank can only start overwriting copy c two calls later,
+    after a barrier that every rank entered behind its own reads of copy c."""
+
+    _FLAG_BYTES = 256
+
+    def __init__(self, rows: int, cols: int, group=None, device=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self._lib, self.lib, self.torch = _lib, _lib.load(), torch
+        self.group = group
+        self.rank, self.world = _rank_world(group)
+        if self.world > 8:
+            raise ValueError("ReplicatedResult covers one node (<= 8 GPUs)")
+        self.rows, self.cols = int(rows), int(cols)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nbytes = ((self.rows * self.cols * 8 + 255) // 256) * 256
+        self.epoch = 0
+        self._imported = []
+        with torch.cuda.device(self.device):
+            p = C.c_void_p()
+            _lib.check(self.lib.mbqc_device_alloc(2 * self.nbytes + self._FLAG_BYTES, C.byref(p)))
+            self._own = p.value
+            flags = self.as_tensor(self._own + 2 * self.nbytes, (self._FLAG_BYTES // 8,), torch.int64)
+            flags.zero_()
+            torch.cuda.synchronize(self.device)
+            self.ptrs = [self._own]
+            if self.world > 1:
+                h = (C.c_char * 64)()
+                _lib.check(self.lib.mbqc_ipc_export(C.c_void_p(self._own), h))
+                gathered = [None] * self.world
+                dist.all_gather_object(gathered, bytes(h), group=group)
+                self.ptrs = []
+                for r, hb in enumerate(gathered):
+                    if r == self.rank:
+                        self.ptrs.append(self._own)
+                        continue
+                    q = C.c_void_p()
+                    _lib.check(self.lib.mbqc_ipc_import((C.c_char * 64).from_buffer_copy(hb), C.byref(q)))
+                    self._imported.append(q.value)
+                    self.ptrs.append(q.value)
+                dist.barrier(group=group)  # every flag array is zeroed and mapped before the first use
+        self.copy = 0  # the copy the last producing call filled
+        self.tensors = [self.as_tensor(self._own + c * self.nbytes, (self.rows, self.cols), torch.float64) for c in (0, 1)]
+
+    @property
+    def tensor(self):
+        return self.tensors[self.copy]
+
+    def next_copy(self) -> int:
+        self.copy ^= 1
+        return self.copy
+
+    def as_tensor(self, ptr: int, shape, dtype):
+        """torch view of raw device memory (no ownership)."""
+        torch = self.torch
+        typestr = {torch.float64: "<f8", torch.int64: "<i8"}[dtype]
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr,
+                                        "data": (int(ptr), False), "version": 2, "strides": None}
+
+        return torch.as_tensor(_Raw(), device=self.device)
+
+    def destinations(self):
+        """(ctypes array of result pointers with the local copy first, count) for *_push entry points."""
+        import ctypes as C
+
+        off = self.copy * self.nbytes
+        order = [self.ptrs[self.rank] + off] + [q + off for r, q in enumerate(self.ptrs) if r != self.rank]
+        return (C.c_void_p * len(order))(*order), len(order)
+
+    def barrier(self, stream=None):
+        import ctypes as C
+
+        if self.world == 1:
+            return
+        torch = self.torch
+        self.epoch += 1
+        flags = (C.c_void_p * self.world)(*[q + 2 * self.nbytes for q in self.ptrs])
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._lib.check(self.lib.mbqc_peer_barrier(flags, self.world, self.rank, self.epoch, st))
+
+    def release(self):
+        import ctypes as C
+
+        if getattr(self, "_own", None) is None:
+            return
+        self.torch.cuda.synchronize(self.device)
+        for q in self._imported:
+            self.lib.mbqc_ipc_close(C.c_void_p(q))
+        self._imported = []
+        self.lib.mbqc_device_free(C.c_void_p(self._own))
+        self._own, self.tensors = None, [None, None]
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, group=None, gather: bool = True,
+                             fused: bool = True, result: Optional["ReplicatedResult"] = None):
+    """BASELINE config 4: parameter-shift gradients of B angle vectors split across the GPUs
+    (gradients/_parameter_shift.py:9-25 per vector).
+
+    fused=True (default): the gradient kernel of every rank stores its rows straight into all
+    ranks' copies of the [B,T] result over NVLink peer memory (`ReplicatedResult`), followed by one
+    flag barrier -- no collective call.  Pass `result` to reuse the replicated buffer across calls
+    (it is otherwise created, and cached on the simulator, per (B, T)); the returned tensor is a
+    view of one of its two alternating copies, valid until the call after the next one.  fused=False: local kernel + one NCCL all_gather."""
+    import ctypes as C
+
     import torch
 
+    from . import _lib
     from .gradients import psr_gradient_batched
 
     rank, world = _rank_world(group)
@@ -89,10 +213,40 @@ def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, grou
     part = angles[lo:hi]
     if not isinstance(part, torch.Tensor):
         part = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float64))
-    local = psr_gradient_batched(sim, part.to(sim._dev()), target, shift=shift)
-    if not gather:
-        return local, (lo, hi)
-    return gather_slices(local, B, group)
+    if not gather or not fused or world == 1:
+        local = psr_gradient_batched(sim, part.to(sim._dev()), target, shift=shift)
+        if not gather:
+            return local, (lo, hi)
+        return gather_slices(local, B, group)
+    dev = sim._dev()
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        a, _ = sim._stage_angles(part.to(dev), dev)
+        batch, T = a.shape
+        if result is None:
+            cache = sim.__dict__.setdefault("_replicated_results", {})
+            result = cache.get((B, T, id(group)))
+            if result is None:
+                for old in cache.values():
+                    old.release()
+                cache.clear()
+                result = cache[(B, T, id(group))] = ReplicatedResult(B, T, group=group, device=dev)
+        if (result.rows, result.cols) != (B, T):
+            raise ValueError("result buffer has the wrong shape")
+        inp, mode = sim._stage_inputs(None, batch, dev)
+        dplan = sim._full_plan()
+        tgt = torch.as_tensor(np.ascontiguousarray(target, dtype=np.complex128)).to(dev) \
+            if not isinstance(target, torch.Tensor) else target.to(device=dev, dtype=torch.complex128).contiguous()
+        status = torch.empty(max(batch, 1), dtype=torch.int32, device=dev)
+        result.next_copy()
+        dst, n = result.destinations()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mbqc_psr_grad_batch_push(dplan.handle, a.data_ptr(), (a.stride(0) if batch > 1 else max(T, 1)),
+                                                None if inp is None else inp.data_ptr(), mode, batch, tgt.data_ptr(),
+                                                C.c_double(shift), dst, n, lo, None, status.data_ptr(), st))
+        result.barrier(st)
+        sim.last_status = status[:batch]
+        return result.tensor
 
 
 def sample_batch_distributed(simulator, angles, group=None, seed: Optional[int] = None, sample_offset: int = 0,

@@ -45,8 +45,16 @@ if __name__ == "__main__":
         B = int(sys.argv[2]); p = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
         print(shape, B, p, time_kernel(shape, B, p, reps=20))
         sys.exit(0)
+    import json
+    lib = _lib.load()
     for shape, window in (([3, 8], None), ([2, 6], None), ([4, 5], None), ([5, 4], None)):
-        for p in (0.0, 0.05):
+        for p in (0.0, 0.01):
             for B in (1024, 4096, 16384, 65536, 262144):
-                us = time_kernel(shape, B, p, window=window)
-                print(f"grid{shape} p={p} B={B:7d}  {us:9.2f} us/launch  {B/us:8.2f} M evals/s", flush=True)
+                row = {"pattern": f"grid_cluster{tuple(shape)} DM", "p": p, "batch": B}
+                for mode, name in ((0, "dm_reg_kernel"), (2, "mbqc_jit_dm")):  # general vs specialised kernel
+                    lib.mbqc_jit_set_mode(mode)
+                    us = time_kernel(shape, B, p, window=window)
+                    row[name + "_us"] = round(us, 2)
+                    row[name + "_Mevals_s"] = round(B / us, 2)
+                row["speedup"] = round(row["dm_reg_kernel_us"] / row["mbqc_jit_dm_us"], 2)
+                print(json.dumps(row), flush=True)

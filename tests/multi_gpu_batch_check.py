@@ -25,9 +25,25 @@ def main():
     ref = ps.run_batch(torch.from_numpy(ang).cuda())
     ok = torch.equal(full, ref)
     tgt = np.full(16, 0.25)
-    g = psr_gradient_distributed(ps, ang[:515], tgt)
     gref = psr_gradient_batched(ps, torch.from_numpy(ang[:515]).cuda(), tgt)
+    g = psr_gradient_distributed(ps, ang[:515], tgt, fused=False)  # local kernel + NCCL all_gather
     ok = ok and torch.equal(g, gref)
+    # replicated result over NVLink peer memory: general kernels + peer copies (small batch), then
+    # the specialised kernel storing into every GPU's copy itself; repeated calls alternate copies
+    from mentpy_b200 import _lib
+    lib = _lib.load()
+    for mode in (0, 2, 2, 2):
+        prev = lib.mbqc_jit_set_mode(mode)
+        g = psr_gradient_distributed(ps, ang[:515], tgt)
+        ok = ok and bool((g - gref).abs().max() < 1e-12)
+        lib.mbqc_jit_set_mode(prev)
+    gbig_ref = psr_gradient_batched(ps, torch.from_numpy(ang).cuda(), tgt)
+    lib.mbqc_jit_set_mode(2)
+    for _ in range(3):
+        gbig = psr_gradient_distributed(ps, ang, tgt)  # ragged split: 2050 + 2049 rows
+        ok = ok and bool((gbig - gbig_ref).abs().max() < 1e-12)
+    lib.mbqc_jit_set_mode(1)
+    ok = ok and "failures=0" in lib.mbqc_jit_info().decode()
     # sampled shots: the Philox stream is indexed by the global shot number -> identical records
     pss = mb.PatternSimulator(gs, backend="cuda-sv", force0=False, seed=9)
     shots = sample_batch_distributed(pss, ang, seed=9, sample_offset=100)

@@ -280,3 +280,123 @@ def test_async_host_calls_with_per_call_input_state_and_dropped_handles():
 
     gc.collect()
     assert ps.run_batch_async(ang).result().shape == (3000, 4)
+
+
+# ---- specialised density-matrix kernel (dm_jit_src.inc) -------------------------------------------
+DM_CASES = [c for c in load_golden("sim_cases.json")["cases"] if c["backend"] == "numpy-dm" and 2 <= c["window_size"] <= 5
+            and not any(str(p) == "Z" for _, p in c["fixed"].values())]
+
+
+def _jit_counts(lib):
+    info = lib.mbqc_jit_info().decode()
+    return {k: int(v) for k, v in (kv.split("=") for kv in info.split() if kv.split("=")[0] in ("compiled", "from_disk", "failures"))}
+
+
+@pytest.mark.parametrize("case", DM_CASES, ids=[f"{c['spec'][0]}{c['spec'][1]}-w{c['window_size']}-s{c['seed']}" for c in DM_CASES])
+def test_specialised_dm_kernel_reproduces_reference_goldens(case, jit_forced):
+    from conftest import dm_distance
+
+    gs = _circuit(case)
+    inp = from_cplx(case["input_state"])
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=case["window_size"])
+    ang = np.asarray(case["angles"])
+    B = 37  # ragged; row 5 carries the golden angles
+    rows = np.random.default_rng(case["seed"]).uniform(0, 2 * np.pi, (B, len(ang)))
+    rows[5] = ang
+    got, oc = ps.run_batch(rows, return_outcomes=True)
+    assert "failures=0" in _launched(jit_forced), _launched(jit_forced)
+    assert dm_distance(got[5], from_cplx(case["output"])) < 1e-10
+    jit_forced.mbqc_jit_set_mode(0)
+    ref, roc = ps.run_batch(rows, return_outcomes=True)
+    jit_forced.mbqc_jit_set_mode(2)
+    assert np.abs(got - ref).max() < 1e-12
+    assert np.array_equal(oc, roc)
+
+
+@pytest.mark.parametrize("spec,w", [(("grid_cluster", [3, 8]), None), (("grid_cluster", [2, 5]), 5), (("grid_cluster", [4, 5]), None),
+                                    (("linear_cluster", [6]), 3), (("linear_cluster", [7]), 2), (("linear_cluster", [5]), None),
+                                    (("many_wires", [[3, 4, 2]]), None), (("grid_cluster", [2, 6]), None)])
+@pytest.mark.parametrize("noise", [None, ("depolarizing", {"p": 0.01}), ("amplitude_damping", {"p": 0.2}),
+                                   ("generalized_amplitude_damping", {"p": 0.1, "p_gad": 0.3})])
+def test_specialised_dm_kernel_matches_oracle_and_general_kernel(spec, w, noise, jit_forced):
+    from conftest import dm_distance
+    from scipy.stats import unitary_group
+
+    name, args = spec
+    gs = getattr(mb.templates, name)(*args)
+    pat = PatternData.from_circuit(gs)
+    rng = np.random.default_rng(13)
+    B, T = 261, len(gs.trainable_nodes)  # ragged: not a multiple of the samples per CTA
+    ang = rng.uniform(0, 2 * np.pi, (B, T))
+    kw = {} if w is None else {"window_size": w}
+    nkw = {} if noise is None else {"circuit_noise": noise[0], **noise[1]}
+    k = len(gs.input_nodes)
+    inp = unitary_group.rvs(2**k, random_state=4)[:, 0] if k else None
+    ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", **kw, **nkw)
+    got, oc = ps.run_batch(ang, return_outcomes=True)
+    after = _jit_counts(jit_forced)
+    assert after["failures"] == 0, _launched(jit_forced)
+    okw = None
+    if noise is not None:
+        okw = {"p": noise[1]["p"]}
+        if "p_gad" in noise[1]:
+            okw["p_gad"] = noise[1]["p_gad"]
+    sub = slice(0, 9)
+    want, woc = matrix_free.run_dm_batch(pat, ang[sub], window_size=(w or 1), input_state=inp, return_outcomes=True,
+                                         **({} if noise is None else {"noise": noise[0], "noise_kwargs": okw}))
+    assert dm_distance(got[sub], want) < 1e-10
+    assert np.array_equal(oc[sub], woc)
+    assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
+    assert np.allclose(got, np.conj(np.swapaxes(got, 1, 2)), atol=1e-12)
+    jit_forced.mbqc_jit_set_mode(0)
+    ref, roc = ps.run_batch(ang, return_outcomes=True)
+    jit_forced.mbqc_jit_set_mode(2)
+    assert np.abs(got - ref).max() < 1e-12
+    assert np.array_equal(oc, roc)
+
+
+def test_specialised_dm_kernel_outcome1_rule(jit_forced):
+    """np_simulator_dm.py:335-338: a step with prob0 < 1e-4 takes outcome 1.  The specialised kernel
+    detects the step lazily and repeats the warp through its exact path; the rows next to the
+    affected one must be untouched."""
+    from conftest import dm_distance
+
+    d = load_golden("dm_outcome_quirk.json")
+    name, args, kwargs = d["spec"]
+    gs = getattr(mb.templates, name)(*args, **kwargs)
+    ps = mb.PatternSimulator(gs, input_state=from_cplx(d["input_state"]), backend="cuda-dm", window_size=d["window_size"])
+    T = len(gs.trainable_nodes)
+    rng = np.random.default_rng(3)
+    seen1 = False
+    for run in d["runs"]:
+        rows = rng.uniform(0, 2 * np.pi, (70, T))
+        rows[33] = np.asarray(run["angles"])
+        got, oc = ps.run_batch(rows, return_outcomes=True)
+        assert dm_distance(got[33], from_cplx(run["output"])) < 1e-10
+        want_oc = [run["outcomes"][str(n)] for n in ps.schedule_measure] if isinstance(run["outcomes"], dict) else None
+        if want_oc is not None:
+            assert list(oc[33]) == want_oc
+            seen1 |= 1 in want_oc
+        jit_forced.mbqc_jit_set_mode(0)
+        ref, roc = ps.run_batch(rows, return_outcomes=True)
+        jit_forced.mbqc_jit_set_mode(2)
+        assert np.abs(got - ref).max() < 1e-12 and np.array_equal(oc, roc)
+    assert seen1, "the golden file no longer exercises outcome 1"
+    assert "failures=0" in _launched(jit_forced)
+
+
+def test_specialised_dm_kernel_full_size_c3(jit_forced):
+    """BASELINE configs[2] at full size (4,096 angle sets, grid_cluster(3,8), depolarizing 0.01):
+    specialised vs general kernel on every row, trace / hermiticity / positivity invariants."""
+    gs = mb.templates.grid_cluster(3, 8)
+    ang = torch.from_numpy(np.random.default_rng(1).uniform(0, 2 * np.pi, (4096, len(gs.trainable_nodes)))).cuda()
+    for nkw in ({}, {"circuit_noise": "depolarizing", "p": 0.01}):
+        ps = mb.PatternSimulator(gs, backend="cuda-dm", **nkw)
+        got = ps.run_batch(ang).cpu().numpy()
+        jit_forced.mbqc_jit_set_mode(0)
+        ref = ps.run_batch(ang).cpu().numpy()
+        jit_forced.mbqc_jit_set_mode(2)
+        assert np.abs(got - ref).max() < 1e-12
+        assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
+        assert np.linalg.eigvalsh(got[::64]).min() > -1e-12
+    assert "failures=0" in _launched(jit_forced)

@@ -56,3 +56,23 @@ def test_host_only_plan_cannot_run():
     assert lib.mbqc_plan_window(dp.handle) == 3 and lib.mbqc_plan_num_steps(dp.handle) == 10
     rc = lib.mbqc_run_batch_sv(dp.handle, C.c_void_p(16), 10, None, _lib.INPUT_PLUS, 4, C.c_void_p(16), _lib.OUT_SV, None, None)
     assert rc == _lib.MBQC_E_ARG and b"host-only" in lib.mbqc_last_error()
+
+
+DM_CASES = [c for c in load_golden("sim_cases.json")["cases"] if c["backend"] == "numpy-dm"]
+
+
+@pytest.mark.parametrize("case", DM_CASES, ids=[f"{c['spec'][0]}{c['spec'][1]}-w{c['window_size']}-s{c['seed']}" for c in DM_CASES])
+def test_specialised_dm_kernel_compiles_for_golden_patterns(case):
+    """dm_jit_src.inc + the preamble of dm_jit_gen.h (layout schedule, sign tables) compile for
+    every golden density-matrix pattern in scope: window 2..5, no plane-Z node."""
+    if not _nvrtc_available():
+        pytest.skip("libnvrtc not found: " + _lib.load().mbqc_jit_info().decode())
+    lowered = plan_mod.lower(_circuit(case), window_size=case["window_size"], mixed=True)
+    noise = plan_mod.noise_from_kraus(plan_mod.kraus_set("depolarizing", p=0.01)) if case["seed"] % 2 else None
+    dp = plan_mod.DevicePlan(lowered, noise=noise, host_only=True)
+    size = dp.jit_compile_check(out_form=200)
+    has_z = any(st.plane == _lib.PLANE_Z for st in lowered.steps)
+    if 2 <= lowered.window <= 5 and not has_z:
+        assert size > 1000
+    else:
+        assert size == 0
