@@ -38,6 +38,7 @@ extern "C" {
 #define MBQC_PLANE_XZ 1
 #define MBQC_PLANE_YZ 2
 #define MBQC_PLANE_Z 3 /* DM path, expectation mode only: trace the qubit out, record prob1 */
+#define MBQC_PLANE_XYZ 4 /* DM path, fixed angles only (ment.py:239-251): M = fixed_cos X + fixed_sin Y + fixed_z Z */
 
 #define MBQC_STEP_APPEND 1u /* a |+> qubit enters the freed slot and is CZ'ed with nbr_mask */
 
@@ -68,6 +69,7 @@ typedef struct mbqc_step {
     double fixed_cos;   /* cos/sin of the fixed angle, evaluated on the host exactly as the */
     double fixed_sin;   /*   reference does (np.cos/np.sin, or exact 1,0 / 0,1 for planes X / Y) */
     uint64_t nbr_mask;  /* slots of the appended qubit's in-window neighbours */
+    double fixed_z;     /* MBQC_PLANE_XYZ: Z component sin(t2); (fixed_cos, fixed_sin) = cos(t2) (cos t1, sin t1) */
 } mbqc_step;
 
 /* Single-qubit channel in block form on (rho00, rho01, rho10, rho11) of the affected qubit:

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MBQC_LIB_PATH", os.path.join(_HERE, "_mbqc_b200.so"))  # override: kernel experiments
 
 MBQC_OK, MBQC_E_ARG, MBQC_E_CUDA, MBQC_E_UNSUPPORTED = 0, -1, -2, -3
-PLANE_XY, PLANE_XZ, PLANE_YZ, PLANE_Z = 0, 1, 2, 3
+PLANE_XY, PLANE_XZ, PLANE_YZ, PLANE_Z, PLANE_XYZ = 0, 1, 2, 3, 4
 STEP_APPEND = 1
 STATUS_BAD_NORM, STATUS_OUTCOME1 = 1, 2
 OUT_SV, OUT_DM = 0, 1
@@ -23,7 +23,7 @@ MAX_IO = 16
 class Step(C.Structure):
     _fields_ = [("slot", C.c_int32), ("angle_idx", C.c_int32), ("plane", C.c_int32),
                 ("flags", C.c_uint32), ("fixed_cos", C.c_double), ("fixed_sin", C.c_double),
-                ("nbr_mask", C.c_uint64)]
+                ("nbr_mask", C.c_uint64), ("fixed_z", C.c_double)]
 
 
 class Optimizer(C.Structure):

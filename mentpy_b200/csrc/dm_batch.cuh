@@ -24,9 +24,11 @@ struct MeasCoef {
 };
 
 // entries of the outcome-0 projector P of plane/angle with the (trace-preserving) channel folded in
-__device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, const PlanTables& t) {
+__device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, const PlanTables& t, double z = 0.0) {
     double p00, p11, p10r, p10i;
-    if (plane == MBQC_PLANE_XY) {
+    if (plane == MBQC_PLANE_XYZ) {  // axis (c, s, z) given directly (fixed angles)
+        p00 = 0.5 * (1.0 + z); p11 = 0.5 * (1.0 - z); p10r = 0.5 * c; p10i = 0.5 * s;
+    } else if (plane == MBQC_PLANE_XY) {
         p00 = 0.5; p11 = 0.5; p10r = 0.5 * c; p10i = 0.5 * s;
     } else if (plane == MBQC_PLANE_XZ) {
         p00 = 0.5 * (1.0 + s); p11 = 0.5 * (1.0 - s); p10r = 0.5 * c; p10i = 0.0;
@@ -155,7 +157,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
         const StepDev st = p.steps[m];
         const int sl = st.slot;
         const uint32_t cbit = 1u << sl, rbit = cbit << w;
-        const MeasCoef q = meas_coef(st.plane, c, s, t);
+        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz);
         double2 sg[kDmMaxGroupsPerThread], sf[kDmMaxGroupsPerThread];
         double tr0 = 0.0, trf = 0.0;
         if (live) {

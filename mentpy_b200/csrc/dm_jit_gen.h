@@ -32,13 +32,15 @@ inline void dm_appendf(std::string& s, const char* fmt, ...) {
 
 // Patterns the specialised kernel covers: the reference schedule (slot w-1-(m mod w) at step m),
 // window 2..5, projective planes only (plane Z / expectation mode stays on dm_reg_kernel).
-inline bool dm_jit_shape(const mbqc_plan* plan, DmJitShape& sh) {
+inline bool dm_jit_shape(const mbqc_plan* plan, DmJitShape& sh, int lb_request = 0) {
     const PlanTables& t = plan->tab;
     const int w = t.window, M = t.n_steps;
     if (w < 2 || w > 5 || M < 1 || !plan->reg_periodic) return false;
     for (int m = 0; m < M; ++m)
         if (plan->h_steps[m].plane == MBQC_PLANE_Z) return false;
+    // lanes per sample = 4^(w-1-lb) <= 32; registers per lane = 2 * 4^lb doubles
     sh.lb = (w == 5) ? 2 : 1;
+    if (lb_request >= 1 && lb_request <= 2 && w - 1 - lb_request >= 0 && w - 1 - lb_request <= 2) sh.lb = lb_request;
     sh.nlb = w - 1 - sh.lb;
     sh.cta = 64;
     const int nreg = 1 << (2 * sh.lb);
@@ -140,14 +142,16 @@ inline std::string dm_jit_preamble(const mbqc_plan* plan, const DmJitShape& sh) 
     int_table("constexpr int kFinalBit[]", finalbit);
     std::vector<int> aidx(M), plane(M), isrc(1 << w), orow(1 << t.n_out), oneg(1 << t.n_out);
     std::string fc = "__constant__ double kFixedCosRt[JM] = {", fs = "__constant__ double kFixedSinRt[JM] = {";
+    std::string fz = "__constant__ double kFixedZRt[JM] = {";
     for (int m = 0; m < M; ++m) {
         const StepDev& d = plan->h_steps[m];
         aidx[m] = d.angle_idx;
         plane[m] = d.plane;
         dm_appendf(fc, "%a,", d.angle_idx >= 0 ? 1.0 : d.fc);
         dm_appendf(fs, "%a,", d.angle_idx >= 0 ? 0.0 : d.fs);
+        dm_appendf(fz, "%a,", d.fz);
     }
-    s += fc + "};\n" + fs + "};\n";
+    s += fc + "};\n" + fs + "};\n" + fz + "};\n";
     for (int i = 0; i < (1 << w); ++i) isrc[i] = t.init_src[i];
     for (int d = 0; d < (1 << t.n_out); ++d) {
         const uint64_t ri = output_state_index(t, (uint32_t)d);

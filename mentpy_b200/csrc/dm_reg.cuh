@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
                 u = philox_uniform(sp.seed, sp.sample_offset + (uint64_t)be, (uint32_t)m);
             }
         }
-        const MeasCoef q = meas_coef(st.plane, c, s, t);
+        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz);
         if (st.plane == MBQC_PLANE_Z) {
             // expectation mode (np_simulator_dm.py:327-344): record prob1 = tr(P1 E(rho)) / tr(rho)
             // (P1 = |1><1| seen through the channel: weights pop[2], pop[3] on rho00, rho11)

@@ -99,7 +99,8 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
         const mbqc_step& s = steps[m];
         if (s.slot < 0 || s.slot >= window) return fail(MBQC_E_ARG, "step %d: slot %d outside window", m, s.slot);
         if (s.angle_idx < -1 || s.angle_idx >= n_angles) return fail(MBQC_E_ARG, "step %d: angle_idx %d outside [ -1, %d)", m, s.angle_idx, n_angles);
-        if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_Z) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
+        if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_XYZ) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
+        if (s.plane == MBQC_PLANE_XYZ && s.angle_idx >= 0) return fail(MBQC_E_ARG, "step %d: plane XYZ takes two fixed angles (ment.py:239-251), not a column of the angle matrix", m);
         if (s.nbr_mask & ~wmask) return fail(MBQC_E_ARG, "step %d: nbr_mask outside window", m);
         if ((s.nbr_mask >> s.slot) & 1ull) return fail(MBQC_E_ARG, "step %d: nbr_mask contains the step's own slot", m);
     }
@@ -152,6 +153,8 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
         d.nbr_mask = (s.flags & MBQC_STEP_APPEND) ? s.nbr_mask : 0ull;
         d.flipmask = 0;
         d.pad = 0;
+        d.fz = s.fixed_z;
+        d.pad2 = 0.0;
         if (window <= MBQC_MAX_WINDOW_REG)
             for (uint32_t i = 0; i < (1u << window); ++i)
                 if (((i >> s.slot) & 1u) && parity64((uint64_t)i & d.nbr_mask)) d.flipmask |= 1u << i;

@@ -126,7 +126,7 @@ void appendf(std::string& s, const char* fmt, ...) {
 std::string make_preamble(const mbqc_plan* plan, Variant v) {
     if (v.kind == kKindDm) {
         DmJitShape sh;
-        if (!dm_jit_shape(plan, sh)) return std::string();
+        if (!dm_jit_shape(plan, sh, v.out_mode)) return std::string();
         return dm_jit_preamble(plan, sh);
     }
     const LeanParams& lp = *plan->lean;
@@ -600,9 +600,13 @@ int mbqc_jit_dm_try_launch(const mbqc_plan* plan, const DmBatchParams& p, cudaSt
     const int mode = jit_mode();
     if (mode == 0 || p.expect) return 0;
     if (mode == 1 && p.batch < min_batch) return 0;
+    static const int lb_env = [] {
+        const char* e = getenv("MBQC_DM_JIT_LB");  // register slots per lane (kernel work)
+        return (e && *e) ? atoi(e) : 0;
+    }();
     DmJitShape sh;
-    if (!dm_jit_shape(plan, sh)) return 0;
-    cudaKernel_t kern = get_kernel(plan, Variant{0, sh.cta, kKindDm});
+    if (!dm_jit_shape(plan, sh, lb_env)) return 0;
+    cudaKernel_t kern = get_kernel(plan, Variant{sh.lb, sh.cta, kKindDm});
     if (!kern) return 0;
     if (sh.smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
@@ -666,8 +670,8 @@ int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t 
     if (out_form == 101) v = Variant{1, 128, kKindGrad};  // replicated-result form of the gradient kernel
     if (out_form == 200) {
         DmJitShape sh;
-        if (!dm_jit_shape(plan, sh)) return 0;
-        v = Variant{0, sh.cta, kKindDm};
+        if (!dm_jit_shape(plan, sh, cta == 1 || cta == 2 ? cta : 0)) return 0;  // cta 1 / 2: register slots per lane
+        v = Variant{sh.lb, sh.cta, kKindDm};
     } else if (!plan->lean) {
         return 0;
     }

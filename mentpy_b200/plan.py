@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 
 _PLANE_CODE = {"XY": _lib.PLANE_XY, "X": _lib.PLANE_XY, "Y": _lib.PLANE_XY,
-               "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ, "Z": _lib.PLANE_Z}
+               "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ, "Z": _lib.PLANE_Z, "XYZ": _lib.PLANE_XYZ}
 
 
 @dataclass
@@ -37,6 +37,7 @@ class StepRecord:
     new_node: Optional[int]
     nbr_mask: int
     dropped_neighbours: List[int] = field(default_factory=list)
+    fixed_z: float = 0.0    # plane XYZ: Z component of the measurement axis
 
 
 @dataclass
@@ -172,8 +173,18 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
             raise NotImplementedError(f"Node {node}: plane {plane} is not supported on the CUDA path.")
         if plane == "Z" and window_size > _lib.MAX_WINDOW_REG:
             raise NotImplementedError(f"plane-Z measurements cover window_size <= {_lib.MAX_WINDOW_REG}")
+        fz = 0.0
         if plane == "Z":  # angle-free; only mode="expectation" runs it (np_simulator_dm.py:327-344)
             angle_idx, fixed, fc, fs = -1, None, 1.0, 0.0
+        elif plane == "XYZ":
+            # two angles, so only a fixed tuple works in the reference: a trainable XYZ node receives one
+            # float from the angle vector and ment.py:240-245 raises
+            if node in trainable or not isinstance(ment.angle, tuple):
+                got = float if node in trainable else type(ment.angle)
+                raise TypeError(f"Invalid argument type. Expected tuple but got {got}")
+            t1, t2 = ment.angle
+            angle_idx, fixed = -1, ment.angle
+            fc, fs, fz = float(np.cos(t1) * np.cos(t2)), float(np.sin(t1) * np.cos(t2)), float(np.sin(t2))
         elif node in trainable:
             angle_idx, fixed, fc, fs = trainable.index(node), None, 1.0, 0.0
         else:
@@ -194,7 +205,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
                     dropped.append(nb)  # already measured: the reference silently skips this CZ
             slot_of[new_node] = slot
         steps.append(StepRecord(node, slot, angle_idx, _PLANE_CODE[plane], fixed, fc, fs, append,
-                                new_node, mask, dropped))
+                                new_node, mask, dropped, fz))
 
     remaining = schedule[n_meas:]
     # np_simulator_dm.py:267-273 reorders to quantum_output_nodes; np_simulator_sv.py:286-290 leaves
@@ -345,6 +356,7 @@ class DevicePlan:
             arr[i].flags = _lib.STEP_APPEND if st.append else 0
             arr[i].fixed_cos, arr[i].fixed_sin = st.fixed_cos, st.fixed_sin
             arr[i].nbr_mask = st.nbr_mask
+            arr[i].fixed_z = st.fixed_z
         out_slot = plan.output_slot if output_slot is None else output_slot
         in_arr = (C.c_int32 * max(len(plan.input_slot), 1))(*plan.input_slot)
         cz_arr = (C.c_uint64 * plan.window)(*plan.init_cz_mask)

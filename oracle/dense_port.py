@@ -66,7 +66,12 @@ def dense_swap(i, j, n):
 
 
 def observable(plane, angle):
-    """2x2 measurement observable.  ment.py:228-251 (XYZ not on the path)."""
+    """2x2 measurement observable.  ment.py:228-251."""
+    if plane == "XYZ":
+        if not isinstance(angle, tuple):
+            raise TypeError(f"Invalid argument type. Expected tuple but got {type(angle)}")
+        a1, a2 = angle
+        return np.cos(a1) * np.cos(a2) * _X + np.sin(a1) * np.cos(a2) * _Y + np.sin(a2) * _Z
     if plane == "XY":
         return np.cos(angle) * _X + np.sin(angle) * _Y
     if plane in ("X", "Y", "Z"):

@@ -139,9 +139,45 @@ def sim_case(mp, spec, backend, seed, window_size=None, x_nodes=(), fixed=None, 
     return rec
 
 
+def xyz_cases(mp):
+    """2d. two-angle XYZ-plane measurements (ment.py:239-251) on the density-matrix backend: fixed
+    (t1, t2) tuples -- the only form the reference can run, a trainable XYZ node receives one float
+    and raises -- on measured inner nodes and on a measured output node."""
+    import warnings
+
+    cases = []
+    for spec, seed, w, nodes, haar in (
+            (("grid_cluster", [2, 4], {}), 40, None, {2: (0.3, 1.1), 5: (2.3, -0.4)}, False),
+            (("grid_cluster", [3, 4], {}), 41, None, {4: (1.0, 0.5), 6: (-2.0, 2.2)}, True),
+            (("linear_cluster", [6], {}), 42, 3, {1: (0.7, 0.2), 4: (4.0, 1.3)}, True),
+            (("grid_cluster", [2, 5], {}), 43, 5, {4: (0.4, 0.9), 3: (1.5, -1.0)}, True),
+            (("grid_cluster", [2, 4], {}), 44, 6, {1: (5.0, 0.6), 6: (0.1, -0.3)}, True)):
+        gs = build(mp, spec)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for v, ang in nodes.items():
+                gs[v] = mp.Ment(ang, "XYZ")
+        T = len(gs.trainable_nodes)
+        angles = np.random.default_rng(seed).uniform(0, 2 * np.pi, T)
+        inp = haar_state(len(gs.input_nodes), seed) if haar else None
+        kw = {} if w is None else {"window_size": w}
+        ps = mp.PatternSimulator(gs, input_state=inp, backend="numpy-dm", **kw)
+        out = ps.run(angles)
+        cases.append({"spec": spec, "seed": seed, "window_size": int(ps.window_size),
+                      "xyz": {str(k): list(v) for k, v in nodes.items()},
+                      "pattern": PatternData.from_circuit(gs).to_json(), "angles": angles.tolist(),
+                      "input_state": None if inp is None else cplx(inp), "output": cplx(out),
+                      "outcomes": {str(k): int(v) for k, v in ps.outcomes.items()}})
+    with open(os.path.join(GOLDEN, "dm_xyz_plane.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py (--only xyz)", "source": "bestquark/mentpy (unmodified)", "cases": cases}, f)
+
+
 def main():
     mp = import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "xyz":
+        xyz_cases(mp)
+        return
 
     # 1. structure tables (integer indexing must be bit-exact)
     structures = [structure_record(mp, s) for s in template_specs()]
@@ -226,6 +262,8 @@ def main():
                        "outcomes": {str(k): float(v) for k, v in ps.outcomes.items()}})
     with open(os.path.join(GOLDEN, "dm_z_expectation.json"), "w") as f:
         json.dump({"generator": "oracle/gen_golden.py", "source": "bestquark/mentpy (unmodified)", "cases": zcases}, f)
+
+    xyz_cases(mp)
 
     # 3. gradient + optimiser known answers: grid_cluster(4,5), cost 1 - <t|rho|t>
     gs = mp.templates.grid_cluster(4, 5)

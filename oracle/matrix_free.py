@@ -91,6 +91,8 @@ def _angles_for_step(pat, node, angles):
         return "XY", np.full(angles.shape[0], np.pi / 2)
     if plane == "Z":
         return "Z", np.zeros(angles.shape[0])
+    if plane == "XYZ":  # two fixed angles (ment.py:239-251): [B,2]
+        return plane, np.tile(np.asarray(fixed, dtype=float), (angles.shape[0], 1))
     return plane, np.full(angles.shape[0], fixed)
 
 
@@ -199,6 +201,10 @@ def apply_channel_at(rho, kraus, pos, n):
 
 def _projector(plane, th):
     """(I+M)/2 per batch element -> p00[B], p11[B], p10[B] (p01 = conj p10).  ment.py:228-260."""
+    if plane == "XYZ":  # M = cos t1 cos t2 X + sin t1 cos t2 Y + sin t2 Z
+        t1, t2 = th[:, 0], th[:, 1]
+        nz = np.sin(t2)
+        return (1 + nz) / 2, (1 - nz) / 2, 0.5 * np.cos(t2) * (np.cos(t1) + 1j * np.sin(t1))
     c, s = np.cos(th), np.sin(th)
     if plane == "XY":
         return np.full_like(c, 0.5), np.full_like(c, 0.5), 0.5 * (c + 1j * s)

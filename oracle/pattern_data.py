@@ -48,7 +48,8 @@ class PatternData:
     def from_json(d: dict) -> "PatternData":
         meas = {}
         for k, v in d["measurements"].items():
-            meas[int(k)] = None if v is None else (v[0], v[1])
+            # JSON turns the two-angle tuple of an XYZ node into a list: restore it
+            meas[int(k)] = None if v is None else (v[0], tuple(v[1]) if isinstance(v[1], list) else v[1])
         return PatternData(
             n_nodes=int(d["n_nodes"]),
             edges=[(int(a), int(b)) for a, b in d["edges"]],
@@ -69,7 +70,9 @@ class PatternData:
                 meas[int(node)] = None
             else:
                 ang = m.angle
-                meas[int(node)] = (str(m.plane), None if ang is None else float(ang))
+                # XYZ carries two angles (ment.py:239-251); every other plane one
+                meas[int(node)] = (str(m.plane), None if ang is None else
+                                   (tuple(float(x) for x in ang) if isinstance(ang, (tuple, list)) else float(ang)))
         qout = getattr(circ, "quantum_output_nodes", None)
         if qout is None:
             qout = [n for n in circ.output_nodes if meas.get(n) is None]

@@ -40,13 +40,22 @@ def time_kernel(shape, B, p=0.0, reps=200, window=None):
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 2:
+    if len(sys.argv) > 2 and sys.argv[1] != "quick":
         shape = [int(x) for x in sys.argv[1].split(",")]
         B = int(sys.argv[2]); p = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
         print(shape, B, p, time_kernel(shape, B, p, reps=20))
         sys.exit(0)
     import json
     lib = _lib.load()
+    if len(sys.argv) > 1 and sys.argv[1] == "quick":  # specialised kernel only (MBQC_DM_JIT_LB picks the layout)
+        lib.mbqc_jit_set_mode(2)
+        for shape in ([3, 8], [4, 5]):
+            for p in (0.0, 0.01):
+                for B in (1024, 4096, 16384, 65536, 262144):
+                    us = time_kernel(shape, B, p)
+                    print(json.dumps({"pattern": f"grid_cluster{tuple(shape)} DM", "p": p, "batch": B, "lb": os.environ.get("MBQC_DM_JIT_LB", "default"),
+                                      "mbqc_jit_dm_us": round(us, 2), "Mevals_s": round(B / us, 2)}), flush=True)
+        sys.exit(0)
     for shape, window in (([3, 8], None), ([2, 6], None), ([4, 5], None), ([5, 4], None)):
         for p in (0.0, 0.01):
             for B in (1024, 4096, 16384, 65536, 262144):

@@ -342,7 +342,7 @@ def test_specialised_dm_kernel_matches_oracle_and_general_kernel(spec, w, noise,
         if "p_gad" in noise[1]:
             okw["p_gad"] = noise[1]["p_gad"]
     sub = slice(0, 9)
-    want, woc = matrix_free.run_dm_batch(pat, ang[sub], window_size=(w or 1), input_state=inp, return_outcomes=True,
+    want, woc = matrix_free.run_dm_batch(pat, ang[sub], window_size=(w or 1), input_states=inp, return_outcomes=True,
                                          **({} if noise is None else {"noise": noise[0], "noise_kwargs": okw}))
     assert dm_distance(got[sub], want) < 1e-10
     assert np.array_equal(oc[sub], woc)

@@ -656,3 +656,51 @@ def test_plane_z_expectation_mode():
             assert np.abs(got - ref).max() < 1e-11 and np.abs(oc - roc).max() < 1e-11
     with pytest.raises(ValueError):
         mb.PatternSimulator(gs, backend="cuda-sv")        # SV path: XY planes only, like the reference
+
+
+def test_xyz_plane_matches_reference_golden():
+    """Fixed two-angle XYZ-plane nodes (ment.py:239-251) on every density-matrix kernel -- specialised
+    (dm_jit_src.inc), register (dm_reg.cuh), shared-memory (dm_batch.cuh, window 6) -- against
+    outputs recorded from the reference; with a channel against the oracle.  A trainable XYZ node
+    raises TypeError like the reference (one float arrives where a tuple is needed)."""
+    import warnings
+
+    from mentpy_b200 import _lib
+
+    lib = _lib.load()
+    for c in load_golden("dm_xyz_plane.json")["cases"]:
+        name, args, kwargs = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kwargs)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for v, ang2 in c["xyz"].items():
+                gs[int(v)] = mb.Ment(tuple(ang2), "XYZ")
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])
+        ang = np.asarray(c["angles"])
+        want = from_cplx(c["output"])
+        pat = PatternData.from_circuit(gs)
+        rows = np.random.default_rng(c["seed"]).uniform(0, 2 * np.pi, (19, len(ang)))
+        rows[7] = ang
+        for mode in (0, 2):
+            prev = lib.mbqc_jit_set_mode(mode)
+            try:
+                ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"])
+                got = ps.run(ang)
+                assert got.shape == want.shape and dm_distance(got, want) < 1e-10
+                assert {str(k): v for k, v in ps.outcomes.items()} == c["outcomes"]
+                batch = ps.run_batch(rows)
+                assert dm_distance(batch[7], want) < 1e-10
+                pn = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"],
+                                         circuit_noise="depolarizing", p=0.05)
+                ref = matrix_free.run_dm_batch(pat, rows[:5], input_states=None if inp is None else np.tile(inp, (5, 1)),
+                                               window_size=c["window_size"], noise="depolarizing", noise_kwargs={"p": 0.05})
+                assert dm_distance(pn.run_batch(rows[:5]), ref) < 1e-10
+            finally:
+                lib.mbqc_jit_set_mode(prev)
+    assert "failures=0" in lib.mbqc_jit_info().decode()
+    gs = mb.templates.grid_cluster(2, 4)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gs[2] = mb.Ment("XYZ")
+    with pytest.raises(TypeError, match="Expected tuple"):
+        mb.PatternSimulator(gs, backend="cuda-dm")

@@ -169,3 +169,20 @@ def test_plane_z_expectation_mode_oracle():
             assert abs(oc[0, m] - c["outcomes"][str(v)]) < 1e-12
     with pytest.raises(NotImplementedError):
         matrix_free.run_dm_batch(pat, np.asarray(c["angles"])[None], window_size=c["window_size"])
+
+
+def test_xyz_plane_oracles():
+    """Two-angle XYZ-plane measurements (ment.py:239-251) on the density-matrix path: both oracles
+    against outputs recorded from the reference (tests/golden/dm_xyz_plane.json)."""
+    for c in load_golden("dm_xyz_plane.json")["cases"]:
+        pat = PatternData.from_json(c["pattern"])
+        assert any(v is not None and v[0] == "XYZ" and isinstance(v[1], tuple) for v in pat.measurements.values())
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])
+        want = from_cplx(c["output"])
+        got = dense_port.run_dm(pat, np.asarray(c["angles"]), inp, window_size=c["window_size"])
+        assert got.shape == want.shape and np.abs(got - want).max() < 1e-12
+        rho, oc = matrix_free.run_dm_batch(pat, np.asarray(c["angles"])[None], input_states=None if inp is None else inp[None],
+                                           window_size=c["window_size"], return_outcomes=True)
+        assert np.abs(rho[0] - want).max() < 1e-12
+        sched_meas = [v for v in pat.measurement_order if v not in pat.quantum_output_nodes]
+        assert [int(x) for x in oc[0]] == [c["outcomes"][str(v)] for v in sched_meas]
