@@ -14,6 +14,7 @@ namespace mbqc {
 struct DmJitShape {
     int lb = 0, nlb = 0;      // register / lane slots
     int cta = 64, minblocks = 1;
+    int xbufs = 2, ost_ofs = 0, ost_extra = 0;  // exchange buffers per warp; place of the output block (double2 units)
     size_t smem = 0;          // dynamic shared memory of one CTA
     int lanes() const { return 1 << (2 * nlb); }
     int samples_per_cta() const { return (cta / 32) * (32 / lanes()); }
@@ -43,9 +44,23 @@ inline bool dm_jit_shape(const mbqc_plan* plan, DmJitShape& sh, int lb_request =
     if (lb_request >= 1 && lb_request <= 2 && w - 1 - lb_request >= 0 && w - 1 - lb_request <= 2) sh.lb = lb_request;
     sh.nlb = w - 1 - sh.lb;
     sh.cta = 64;
-    const int nreg = 1 << (2 * sh.lb);
-    const size_t warps = sh.cta / 32, spb = sh.samples_per_cta();
-    sh.smem = 16 * (warps * 2 * nreg * kDmJitPitch + spb * ((size_t)M * 2 + ((size_t)1 << w) + ((size_t)1 << (2 * t.n_out))));
+    // per warp: exchange buffer(s) (the seed state and the final sigma share buffer 0) + the gathered
+    // output block when a channel has to run over it (in buffer 1 where there is one and it fits)
+    const size_t nreg = (size_t)1 << (2 * sh.lb), xbuf = nreg * kDmJitPitch;
+    const size_t warps = sh.cta / 32, spw = 32 / sh.lanes(), spb = sh.samples_per_cta();
+    sh.xbufs = sh.lb == 1 ? 2 : 1;
+    const size_t ost = (t.has_noise && t.n_out > 0) ? spw << (2 * t.n_out) : 0;
+    if (ost == 0) {
+        sh.ost_ofs = sh.ost_extra = 0;
+    } else if (sh.xbufs == 2 && ost <= xbuf) {
+        sh.ost_ofs = (int)xbuf;
+        sh.ost_extra = 0;
+    } else {
+        sh.ost_ofs = (int)(sh.xbufs * xbuf);
+        sh.ost_extra = (int)ost;
+    }
+    if ((spw << w) > xbuf || (spw << (2 * (w - 1))) > xbuf) return false;
+    sh.smem = 16 * (warps * (sh.xbufs * xbuf + sh.ost_extra) + spb * (size_t)M * 2);
     if (sh.smem > 160 * 1024) return false;
     // registers: 2 * 4^lb doubles of state plus the working set of one group
     sh.minblocks = sh.lb == 1 ? 16 : 6;
@@ -112,6 +127,7 @@ inline std::string dm_jit_preamble(const mbqc_plan* plan, const DmJitShape& sh) 
                NLB, sh.cta, sh.minblocks);
     dm_appendf(s, "#define JNOUT %d\n#define JNIN %d\n#define JPITCH %d\n#define JNOISE %d\n", t.n_out, t.n_in, kDmJitPitch,
                t.has_noise ? 1 : 0);
+    dm_appendf(s, "#define JXBUFS %d\n#define JOST_OFS %d\n#define JOST_EXTRA %d\n", sh.xbufs, sh.ost_ofs, sh.ost_extra);
     const mbqc_noise& nz = t.noise;
     dm_appendf(s, "#define JPOP0 %a\n#define JPOP1 %a\n#define JPOP2 %a\n#define JPOP3 %a\n#define JCOHG %a\n#define JCOHD %a\n",
                t.has_noise ? nz.pop[0] : 1.0, t.has_noise ? nz.pop[1] : 0.0, t.has_noise ? nz.pop[2] : 0.0,
@@ -141,8 +157,8 @@ inline std::string dm_jit_preamble(const mbqc_plan* plan, const DmJitShape& sh) 
     int_table("constexpr int kPosSlot1[]", pos_slot1);
     int_table("constexpr int kFinalBit[]", finalbit);
     std::vector<int> aidx(M), plane(M), isrc(1 << w), orow(1 << t.n_out), oneg(1 << t.n_out);
-    std::string fc = "__constant__ double kFixedCosRt[JM] = {", fs = "__constant__ double kFixedSinRt[JM] = {";
-    std::string fz = "__constant__ double kFixedZRt[JM] = {";
+    std::string fc = "__device__ const double kFixedCosRt[JM] = {", fs = "__device__ const double kFixedSinRt[JM] = {";
+    std::string fz = "__device__ const double kFixedZRt[JM] = {";
     for (int m = 0; m < M; ++m) {
         const StepDev& d = plan->h_steps[m];
         aidx[m] = d.angle_idx;
@@ -158,11 +174,11 @@ inline std::string dm_jit_preamble(const mbqc_plan* plan, const DmJitShape& sh) 
         orow[d] = compress(ri);
         oneg[d] = (int)(((ri >> s_last) & 1ull) & parity64(ri & mask_last));
     }
-    int_table("__constant__ int kAngleIdxRt[JM]", aidx);
-    int_table("__constant__ int kPlaneRt[JM]", plane);
-    int_table("__constant__ int kInitSrcRt[]", isrc);
-    int_table("__constant__ int kOutRowRt[]", orow);
-    int_table("__constant__ int kOutNegRt[]", oneg);
+    int_table("__device__ const int kAngleIdxRt[JM]", aidx);
+    int_table("__device__ const int kPlaneRt[JM]", plane);
+    int_table("__device__ const int kInitSrcRt[]", isrc);
+    int_table("__device__ const int kOutRowRt[]", orow);
+    int_table("__device__ const int kOutNegRt[]", oneg);
     std::string spec = "#define JSTEPS_SPEC", exact = "#define JSTEPS_EXACT";
     for (int m = 0; m < M; ++m) {
         dm_appendf(spec, " dm_step_spec<%d>(vr, vi, L, trc, rare);", m);

@@ -604,8 +604,12 @@ int mbqc_jit_dm_try_launch(const mbqc_plan* plan, const DmBatchParams& p, cudaSt
         const char* e = getenv("MBQC_DM_JIT_LB");  // register slots per lane (kernel work)
         return (e && *e) ? atoi(e) : 0;
     }();
+    // window 4: 16 lanes x 4 entries per sample keep small batches short (5.8 vs 9.1 us at 1,024 samples);
+    // from 4,096 samples on 4 lanes x 16 entries win (half the shared-memory traffic per step:
+    // 340 vs 595 us at 262,144) -- profiles/README.md
+    const int lb = lb_env ? lb_env : ((plan->tab.window == 4 && p.batch >= 4096) ? 2 : 0);
     DmJitShape sh;
-    if (!dm_jit_shape(plan, sh, lb_env)) return 0;
+    if (!dm_jit_shape(plan, sh, lb)) return 0;
     cudaKernel_t kern = get_kernel(plan, Variant{sh.lb, sh.cta, kKindDm});
     if (!kern) return 0;
     if (sh.smem > 40 * 1024) {
