@@ -212,6 +212,15 @@ int mbqc_run_batch_dm_sampled(const mbqc_plan* plan, const double* d_angles, int
                               int8_t* d_outcomes, uint32_t* d_byproducts, double* d_prob, int32_t* d_status,
                               void* stream);
 
+/* mbqc_run_batch_dm for patterns with plane-Z steps in the reference's mode="sample"
+ * (np_simulator_dm.py:329-346): even under force0 the outcome of a plane-Z step is drawn from
+ * (prob0, prob1) -- here from the Philox stream (seed, sample_offset + b, step), so a run is
+ * reproducible -- and the state is projected on |0><0| or |1><1|; every other step follows the
+ * deterministic rule.  d_outcomes [B][n_steps] (may be NULL) receives the record. */
+int mbqc_run_batch_dm_zsample(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, void* d_out, int8_t* d_outcomes, int32_t* d_status, void* stream);
+
 /* Batched parameter-shift / central-difference gradient of cost(x) = 1 - |<target|psi(x)>|^2:
  * grad[b][i] = (cost(x_b + s e_i) - cost(x_b - s e_i)) / (2 s)
  * (gradients/_parameter_shift.py:9-25 with s = 1.5; _finite_difference.py:9-25 central with

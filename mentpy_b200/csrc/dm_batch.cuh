@@ -24,7 +24,8 @@ struct MeasCoef {
 };
 
 // entries of the outcome-0 projector P of plane/angle with the (trace-preserving) channel folded in
-__device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, const PlanTables& t, double z = 0.0) {
+__device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, const PlanTables& t, double z = 0.0,
+                                              bool z_project = false) {
     double p00, p11, p10r, p10i;
     if (plane == MBQC_PLANE_XYZ) {  // axis (c, s, z) given directly (fixed angles)
         p00 = 0.5 * (1.0 + z); p11 = 0.5 * (1.0 - z); p10r = 0.5 * c; p10i = 0.5 * s;
@@ -32,8 +33,9 @@ __device__ __forceinline__ MeasCoef meas_coef(int plane, double c, double s, con
         p00 = 0.5; p11 = 0.5; p10r = 0.5 * c; p10i = 0.5 * s;
     } else if (plane == MBQC_PLANE_XZ) {
         p00 = 0.5 * (1.0 + s); p11 = 0.5 * (1.0 - s); p10r = 0.5 * c; p10i = 0.0;
-    } else if (plane == MBQC_PLANE_Z) {  // expectation mode: P0 + P1 = I, the qubit is only traced out
-        p00 = 1.0; p11 = 1.0; p10r = 0.0; p10i = 0.0;
+    } else if (plane == MBQC_PLANE_Z) {
+        // expectation mode: P0 + P1 = I, the qubit is only traced out; sample mode: P0 = |0><0|
+        p00 = 1.0; p11 = z_project ? 0.0 : 1.0; p10r = 0.0; p10i = 0.0;
     } else {
         p00 = 0.5 * (1.0 + s); p11 = 0.5 * (1.0 - s); p10r = 0.0; p10i = 0.5 * c;
     }

@@ -244,8 +244,13 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
                 u = philox_uniform(sp.seed, sp.sample_offset + (uint64_t)be, (uint32_t)m);
             }
         }
-        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz);
-        if (st.plane == MBQC_PLANE_Z) {
+        const bool zs = p.z_sample != 0;
+        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz, zs);
+        if (st.plane == MBQC_PLANE_Z && zs) {
+            // mode="sample": the reference draws the outcome even under force0 (np_simulator_dm.py:329-333)
+            rule = kDmRuleSample;
+            u = philox_uniform(p.z_seed, p.z_offset + (uint64_t)be, (uint32_t)m);
+        } else if (st.plane == MBQC_PLANE_Z) {
             // expectation mode (np_simulator_dm.py:327-344): record prob1 = tr(P1 E(rho)) / tr(rho)
             // (P1 = |1><1| seen through the channel: weights pop[2], pop[3] on rho00, rho11)
             rule = kDmRuleTrace;

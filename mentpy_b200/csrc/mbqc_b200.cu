@@ -658,7 +658,8 @@ static int dm_reg_threads(int64_t batch, int n) {
 
 static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
                              const void* d_inputs, int32_t input_mode, int64_t batch, void* d_out,
-                             int8_t* d_outcomes, double* d_expect, bool expect_mode, int32_t* d_status, void* stream) {
+                             int8_t* d_outcomes, double* d_expect, bool expect_mode, int32_t* d_status, void* stream,
+                             bool z_sample = false, uint64_t z_seed = 0, uint64_t z_offset = 0) {
     int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
     if (rc) return rc;
     const int w = plan->tab.window;
@@ -666,10 +667,10 @@ static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int6
         return fail(MBQC_E_UNSUPPORTED, "batched DM covers window <= %d (got %d)", MBQC_MAX_WINDOW_SMEM_DM, w);
     bool has_z = false;
     for (int m = 0; m < plan->tab.n_steps; ++m) has_z |= plan->h_steps[m].plane == MBQC_PLANE_Z;
-    if (has_z && !expect_mode)
+    if (has_z && !expect_mode && !z_sample)
         return fail(MBQC_E_UNSUPPORTED, "plane-Z steps are drawn at random by the reference outside mode='expectation' "
-                                        "(np_simulator_dm.py:329-333): use mbqc_run_batch_dm_expect");
-    if (has_z && !d_expect) return fail(MBQC_E_ARG, "d_expect is NULL but the plan has plane-Z steps");
+                                        "(np_simulator_dm.py:329-333): use mbqc_run_batch_dm_expect or mbqc_run_batch_dm_zsample");
+    if (has_z && expect_mode && !d_expect) return fail(MBQC_E_ARG, "d_expect is NULL but the plan has plane-Z steps");
     if (has_z && w > MBQC_MAX_WINDOW_REG)
         return fail(MBQC_E_UNSUPPORTED, "plane-Z steps cover window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
     if (batch == 0) return MBQC_OK;
@@ -686,6 +687,9 @@ static int run_batch_dm_impl(const mbqc_plan* plan, const double* d_angles, int6
     p.outcomes = d_outcomes;
     p.status = d_status;
     p.expect = d_expect;
+    p.z_sample = z_sample ? 1 : 0;
+    p.z_seed = z_seed;
+    p.z_offset = z_offset;
     if (d_expect) CUDA_TRY(cudaMemsetAsync(d_expect, 0, sizeof(double) * (size_t)batch * plan->tab.n_steps, (cudaStream_t)stream));
     // w <= 5: one lane per row of rho, registers + shuffles; w = 6: rho in shared memory
     const char* force = getenv("MBQC_DM_KERNEL");  // "smem" forces the shared-memory kernel (tests)
@@ -741,6 +745,13 @@ int mbqc_run_batch_dm_expect(const mbqc_plan* plan, const double* d_angles, int6
                              int8_t* d_outcomes, double* d_expect, int32_t* d_status, void* stream) {
     return run_batch_dm_impl(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_outcomes, d_expect,
                              true, d_status, stream);
+}
+
+int mbqc_run_batch_dm_zsample(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                              const void* d_inputs, int32_t input_mode, int64_t batch, uint64_t seed,
+                              uint64_t sample_offset, void* d_out, int8_t* d_outcomes, int32_t* d_status, void* stream) {
+    return run_batch_dm_impl(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_outcomes, nullptr,
+                             false, d_status, stream, true, seed, sample_offset);
 }
 
 }  // extern "C"

@@ -538,9 +538,15 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
     const int T = p.tab.n_angles;
     const bool push = p.push_n > 0;
     Variant v{push ? 1 : 0, 128, kKindGrad};
-    size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
-    if (push) smem += (size_t)(v.cta + 1) * T * sizeof(double);  // gradient stage of the CTA
+    const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
     if (smem > 200 * 1024 || T > 64) return 0;
+    if (push) {  // the gradient is staged in the (cos, sin) slots: every column must belong to exactly one measurement
+        std::vector<int> uses(T, 0);
+        for (int m = 0; m < p.tab.n_steps; ++m)
+            if (plan->h_steps[m].angle_idx >= 0) ++uses[plan->h_steps[m].angle_idx];
+        for (int c = 0; c < T; ++c)
+            if (uses[c] != 1) return 0;
+    }
     cudaKernel_t kern = get_kernel(plan, v);
     if (!kern) return 0;
     if (smem > 40 * 1024) {  // static shared memory (tables, barriers) counts against the 48 KB default too

@@ -340,6 +340,7 @@ class _CudaPatternBase(BaseSimulator):
             self._input_synced = False
         self._angles_seen[:] = 0.0
         self.outcomes = {}
+        self._shots_done += 1  # a stateful run is one shot of the Philox stream (plane-Z draws, mode="sample")
 
     def current_simulated_nodes(self) -> List[int]:
         return self.schedule[self.current_measurement: self.current_measurement + self.window_size]
@@ -599,24 +600,28 @@ class CudaSimulatorDM(_CudaPatternBase):
         return self._noise
 
     def run_batch(self, angles, input_states=None, check: bool = True, return_outcomes: bool = False,
-                  mode: str = "sample"):
+                  mode: str = "sample", seed: Optional[int] = None, sample_offset: Optional[int] = None):
         """angles [B,T] -> rho [B,2^k,2^k] (and the outcome record [B,M] if requested).
 
-        Patterns with plane-Z nodes need mode="expectation" (np_simulator_dm.py:327-344): those
-        qubits are traced out unprojected and their entry of the outcome record is prob1 (the
-        record is then float64); in mode="sample" the reference draws them at random."""
-        return self._run_plan(self._full_plan(), angles, input_states, check, return_outcomes, mode)
+        Patterns with plane-Z nodes (np_simulator_dm.py:327-346): in mode="expectation" those qubits
+        are traced out unprojected and their entry of the outcome record is prob1 (the record is
+        then float64); in mode="sample" their outcome is drawn from (prob0, prob1), even under
+        force0, and the state projected -- row b draws from the Philox stream (seed, sample_offset +
+        b), by default continuing where the previous call stopped (parity with the reference's
+        np.random draws is statistical only)."""
+        return self._run_plan(self._full_plan(), angles, input_states, check, return_outcomes, mode,
+                              seed=seed, sample_offset=sample_offset)
 
     def _has_z(self, n_steps):
         return any(st.plane == _lib.PLANE_Z for st in self.plan.steps[:n_steps])
 
-    def _run_plan(self, dplan, angles, input_states, check, return_outcomes, zmode="sample"):
+    def _run_plan(self, dplan, angles, input_states, check, return_outcomes, zmode="sample", seed=None,
+                  sample_offset=None, advance=True):
         dev = self._dev()
         lib = _lib.load()
-        expect = self._has_z(dplan.n_steps)
-        if expect and zmode not in ("expectation", "exp"):
-            raise NotImplementedError("plane-Z nodes are drawn at random by the reference in mode='sample' "
-                                      "(np_simulator_dm.py:329-333); use mode='expectation'")
+        has_z = self._has_z(dplan.n_steps)
+        expect = has_z and zmode in ("expectation", "exp")
+        zsample = has_z and not expect
         with torch.cuda.device(dev):
             a, on_host = self._stage_angles(angles, dev)
             batch = a.shape[0]
@@ -631,6 +636,15 @@ class CudaSimulatorDM(_CudaPatternBase):
                                                         batch, _ptr(out), _ptr(outc), _ptr(zp), _ptr(status),
                                                         torch.cuda.current_stream(dev).cuda_stream))
                 outc = outc.to(torch.float64) + zp  # plane-Z entries: prob1; the others stay 0 / 1
+            elif zsample:
+                if sample_offset is None:
+                    sample_offset = self._shots_done
+                    if advance:
+                        self._shots_done += batch
+                _lib.check(lib.mbqc_run_batch_dm_zsample(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode, batch,
+                                                         C.c_uint64(self.seed if seed is None else int(seed)),
+                                                         C.c_uint64(int(sample_offset)), _ptr(out), _ptr(outc), _ptr(status),
+                                                         torch.cuda.current_stream(dev).cuda_stream))
             else:
                 _lib.check(lib.mbqc_run_batch_dm(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
                                                  batch, _ptr(out), _ptr(outc), _ptr(status),
@@ -647,8 +661,12 @@ class CudaSimulatorDM(_CudaPatternBase):
     def measure(self, angle: float, mode="sample") -> Tuple[np.ndarray, int]:
         st = self._record_angle(angle)
         self.current_measurement += 1
+        self._last_mode = mode
         dplan, _nodes = self._prefix_plan(self.current_measurement)
-        rho, oc = self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, True, mode)
+        # the prefix is re-run from the seed state: the plane-Z draws of earlier steps must repeat, so
+        # the whole run uses ONE shot index (advanced by reset())
+        rho, oc = self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, True, mode,
+                                 sample_offset=self._shots_done, advance=False)
         outcome = oc[0, self.current_measurement - 1]
         outcome = float(outcome) if st.plane == _lib.PLANE_Z else int(outcome)
         self.outcomes[st.node] = outcome
@@ -657,7 +675,8 @@ class CudaSimulatorDM(_CudaPatternBase):
     @property
     def qstate(self) -> np.ndarray:
         dplan, _nodes = self._prefix_plan(self.current_measurement)
-        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, False, "expectation")[0]
+        return self._run_plan(dplan, self._angles_seen[None, : self.plan.n_angles], None, True, False,
+                              getattr(self, "_last_mode", "expectation"), sample_offset=self._shots_done, advance=False)[0]
 
     def run(self, angles: List[float], mode="sample", input_state=None):
         if input_state is not None:

@@ -218,11 +218,14 @@ def _projector(plane, th):
 
 
 def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
-                 noise=None, noise_kwargs=None, return_outcomes=False, mode="sample"):
+                 noise=None, noise_kwargs=None, return_outcomes=False, mode="sample", z_outcomes=None):
     """Batched restatement of NumpySimulatorDM.run (np_simulator_dm.py:218-283) + optional noise.
     angles [B,T] -> rho [B,2^k,2^k].  Plane-Z nodes: mode="expectation" traces the qubit out
     unprojected and records prob1 as the (float) outcome (np_simulator_dm.py:327-344); in
-    mode="sample" the reference draws them at random even under force0 -- not restated."""
+    mode="sample" the reference draws them at random even under force0 (np_simulator_dm.py:329-346):
+    pass the drawn record as z_outcomes [B, n_measurements] (entries of the plane-Z steps are used) to
+    get that branch -- projection on |0><0| / |1><1|; `outcomes` then also returns prob1 of those
+    steps in a second array."""
     angles = np.atleast_2d(np.asarray(angles, dtype=float))
     B = angles.shape[0]
     schedule, sched_meas, w = _plan(pat, window_size, schedule, mixed=True)
@@ -232,8 +235,10 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
     N = pat.n_nodes
     has_z = any(pat.measurements[v][0] == "Z" for v in sched_meas)
     outcomes = np.zeros((B, len(sched_meas)), dtype=np.float64 if has_z else np.int8)
-    if has_z and mode not in ("expectation", "exp"):
-        raise NotImplementedError("plane Z in mode='sample' is random in the reference")
+    zsample = has_z and mode not in ("expectation", "exp")
+    if zsample and z_outcomes is None:
+        raise NotImplementedError("plane Z in mode='sample' is random in the reference: pass z_outcomes")
+    zprob1 = np.zeros((B, len(sched_meas)))
     for cm0, node in enumerate(sched_meas):
         plane, th = _angles_for_step(pat, node, angles)
         if kr is not None:
@@ -247,7 +252,16 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
         full = r00 + r11
         prob0 = np.real(np.trace(sig0, axis1=1, axis2=2))
         prob1 = np.real(np.trace(full, axis1=1, axis2=2)) - prob0
-        if plane == "Z":  # expectation mode: no projection, outcome = prob1 / (prob0 + prob1)
+        if plane == "Z" and zsample:  # P0 = |0><0| (with the channel in front), outcome given
+            sig0 = r00  # the channel has already acted on rho (apply_channel_first above)
+            prob0 = np.real(np.trace(sig0, axis1=1, axis2=2))
+            prob1 = np.real(np.trace(full, axis1=1, axis2=2)) - prob0
+            take1 = np.asarray(z_outcomes)[:, cm0].astype(bool)
+            outcomes[:, cm0] = take1
+            zprob1[:, cm0] = prob1 / (prob0 + prob1)
+            sig = np.where(take1[:, None, None], (full - sig0) / np.where(take1, prob1, 1.0)[:, None, None],
+                           sig0 / np.where(take1, 1.0, prob0)[:, None, None])
+        elif plane == "Z":  # expectation mode: no projection, outcome = prob1 / (prob0 + prob1)
             outcomes[:, cm0] = prob1 / (prob0 + prob1)
             sig = full
         else:
@@ -276,7 +290,7 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
         axes = [0] + [1 + p for p in perm] + [1 + k + p for p in perm]
         rho = t.transpose(axes).reshape(B, 2**k, 2**k)
     if return_outcomes:
-        return rho, outcomes
+        return (rho, outcomes, zprob1) if zsample else (rho, outcomes)
     return rho
 
 

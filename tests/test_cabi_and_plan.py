@@ -105,8 +105,14 @@ def test_lowering_errors_mirror_reference():
     big[1] = mb.Ment("Z")
     with pytest.raises(NotImplementedError):
         lower(big, mixed=True)
-    gs[1] = mb.Ment((0.1, 0.2), "XYZ")
-    with pytest.raises(NotImplementedError):
+    gs[1] = mb.Ment((0.1, 0.2), "XYZ")  # fixed two-angle XYZ: lowered on the density-matrix path (ment.py:239-251)
+    xyz = [st for st in lower(gs, mixed=True).steps if st.node == 1][0]
+    n = np.array([np.cos(0.1) * np.cos(0.2), np.sin(0.1) * np.cos(0.2), np.sin(0.2)])
+    assert xyz.plane == _lib.PLANE_XYZ and np.allclose([xyz.fixed_cos, xyz.fixed_sin, xyz.fixed_z], n, atol=1e-16)
+    with pytest.raises(ValueError, match="only XY plane is supported"):
+        lower(gs)  # the state-vector path rejects it like every non-XY plane
+    gs[1] = mb.Ment("XYZ")  # trainable XYZ: one float arrives where the reference needs a tuple
+    with pytest.raises(TypeError, match="Expected tuple"):
         lower(gs, mixed=True)
     tri = mb.MBQCircuit(mb.GraphState([(0, 1), (1, 2), (2, 0)]), input_nodes=[0], output_nodes=[2])
     with pytest.raises(ValueError, match="Schedule must be provided"):

@@ -633,9 +633,6 @@ def test_plane_z_expectation_mode():
             assert abs(v - c["outcomes"][str(k)]) < 1e-12
             assert isinstance(v, float) == (c["planes"].get(str(k)) == "Z")
         ps.reset()
-        with pytest.raises(NotImplementedError):
-            ps.run(ang)                                   # mode="sample": random in the reference
-        ps.reset()
         for node in ps.schedule_measure:                  # step-by-step API
             a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
             st, oc = ps.measure(a, mode="expectation")
@@ -704,3 +701,53 @@ def test_xyz_plane_matches_reference_golden():
         gs[2] = mb.Ment("XYZ")
     with pytest.raises(TypeError, match="Expected tuple"):
         mb.PatternSimulator(gs, backend="cuda-dm")
+
+
+def test_plane_z_sample_mode():
+    """Plane-Z nodes in mode='sample' (np_simulator_dm.py:329-346): the reference draws their outcome
+    from (prob0, prob1) even under force0 and projects.  Parity is statistical by nature (np.random
+    there, Philox here): every shot's state must be the oracle's branch state for the outcomes the
+    kernel recorded, the outcome frequencies must follow the branch probabilities, and a
+    (seed, sample_offset) pair must reproduce the run."""
+    for c in load_golden("dm_z_expectation.json")["cases"][:3]:
+        name, args, kwargs = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kwargs)
+        for v, pl in c["planes"].items():
+            gs[int(v)] = mb.Ment(pl)
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])
+        pat = PatternData.from_circuit(gs)
+        ang = np.asarray(c["angles"])
+        for noise in ({}, {"circuit_noise": "depolarizing", "p": 0.1}):
+            ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"], seed=5, **noise)
+            B = 4000
+            rows = np.tile(ang, (B, 1))
+            rho, oc = ps.run_batch(rows, return_outcomes=True, mode="sample", seed=5, sample_offset=0)
+            assert oc.dtype == np.int8 and set(np.unique(oc)) <= {0, 1}
+            kw = {k: v for k, v in noise.items() if k != "circuit_noise"}
+            ins = None if inp is None else np.tile(inp, (64, 1))
+            ref, roc, zp1 = matrix_free.run_dm_batch(pat, rows[:64], input_states=ins, window_size=c["window_size"],
+                                                     noise=noise.get("circuit_noise"), noise_kwargs=kw, return_outcomes=True,
+                                                     mode="sample", z_outcomes=oc[:64])
+            assert dm_distance(rho[:64], ref) < 1e-10
+            assert np.array_equal(roc.astype(np.int8), oc[:64])
+            # first plane-Z step: every shot sees the same prob1 -> binomial frequency within 5 sigma
+            zcols = [m for m, st in enumerate(ps.simulator.plan.steps) if st.plane == mb._lib.PLANE_Z]
+            p1 = zp1[0, zcols[0]]
+            freq = oc[:, zcols[0]].mean()
+            assert abs(freq - p1) < 5 * np.sqrt(max(p1 * (1 - p1), 1e-4) / B) + 1e-3
+            again, oc2 = ps.run_batch(rows[:100], return_outcomes=True, mode="sample", seed=5, sample_offset=0)
+            assert np.array_equal(oc2, oc[:100]) and np.array_equal(again, rho[:100])
+            other, oc3 = ps.run_batch(rows[:100], return_outcomes=True, mode="sample", seed=5, sample_offset=100)
+            assert np.array_equal(oc3, oc[100:200])
+        # stateful API: one shot, prefix re-runs repeat the earlier draws
+        ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"], seed=11)
+        ps.reset()
+        rec = []
+        for node in ps.schedule_measure:
+            a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
+            st, o = ps.measure(a)
+            rec.append(int(o))
+        ins1 = None if inp is None else inp[None]
+        ref1, _, _ = matrix_free.run_dm_batch(pat, ang[None], input_states=ins1, window_size=c["window_size"],
+                                              return_outcomes=True, mode="sample", z_outcomes=np.asarray(rec)[None])
+        assert dm_distance(st, ref1[0]) < 1e-10
