@@ -860,8 +860,11 @@ int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int
     int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out);
     if (rc) return rc;
     const int w = plan->tab.window;
-    if (w > MBQC_MAX_WINDOW_REG)
-        return fail(MBQC_E_UNSUPPORTED, "sampled runs cover window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
+    if (w > MBQC_MAX_WINDOW_SMEM_SV)
+        return fail(MBQC_E_UNSUPPORTED, "sampled runs cover window <= %d (got %d)", MBQC_MAX_WINDOW_SMEM_SV, w);
+    for (int m = 0; m < plan->tab.n_steps; ++m)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+            return fail(MBQC_E_UNSUPPORTED, "the state-vector path measures in the XY plane only (np_simulator_sv.py:54-59)");
     SampleParams sp;
     if ((rc = fill_sample_params(sp, plan, batch, seed, sample_offset, outcome_mode, correct, d_outcomes,
                                  d_byproducts, d_prob)))
@@ -869,6 +872,18 @@ int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int
     if (batch == 0) return MBQC_OK;
     SvBatchParams p;
     fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_out, d_status);
+    if (w > MBQC_MAX_WINDOW_REG) {  // 6..12: amplitudes in shared memory, a thread group per shot
+        int tps_log2 = w - 1;
+        if (tps_log2 > 8) tps_log2 = 8;
+        const int tps = 1 << tps_log2;
+        int spb = 256 / tps;
+        if (spb < 1) spb = 1;
+        const size_t smem = (size_t)spb * (16ull << w);
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sv_smem_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
+        sv_smem_sample_kernel<<<blocks, tps * spb, smem, (cudaStream_t)stream>>>(p, sp, tps_log2, spb);
+        return after_launch("sv_smem_sample_kernel");
+    }
     SvRegParams rp;
     fill_reg_params(rp, p, plan);
     const int T = plan->tab.n_angles;

@@ -14,6 +14,7 @@
 // RNG: Philox4x32-10 (Salmon et al., SC'11), counter = (sample lo, sample hi, step, 0), key =
 // seed: stateless, so a sample's outcomes do not depend on batch size, launch shape or GPU count.
 #pragma once
+#include "sv_batch.cuh"
 #include "sv_reg.cuh"
 
 namespace mbqc {
@@ -208,6 +209,139 @@ __global__ void __launch_bounds__(128) sv_reg_sample_kernel(const __grid_constan
             const uint32_t sg = (uint32_t)(__popc((uint32_t)d & zm) & 1) << 31;
             o[(uint32_t)d ^ xm] = make_double2(flip_sign(re[i] * r, sg), flip_sign(im[i] * r, sg));
         }
+    }
+}
+
+// Shared-memory variant for 6 <= window <= 12: a group of 2^tps_log2 threads per shot, amplitudes in
+// shared memory (the layout of sv_smem_kernel); every thread of the group evaluates the same Born
+// probability (group reduction) and the same Philox draw, so the outcome is group-uniform.
+__global__ void sv_smem_sample_kernel(const __grid_constant__ SvBatchParams p, const __grid_constant__ SampleParams sp,
+                                      int tps_log2, int spb) {
+    extern __shared__ double2 smem[];
+    __shared__ double red[32];
+    const PlanTables& t = p.tab;
+    const int w = t.window, M = t.n_steps;
+    const int tps = 1 << tps_log2;
+    const int ls = threadIdx.x >> tps_log2;
+    const int tid = threadIdx.x & (tps - 1);
+    const int64_t b = (int64_t)blockIdx.x * spb + ls;
+    const bool live = b < p.batch;
+    const int64_t be = live ? b : 0;
+    double2* psi = smem + ((size_t)ls << w);
+    const uint64_t n = 1ull << w, half = n >> 1;
+    double nrm = 0.0;
+    {
+        const double2* in = (p.input_mode == MBQC_INPUT_PLUS)
+                                ? nullptr
+                                : p.inputs + (p.input_mode == MBQC_INPUT_BATCH ? (be << t.n_in) : 0);
+        for (uint64_t i = tid; i < n; i += tps) {
+            double2 v = make_double2(t.plus_amp, 0.0);
+            if (in) {
+                v = __ldg(in + init_source_index(t, i));
+                v.x *= t.init_scale;
+                v.y *= t.init_scale;
+            }
+            if (init_sign_bit(t, i)) {
+                v.x = -v.x;
+                v.y = -v.y;
+            }
+            psi[i] = v;
+            nrm = fma(v.x, v.x, fma(v.y, v.y, nrm));
+        }
+    }
+    nrm = group_sum(nrm, tps_log2, ls, red);  // contains the barrier that publishes psi for tps > 32
+    __syncthreads();
+    const double* row = p.angles + be * p.stride;
+    const uint64_t sample = sp.sample_offset + (uint64_t)be;
+    uint32_t hist = 0, bx = 0, bz = 0;
+    double pb = 1.0;
+    int took1 = 0;
+    for (int m = 0; m < M; ++m) {
+        const StepDev st = p.steps[m];
+        double c = st.fc, s = st.fs;
+        if (st.angle_idx >= 0) sincos(__ldg(row + st.angle_idx), &s, &c);
+        const FeedForwardDev ff = sp.ff[m];
+        const uint32_t a = __popc(hist & ff.xdep) & 1u, z = __popc(hist & ff.zdep) & 1u;
+        c = flip_sign(c, z << 31);
+        s = flip_sign(s, (a ^ z) << 31);
+        const uint64_t bit = 1ull << st.slot;
+        double n0 = 0.0;  // || <0_theta| psi ||^2 (times 2): Born weight of outcome 0
+        for (uint64_t g = tid; g < half; g += tps) {
+            const uint64_t i0 = insert_zero(g, st.slot);
+            const double2 x = psi[i0], y = psi[i0 | bit];
+            const double tr = fma(c, y.x, fma(s, y.y, x.x)), ti = fma(c, y.y, fma(-s, y.x, x.y));
+            n0 = fma(tr, tr, fma(ti, ti, n0));
+        }
+        n0 = group_sum(n0, tps_log2, ls, red);
+        const double p0 = n0 / (2.0 * nrm);
+        int outcome;
+        if (sp.outcome_mode == MBQC_OUTCOMES_FORCED)
+            outcome = sp.outcomes[be * M + m] ? 1 : 0;
+        else
+            outcome = philox_uniform(sp.seed, sample, (uint32_t)m) < p0 ? 0 : 1;
+        if (outcome) {  // project on (I - M)/2: angle + pi
+            c = -c;
+            s = -s;
+        }
+        pb *= outcome ? (1.0 - p0) : p0;
+        double ns = 0.0;  // squared norm of the projected state, summed while it is written
+        for (uint64_t g = tid; g < half; g += tps) {
+            const uint64_t i0 = insert_zero(g, st.slot);
+            const double2 x = psi[i0], y = psi[i0 | bit];
+            double2 tt;
+            tt.x = fma(c, y.x, fma(s, y.y, x.x));
+            tt.y = fma(c, y.y, fma(-s, y.x, x.y));
+            ns = fma(tt.x, tt.x, fma(tt.y, tt.y, ns));
+            psi[i0] = tt;
+            if (parity64(i0 & st.nbr_mask)) {
+                tt.x = -tt.x;
+                tt.y = -tt.y;
+            }
+            psi[i0 | bit] = tt;
+        }
+        ns = group_sum(ns, tps_log2, ls, red);
+        nrm = 2.0 * ns;  // both copies of the reduced state
+        __syncthreads();
+        if ((m & 7) == 7) {  // keep the magnitudes bounded (the norm doubles per step at prob 1/2)
+            const double r = rsqrt(nrm);
+            for (uint64_t i = tid; i < n; i += tps) {
+                psi[i].x *= r;
+                psi[i].y *= r;
+            }
+            nrm = 1.0;
+            __syncthreads();
+        }
+        hist = (hist << 1) | (uint32_t)outcome;
+        if (outcome) {
+            bx ^= ff.outx;
+            bz ^= ff.outz;
+        }
+        took1 |= outcome;
+        if (live && tid == 0 && sp.outcome_mode != MBQC_OUTCOMES_FORCED && sp.outcomes) sp.outcomes[b * M + m] = (int8_t)outcome;
+    }
+    const int k = t.n_out;
+    const uint32_t no = 1u << k;
+    double n2 = 0.0;
+    for (uint32_t o = tid; o < no; o += tps) {
+        const double2 v = psi[output_state_index(t, o)];
+        n2 = fma(v.x, v.x, fma(v.y, v.y, n2));
+    }
+    n2 = group_sum(n2, tps_log2, ls, red);
+    if (!live) return;
+    const bool ok = (n2 > 0.0) && isfinite(n2) && (pb == pb);
+    if (tid == 0) {
+        if (p.status) p.status[b] = (ok ? MBQC_STATUS_OK : MBQC_STATUS_BAD_NORM) | (took1 ? MBQC_STATUS_OUTCOME1 : 0);
+        if (sp.byproducts) sp.byproducts[b] = bx | (bz << 16);
+        if (sp.prob) sp.prob[b] = pb;
+    }
+    const uint32_t xm = sp.correct ? byproduct_index_mask(bx, k) : 0u;
+    const uint32_t zm = sp.correct ? byproduct_index_mask(bz, k) : 0u;
+    const double r = rsqrt(n2);
+    double2* o = p.out + (b << k);
+    for (uint32_t d = tid; d < no; d += tps) {  // Z^z then X^x on the output register
+        const double2 v = psi[output_state_index(t, d)];
+        const uint32_t sg = (uint32_t)(__popc(d & zm) & 1) << 31;
+        o[d ^ xm] = make_double2(flip_sign(v.x * r, sg), flip_sign(v.y * r, sg));
     }
 }
 

@@ -276,8 +276,9 @@ class _CudaPatternBase(BaseSimulator):
         lib = _lib.load()
         if self.dtype != "complex128":
             raise NotImplementedError("sampled runs are complex128 only")
-        if self.plan.window > _lib.MAX_WINDOW_REG:
-            raise NotImplementedError(f"sampled runs cover window_size <= {_lib.MAX_WINDOW_REG}")
+        wmax = _lib.MAX_WINDOW_REG if self.mixed else _lib.MAX_WINDOW_SMEM_SV
+        if self.plan.window > wmax:
+            raise NotImplementedError(f"sampled runs cover window_size <= {wmax}")
         form = (output_form or ("dm" if self.mixed else "sv")).lower()
         if form not in ("sv", "statevector", "dm", "densitymatrix"):
             raise ValueError(f"Output form {output_form} is not supported.")
