@@ -353,11 +353,12 @@ int mbqc_ipc_import(const void* handle64, void** d_ptr);
 int mbqc_ipc_close(void* d_ptr);
 
 /* Stream-ordered barrier across the GPUs of one node through flag words in peer-mapped memory:
- * d_flags[r] = rank r's array of 8 uint64 (zeroed once; entry `rank` is the caller's own
- * allocation, the others are IPC imports).  `epoch` grows by one per call on every rank.  Work
- * queued on `stream` after the call starts only when every rank's earlier work on its stream --
- * including its peer stores -- has completed. */
-int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, uint64_t epoch, void* stream);
+ * d_flags[r] = rank r's array of 16 uint64 (zeroed once; entry `rank` is the caller's own
+ * allocation, the others are IPC imports; the kernel keeps its call count in word 8, so the launch
+ * has no changing argument and can be captured in a CUDA graph).  Every rank makes the same
+ * sequence of calls.  Work queued on `stream` after the call starts only when every rank's earlier
+ * work on its stream -- including its peer stores -- has completed. */
+int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, void* stream);
 
 /* ---- calculator helpers (mentpy/calculator/state_ops.py), single state, qubit 0 = MSB ------------
  * pure: SUM over the traced qubits then renormalise (:42-74 -- the reference's pure-state "partial

@@ -124,7 +124,7 @@ _SIGNATURES = {
     "mbqc_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mbqc_ipc_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "mbqc_ipc_close": (C.c_int, [C.c_void_p]),
-    "mbqc_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint64, C.c_void_p]),
+    "mbqc_peer_barrier": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
     "mbqc_partial_trace_pure": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "mbqc_partial_trace_mixed": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p]),
     "mbqc_pure2density": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),

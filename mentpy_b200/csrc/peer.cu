@@ -7,33 +7,43 @@
 namespace {
 
 struct BarrierArgs {
-    unsigned long long* flags[8];  // flags[d]: the flag array of rank d (peer-mapped; [8] words each)
+    unsigned long long* flags[8];  // flags[d]: the flag array of rank d (peer-mapped; [16] words each)
     int n, me;
-    unsigned long long epoch;
 };
 
-// thread d: release-store `epoch` into slot `me` of rank d's flags, then wait for slot d of our own.
-// The kernel before this one on the stream has completed, so its peer stores are performed; the
-// system-scope release / acquire pair orders them before anything the waiting rank runs next.
+// The epoch is word 8 of the rank's own flag array, advanced by the kernel itself: the launch has no
+// changing argument, so it can sit in a CUDA graph.  thread d: release-store the epoch into slot
+// `me` of rank d's flags, then wait for slot d of our own.  The kernel before this one on the stream
+// has completed, so its peer stores are performed; the system-scope release / acquire pair orders
+// them before anything the waiting rank runs next.
 __global__ void peer_barrier_kernel(const __grid_constant__ BarrierArgs a) {
+    __shared__ unsigned long long s_epoch;
     const int d = threadIdx.x;
+    if (d == 0) {
+        unsigned long long* counter = a.flags[a.me] + 8;
+        s_epoch = *counter + 1ull;
+        *counter = s_epoch;
+    }
+    __syncthreads();
     if (d >= a.n) return;
+    const unsigned long long epoch = s_epoch;
     unsigned long long* theirs = a.flags[d] + a.me;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(a.epoch) : "memory");
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long* mine = a.flags[a.me] + d;
     unsigned long long v;
     do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    } while (v < a.epoch);
+    } while (v < epoch);
 }
 
 }  // namespace
 
 extern "C" {
 
-// d_flags[r]: rank r's flag array (8 x uint64, zero-initialised once, in IPC-shared memory; entry
-// `rank` is this process's own allocation).  epoch must grow by one per call on every rank.
-int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, uint64_t epoch, void* stream) {
+// d_flags[r]: rank r's flag array (16 x uint64, zero-initialised once, in IPC-shared memory; entry
+// `rank` is this process's own allocation; words 0..7 arrival flags, word 8 the rank's call count).
+// Every rank must make the same sequence of calls.
+int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, void* stream) {
     if (!d_flags || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks) return mbqc_set_error(MBQC_E_ARG, "bad barrier arguments");
     BarrierArgs a;
     for (int d = 0; d < 8; ++d) {
@@ -42,7 +52,6 @@ int mbqc_peer_barrier(void* const* d_flags, int32_t n_ranks, int32_t rank, uint6
     }
     a.n = n_ranks;
     a.me = rank;
-    a.epoch = epoch;
     peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
     return mbqc_after_launch("peer_barrier_kernel");
 }

@@ -536,8 +536,12 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
     if (mode == 0 || !plan->lean) return 0;
     if (mode == 1 && p.batch < min_batch) return 0;
     const int T = p.tab.n_angles;
+    static const int cta_env = [] {
+        const char* e = getenv("MBQC_GRAD_CTA");  // 64 | 128 (kernel work)
+        return (e && atoi(e) == 64) ? 64 : 128;
+    }();
     const bool push = p.push_n > 0;
-    Variant v{push ? 1 : 0, 128, kKindGrad};
+    Variant v{push ? 1 : 0, cta_env, kKindGrad};
     const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
     if (smem > 200 * 1024 || T > 64) return 0;
     if (push) {  // the gradient is staged in the (cos, sin) slots: every column must belong to exactly one measurement

@@ -104,7 +104,8 @@ class ReplicatedResult:
         self.rows, self.cols = int(rows), int(cols)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.nbytes = ((self.rows * self.cols * 8 + 255) // 256) * 256
-        self.epoch = 0
+        self._flag_ptrs = None
+        self._dst = [None, None]
         self._imported = []
         with torch.cuda.device(self.device):
             p = C.c_void_p()
@@ -155,9 +156,11 @@ class ReplicatedResult:
         """(ctypes array of result pointers with the local copy first, count) for *_push entry points."""
         import ctypes as C
 
-        off = self.copy * self.nbytes
-        order = [self.ptrs[self.rank] + off] + [q + off for r, q in enumerate(self.ptrs) if r != self.rank]
-        return (C.c_void_p * len(order))(*order), len(order)
+        if self._dst[self.copy] is None:
+            off = self.copy * self.nbytes
+            order = [self.ptrs[self.rank] + off] + [q + off for r, q in enumerate(self.ptrs) if r != self.rank]
+            self._dst[self.copy] = (C.c_void_p * len(order))(*order)
+        return self._dst[self.copy], self.world
 
     def barrier(self, stream=None):
         import ctypes as C
@@ -165,10 +168,10 @@ class ReplicatedResult:
         if self.world == 1:
             return
         torch = self.torch
-        self.epoch += 1
-        flags = (C.c_void_p * self.world)(*[q + 2 * self.nbytes for q in self.ptrs])
+        if self._flag_ptrs is None:
+            self._flag_ptrs = (C.c_void_p * self.world)(*[q + 2 * self.nbytes for q in self.ptrs])
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        self._lib.check(self.lib.mbqc_peer_barrier(flags, self.world, self.rank, self.epoch, st))
+        self._lib.check(self.lib.mbqc_peer_barrier(self._flag_ptrs, self.world, self.rank, st))
 
     def release(self):
         import ctypes as C

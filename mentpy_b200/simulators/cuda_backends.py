@@ -148,8 +148,9 @@ class _CudaPatternBase(BaseSimulator):
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure
         if not self.force0:  # fail early (no GPU needed): flow, planes and window of the sampled path
-            if self.plan.window > _lib.MAX_WINDOW_REG:
-                raise NotImplementedError(f"force0=False covers window_size <= {_lib.MAX_WINDOW_REG}")
+            wmax = _lib.MAX_WINDOW_REG if self.mixed else _lib.MAX_WINDOW_SMEM_SV
+            if self.plan.window > wmax:
+                raise NotImplementedError(f"force0=False covers window_size <= {wmax}")
             feedforward(mbqcircuit, self.plan)
         if input_state is None:
             n_in = len(mbqcircuit.input_nodes)
@@ -213,6 +214,10 @@ class _CudaPatternBase(BaseSimulator):
         if input_states is None:
             if self._d_input is None or self._d_input.device != dev:
                 self._d_input = self._device_input(dev)
+                # the default |+>^|I| input needs no loads at all: the kernels seed constants
+                self._plus_input = self._input_is_plus()
+            if self._plus_input:
+                return None, _lib.INPUT_PLUS
             return self._d_input, _lib.INPUT_SHARED
         if isinstance(input_states, torch.Tensor):
             t = input_states.to(device=dev, dtype=torch.complex128).contiguous()
@@ -436,7 +441,7 @@ class CudaSimulatorSV(_CudaPatternBase):
             a, on_host = self._stage_angles(angles, dev)
             batch = a.shape[0]
             inp, mode = self._stage_inputs(input_states, batch, dev)
-            inp = inp.to(torch.complex64).contiguous()
+            inp = None if inp is None else inp.to(torch.complex64).contiguous()
             dim = 2 ** dplan.n_out
             shape = (batch, dim) if code == _lib.OUT_SV else (batch, dim, dim)
             out = torch.empty(shape, dtype=torch.complex64, device=dev)

@@ -145,7 +145,10 @@ def test_facade_contract_without_gpu():
     with pytest.raises(NotImplementedError):
         mb.PatternSimulator(gs, backend="cuda-sv-stream", force0=False)
     with pytest.raises(NotImplementedError):  # sampled runs: register kernels only
-        mb.PatternSimulator(mb.templates.grid_cluster(6, 3), backend="cuda-sv", force0=False)
+        mb.PatternSimulator(mb.templates.grid_cluster(6, 3), backend="cuda-dm", force0=False)  # DM shots: window <= 5
+    assert mb.PatternSimulator(mb.templates.grid_cluster(6, 3), backend="cuda-sv", force0=False).window_size == 7  # SV shots: <= 12
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(mb.templates.grid_cluster(13, 3), backend="cuda-sv", force0=False)
     assert mb.PatternSimulator(gs, backend="cuda-sv", force0=False, seed=5).seed == 5
     ps = mb.PatternSimulator(gs, backend="CUDA-SV", some_unknown_kwarg=3)
     assert ps.window_size == 2 and ps.mbqcircuit is gs and ps.outcomes == {}

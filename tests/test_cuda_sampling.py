@@ -29,7 +29,7 @@ def _fid(a, b):
     ("grid_cluster", [3, 4], 4, {1: "Y", 5: "X"}), ("grid_cluster", [4, 4], None, {}), ("grid_cluster", [2, 6], 5, {}),
     ("muta", [2, 1], 5, {}),
     # windows 6..12: the shared-memory sampled kernel (sv_smem_sample_kernel)
-    ("grid_cluster", [2, 6], 6, {}), ("grid_cluster", [3, 5], 7, {4: "X"}), ("grid_cluster", [3, 4], 8, {}),
+    ("grid_cluster", [2, 6], 6, {}), ("grid_cluster", [3, 5], 7, {3: "X"}), ("grid_cluster", [3, 4], 8, {}),
     ("linear_cluster", [12], 10, {}), ("grid_cluster", [4, 4], 12, {}),
 ])
 def test_sampled_sv_matches_oracle_shot_by_shot(name, args, w, fixed):
