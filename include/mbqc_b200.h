@@ -70,6 +70,15 @@ typedef struct mbqc_step {
     double fixed_sin;   /*   reference does (np.cos/np.sin, or exact 1,0 / 0,1 for planes X / Y) */
     uint64_t nbr_mask;  /* slots of the appended qubit's in-window neighbours */
     double fixed_z;     /* MBQC_PLANE_XYZ: Z component sin(t2); (fixed_cos, fixed_sin) = cos(t2) (cos t1, sin t1) */
+    /* Outcome-controlled measurement (operators/controlled_ment.py:14-113), density-matrix path:
+     * cond_mask != 0 selects earlier outcomes (bit j = the step j+1 measurements back, at most 32);
+     * their values, packed lowest selected bit first, index cond_table; a 1 there replaces
+     * (plane, angle_idx, fixed_*) by the alt_* fields for that sample.  cond_mask == 0: plain step. */
+    uint32_t cond_mask;
+    uint32_t cond_table;
+    int32_t alt_plane;
+    int32_t alt_angle_idx;
+    double alt_cos, alt_sin, alt_z;
 } mbqc_step;
 
 /* Single-qubit channel in block form on (rho00, rho01, rho10, rho11) of the affected qubit:

@@ -4,7 +4,7 @@ Importing the package never needs a GPU (the host-side pattern layer is pure Pyt
 that simulates needs the in-tree CUDA library and a CUDA device and raises otherwise.
 """
 from . import mbqc
-from .mbqc import (GraphState, MBQCircuit, Measurement, Ment, hstack, merge, templates, vstack)
+from .mbqc import (ControlledMent, ControlMent, GraphState, MBQCircuit, Measurement, Ment, MentOutcome, hstack, merge, templates, vstack)
 from . import calculator, gates, gradients, optimizers, simulators, utils
 from .simulators import BaseSimulator, CudaSimulatorDM, CudaSimulatorSV, PatternSimulator
 

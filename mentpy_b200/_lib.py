@@ -23,7 +23,9 @@ MAX_IO = 16
 class Step(C.Structure):
     _fields_ = [("slot", C.c_int32), ("angle_idx", C.c_int32), ("plane", C.c_int32),
                 ("flags", C.c_uint32), ("fixed_cos", C.c_double), ("fixed_sin", C.c_double),
-                ("nbr_mask", C.c_uint64), ("fixed_z", C.c_double)]
+                ("nbr_mask", C.c_uint64), ("fixed_z", C.c_double), ("cond_mask", C.c_uint32), ("cond_table", C.c_uint32),
+                ("alt_plane", C.c_int32), ("alt_angle_idx", C.c_int32), ("alt_cos", C.c_double), ("alt_sin", C.c_double),
+                ("alt_z", C.c_double)]
 
 
 class Optimizer(C.Structure):

@@ -135,6 +135,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
     const uint32_t ngroups = nelem >> 2;
     const uint32_t gmask = (dim >> 1) - 1;  // w-1 bits
     int bad = 0, took1 = 0;
+    uint32_t hist = 0;  // outcome record, newest in bit 0 (controlled steps)
     // (cos, sin) of the next `chunk` measurements are evaluated by different lanes of the sample's
     // group (one sincos per measurement per warp instead of one per lane) and broadcast by shuffle
     const int chunk = tps < 32 ? tps : 32;
@@ -151,15 +152,27 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
                 const StepDev sx = p.steps[mm];
                 c_mine = sx.fc;
                 s_mine = sx.fs;
-                if (sx.angle_idx >= 0) sincos_cw(__ldg(row + sx.angle_idx), s_mine, c_mine);
+                const int ai = sx.angle_idx >= 0 ? sx.angle_idx : sx.alt_angle_idx;  // controlled step: either branch
+                if (ai >= 0) sincos_cw(__ldg(row + ai), s_mine, c_mine);
             }
         }
-        const double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
-        const double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
+        double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
+        double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
         const StepDev st = p.steps[m];
+        int plane = st.plane;
+        double fz = st.fz;
+        if (st.cond_mask) {  // outcome-controlled measurement (controlled_ment.py:96-113)
+            const bool alt = cond_takes_alt(hist, st.cond_mask, st.cond_table);
+            plane = alt ? st.alt_plane : st.plane;
+            fz = alt ? st.afz : st.fz;
+            if ((alt ? st.alt_angle_idx : st.angle_idx) < 0) {
+                c = alt ? st.afc : st.fc;
+                s = alt ? st.afs : st.fs;
+            }
+        }
         const int sl = st.slot;
         const uint32_t cbit = 1u << sl, rbit = cbit << w;
-        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz);
+        const MeasCoef q = meas_coef(plane, c, s, t, fz);
         double2 sg[kDmMaxGroupsPerThread], sf[kDmMaxGroupsPerThread];
         double tr0 = 0.0, trf = 0.0;
         if (live) {
@@ -185,6 +198,7 @@ __global__ void dm_smem_kernel(const __grid_constant__ DmBatchParams p, int tps_
         // outcome 1 iff prob0 < 1e-4 (np_simulator_dm.py:335-338); sigma1 = tr_s(rho) - sigma0
         const int outcome = (tr0 < 1e-4) ? 1 : 0;
         took1 |= outcome;
+        hist = (hist << 1) | (uint32_t)outcome;
         const double prob = outcome ? (trf - tr0) : tr0;
         if (outcome) {
 #pragma unroll

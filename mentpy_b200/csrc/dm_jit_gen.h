@@ -38,7 +38,7 @@ inline bool dm_jit_shape(const mbqc_plan* plan, DmJitShape& sh, int lb_request =
     const int w = t.window, M = t.n_steps;
     if (w < 2 || w > 5 || M < 1 || !plan->reg_periodic) return false;
     for (int m = 0; m < M; ++m)
-        if (plan->h_steps[m].plane == MBQC_PLANE_Z) return false;
+        if (plan->h_steps[m].plane == MBQC_PLANE_Z || plan->h_steps[m].cond_mask) return false;
     // lanes per sample = 4^(w-1-lb) <= 32; registers per lane = 2 * 4^lb doubles
     sh.lb = (w == 5) ? 2 : 1;
     if (lb_request >= 1 && lb_request <= 2 && w - 1 - lb_request >= 0 && w - 1 - lb_request <= 2) sh.lb = lb_request;

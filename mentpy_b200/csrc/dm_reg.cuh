@@ -222,12 +222,25 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
                 const StepDev sx = p.steps[mm];
                 c_mine = sx.fc;
                 s_mine = sx.fs;
-                if (sx.angle_idx >= 0) sincos_cw(__ldg(row + sx.angle_idx), s_mine, c_mine);
+                // a controlled step stages the trainable angle of whichever branch has one
+                const int ai = sx.angle_idx >= 0 ? sx.angle_idx : sx.alt_angle_idx;
+                if (ai >= 0) sincos_cw(__ldg(row + ai), s_mine, c_mine);
             }
         }
         double c = __shfl_sync(0xffffffffu, c_mine, lane_base + within);
         double s = __shfl_sync(0xffffffffu, s_mine, lane_base + within);
         const StepDev st = p.steps[m];
+        int plane = st.plane;
+        double fz = st.fz;
+        if (st.cond_mask) {  // outcome-controlled measurement (controlled_ment.py:96-113): pick the branch
+            const bool alt = cond_takes_alt(hist, st.cond_mask, st.cond_table);
+            plane = alt ? st.alt_plane : st.plane;
+            fz = alt ? st.afz : st.fz;
+            if ((alt ? st.alt_angle_idx : st.angle_idx) < 0) {
+                c = alt ? st.afc : st.fc;
+                s = alt ? st.afs : st.fs;
+            }
+        }
         FeedForwardDev ff = {0, 0, 0, 0};
         int rule = kDmRuleThreshold;
         double u = 0.0, pstep = 1.0;
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
             }
         }
         const bool zs = p.z_sample != 0;
-        const MeasCoef q = meas_coef(st.plane, c, s, t, st.fz, zs);
+        const MeasCoef q = meas_coef(plane, c, s, t, fz, zs);
         if (st.plane == MBQC_PLANE_Z && zs) {
             // mode="sample": the reference draws the outcome even under force0 (np_simulator_dm.py:329-333)
             rule = kDmRuleSample;
@@ -284,6 +297,7 @@ __global__ void __launch_bounds__(128) dm_reg_kernel(const __grid_constant__ DmB
             if (live && r == 0 && sp.outcomes && sp.outcome_mode != MBQC_OUTCOMES_FORCED)
                 sp.outcomes[b * t.n_steps + m] = (int8_t)outcome;
         } else {
+            hist = (hist << 1) | (uint32_t)outcome;
             if (live && p.outcomes && r == 0) p.outcomes[b * t.n_steps + m] = (int8_t)outcome;
         }
     }

@@ -101,6 +101,14 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
         if (s.angle_idx < -1 || s.angle_idx >= n_angles) return fail(MBQC_E_ARG, "step %d: angle_idx %d outside [ -1, %d)", m, s.angle_idx, n_angles);
         if (s.plane < MBQC_PLANE_XY || s.plane > MBQC_PLANE_XYZ) return fail(MBQC_E_ARG, "step %d: plane %d unknown", m, s.plane);
         if (s.plane == MBQC_PLANE_XYZ && s.angle_idx >= 0) return fail(MBQC_E_ARG, "step %d: plane XYZ takes two fixed angles (ment.py:239-251), not a column of the angle matrix", m);
+        if (s.cond_mask) {
+            if (s.alt_plane < MBQC_PLANE_XY || s.alt_plane > MBQC_PLANE_XYZ || s.alt_plane == MBQC_PLANE_Z || s.plane == MBQC_PLANE_Z)
+                return fail(MBQC_E_ARG, "step %d: controlled measurements take the planes XY, XZ, YZ, XYZ", m);
+            if (s.alt_angle_idx < -1 || s.alt_angle_idx >= n_angles) return fail(MBQC_E_ARG, "step %d: alt_angle_idx %d outside [-1, %d)", m, s.alt_angle_idx, n_angles);
+            if (s.alt_plane == MBQC_PLANE_XYZ && s.alt_angle_idx >= 0) return fail(MBQC_E_ARG, "step %d: plane XYZ takes two fixed angles", m);
+            if (m < 32 && (s.cond_mask >> m)) return fail(MBQC_E_ARG, "step %d: condition reads an outcome before the first measurement", m);
+            if (__builtin_popcount(s.cond_mask) > 5) return fail(MBQC_E_ARG, "step %d: a condition reads at most 5 outcomes (got %d)", m, __builtin_popcount(s.cond_mask));
+        }
         if (s.nbr_mask & ~wmask) return fail(MBQC_E_ARG, "step %d: nbr_mask outside window", m);
         if ((s.nbr_mask >> s.slot) & 1ull) return fail(MBQC_E_ARG, "step %d: nbr_mask contains the step's own slot", m);
     }
@@ -154,7 +162,13 @@ static int plan_create_impl(const mbqc_step* steps, int32_t n_steps, int32_t win
         d.flipmask = 0;
         d.pad = 0;
         d.fz = s.fixed_z;
-        d.pad2 = 0.0;
+        d.cond_mask = s.cond_mask;
+        d.cond_table = s.cond_mask ? s.cond_table : 0u;
+        d.alt_plane = s.cond_mask ? s.alt_plane : s.plane;
+        d.alt_angle_idx = s.cond_mask ? s.alt_angle_idx : -1;
+        d.afc = s.alt_cos;
+        d.afs = s.alt_sin;
+        d.afz = s.alt_z;
         if (window <= MBQC_MAX_WINDOW_REG)
             for (uint32_t i = 0; i < (1u << window); ++i)
                 if (((i >> s.slot) & 1u) && parity64((uint64_t)i & d.nbr_mask)) d.flipmask |= 1u << i;
@@ -403,7 +417,7 @@ int mbqc_run_batch_sv(const mbqc_plan* plan, const double* d_angles, int64_t ang
     if (rc) return rc;
     if (out_form != MBQC_OUT_SV && out_form != MBQC_OUT_DM) return fail(MBQC_E_ARG, "out_form %d unknown", out_form);
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
     if (batch == 0) return MBQC_OK;
     SvBatchParams p;
@@ -476,7 +490,7 @@ extern "C" int mbqc_run_batch_sv_host_submit(const mbqc_plan* plan, const double
     if (!d_work || work_bytes < mbqc_host_workspace_bytes(plan, batch, out_form))
         return fail(MBQC_E_ARG, "d_work too small: need %lld bytes", (long long)mbqc_host_workspace_bytes(plan, batch, out_form));
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
     PipeState* ps = nullptr;
     int device = 0;
@@ -630,7 +644,7 @@ int mbqc_run_batch_sv_f32(const mbqc_plan* plan, const double* d_angles, int64_t
     if (plan->tab.window > MBQC_MAX_WINDOW_REG)
         return fail(MBQC_E_UNSUPPORTED, "complex64 mode covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, plan->tab.window);
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
     if (batch == 0) return MBQC_OK;
     SvBatchParams p;
@@ -819,7 +833,7 @@ int check_grad_plan(const mbqc_plan* plan, const void* d_target, double shift) {
     if (w > MBQC_MAX_WINDOW_REG)
         return fail(MBQC_E_UNSUPPORTED, "fused gradient covers window <= %d (got %d)", MBQC_MAX_WINDOW_REG, w);
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_ARG, "step %d: only the XY plane is supported on the state-vector path", m);
     return MBQC_OK;
 }
@@ -838,7 +852,7 @@ static int fill_sample_params(SampleParams& sp, const mbqc_plan* plan, int64_t b
     if (outcome_mode == MBQC_OUTCOMES_FORCED && !d_outcomes && batch > 0 && plan->tab.n_steps > 0)
         return fail(MBQC_E_ARG, "forced outcomes need d_outcomes");
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_ARG, "step %d: byproduct corrections are implemented for the XY plane only", m);
     memset(&sp, 0, sizeof(sp));
     sp.ff = (const FeedForwardDev*)plan->d_ff;
@@ -863,7 +877,7 @@ int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int
     if (w > MBQC_MAX_WINDOW_SMEM_SV)
         return fail(MBQC_E_UNSUPPORTED, "sampled runs cover window <= %d (got %d)", MBQC_MAX_WINDOW_SMEM_SV, w);
     for (int m = 0; m < plan->tab.n_steps; ++m)
-        if (plan->h_steps[m].plane != MBQC_PLANE_XY)
+        if (plan->h_steps[m].plane != MBQC_PLANE_XY || plan->h_steps[m].cond_mask)
             return fail(MBQC_E_UNSUPPORTED, "the state-vector path measures in the XY plane only (np_simulator_sv.py:54-59)");
     SampleParams sp;
     if ((rc = fill_sample_params(sp, plan, batch, seed, sample_offset, outcome_mode, correct, d_outcomes,

@@ -550,6 +550,8 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
             if (plan->h_steps[m].angle_idx >= 0) ++uses[plan->h_steps[m].angle_idx];
         for (int c = 0; c < T; ++c)
             if (uses[c] != 1) return 0;
+        // row-major staging of the CTA's rows in the dead output / prefix regions before the bulk copies
+        if (2 * (((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) < (size_t)T) return 0;
     }
     cudaKernel_t kern = get_kernel(plan, v);
     if (!kern) return 0;

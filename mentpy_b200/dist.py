@@ -158,7 +158,9 @@ class ReplicatedResult:
 
         if self._dst[self.copy] is None:
             off = self.copy * self.nbytes
-            order = [self.ptrs[self.rank] + off] + [q + off for r, q in enumerate(self.ptrs) if r != self.rank]
+            # local copy first, then the peers in ring order from this rank: in every phase of the
+            # producing kernels the sender -> receiver map is a permutation (no GPU is everyone's target)
+            order = [self.ptrs[(self.rank + k) % self.world] + off for k in range(self.world)]
             self._dst[self.copy] = (C.c_void_p * len(order))(*order)
         return self._dst[self.copy], self.world
 

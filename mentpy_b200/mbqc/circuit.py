@@ -18,7 +18,7 @@ import numpy as np
 
 from .causal_flow import Flow, check_if_flow, find_cflow
 from .graph import GraphState, contract_into, disjoint_union
-from .measurement import Ment
+from .measurement import ControlMent, Ment
 
 __all__ = ["MBQCircuit", "merge", "hstack", "vstack"]
 
@@ -104,26 +104,30 @@ class MBQCircuit:
     # -- derived tables -------------------------------------------------------------------------
     def _refresh(self) -> None:
         """Rebuild trainable / plane / output tables from the measurement table (:325-373)."""
-        trainable, planes, q_out, c_out = [], {}, [], []
+        trainable, controlled, planes, q_out, c_out = [], [], {}, [], []
         for v, m in self._measurements.items():
             if m is None:
                 planes[v] = ""
                 if v in self._output_nodes:
                     q_out.append(v)
                 continue
+            if isinstance(m, ControlMent):
+                controlled.append(v)
             if m.is_trainable():
                 trainable.append(v)
-            planes[v] = m.plane
+            planes[v] = m.plane() if isinstance(m, ControlMent) else m.plane  # ControlMent: plane of the false branch
             owned = copy.deepcopy(m)
             owned.node_id = v
             self._measurements[v] = owned
             if v in self._output_nodes:
                 c_out.append(v)
         self._trainable_nodes = trainable
-        self._controlled_nodes = []
+        self._controlled_nodes = controlled
         self._planes = planes
         self._quantum_output_nodes = q_out
         self._classical_output_nodes = c_out
+        if controlled and getattr(self, "_partial_order", None) is not None:
+            self._partial_order = _order_with_conditions(controlled, self._measurements, self._partial_order)
 
     def calculate_order(self) -> List[int]:
         """Layers descending (count of strictly-later nodes), ties in node order, inputs first."""
@@ -171,6 +175,9 @@ class MBQCircuit:
             raise ValueError(f"Value {ment} is not a Measurement object.")
         self._measurements[node] = ment
         self._refresh()
+        if isinstance(ment, ControlMent):
+            # the controlled node must come after the nodes its condition reads (mbqcircuit.py:191-193)
+            self._measurement_order = self.calculate_order()
 
     def __delitem__(self, node) -> None:
         if node not in self._graph:
@@ -337,3 +344,21 @@ def merge(a: MBQCircuit, b: MBQCircuit, along=[]) -> MBQCircuit:
         g = contract_into(g, keep=j + off, gone=i)
         del table[i]
     return MBQCircuit(g, inputs, outputs, measurements=table)
+
+
+def _order_with_conditions(controlled, measurements, base):
+    """Partial order extended by the outcome dependencies of the controlled measurements
+    (mbqcircuit.py:614-633): whatever precedes (or is) a condition node of c precedes everything from c on."""
+    def order(i, j):
+        for c in controlled:
+            cond = measurements[c].condition
+            reads = cond.cond_nodes  # a plain bool condition has none: AttributeError, as in the reference
+            i_feeds_c = i in reads or any(base(i, r) for r in reads)
+            j_from_c = j == c or base(c, j)
+            if i_feeds_c and j_from_c and i != j:
+                return True
+            if j in reads and i == c:
+                return False
+        return base(i, j)
+
+    return order

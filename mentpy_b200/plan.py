@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
+from .mbqc.measurement import ControlMent, condition_reads
 
 _PLANE_CODE = {"XY": _lib.PLANE_XY, "X": _lib.PLANE_XY, "Y": _lib.PLANE_XY,
                "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ, "Z": _lib.PLANE_Z, "XYZ": _lib.PLANE_XYZ}
@@ -38,6 +39,17 @@ class StepRecord:
     nbr_mask: int
     dropped_neighbours: List[int] = field(default_factory=list)
     fixed_z: float = 0.0    # plane XYZ: Z component of the measurement axis
+    # outcome-controlled measurement (ControlMent): the fields above describe the FALSE branch, alt_* the
+    # TRUE branch; cond_mask selects earlier outcomes (bit j = j+1 measurements back), cond_table is the
+    # condition's truth table over them (lowest selected bit = lowest index bit); column = the node's angle column
+    cond_mask: int = 0
+    cond_table: int = 0
+    alt_plane: int = 0
+    alt_angle_idx: int = -1
+    alt_cos: float = 1.0
+    alt_sin: float = 0.0
+    alt_z: float = 0.0
+    column: int = -1
 
 
 @dataclass
@@ -95,7 +107,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
     if not mixed:
         for v in nodes:
             m = circuit[v]
-            if m is not None and m.plane not in ("X", "Y", "XY"):
+            if m is not None and (isinstance(m, ControlMent) or m.plane not in ("X", "Y", "XY")):
                 raise ValueError(f"Node {v} has plane {m.plane}, but only XY plane is supported.")
 
     if schedule is not None:
@@ -166,8 +178,74 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
 
     trainable = list(circuit.trainable_nodes)
     steps: List[StepRecord] = []
+
+    def branch_spec(node, b):
+        """(plane code, angle column | -1, fixed angle, cos, sin, z) of one plain measurement."""
+        if b.plane not in _PLANE_CODE or b.plane == "Z":
+            raise NotImplementedError(f"Node {node}: plane {b.plane} is not supported in a controlled measurement.")
+        if b.plane == "XYZ":
+            if not isinstance(b.angle, tuple):
+                raise TypeError(f"Invalid argument type. Expected tuple but got {float if b.angle is None else type(b.angle)}")
+            t1, t2 = b.angle
+            return (_PLANE_CODE["XYZ"], -1, b.angle, float(np.cos(t1) * np.cos(t2)), float(np.sin(t1) * np.cos(t2)),
+                    float(np.sin(t2)))
+        if b.is_trainable():
+            return _PLANE_CODE[b.plane], trainable.index(node), None, 1.0, 0.0, 0.0
+        fc, fs = _fixed_cos_sin(b.plane, b.angle)
+        return _PLANE_CODE[b.plane], -1, b.angle, fc, fs, 0.0
+
     for m, node in enumerate(schedule_measure):
         ment = circuit[node]
+        ctl = None
+        if isinstance(ment, ControlMent):
+            # controlled_ment.py:96-113 through np_simulator_dm.py:307-346: only the density-matrix simulator
+            # evaluates conditions, and only for nodes that receive an angle (a fixed-fixed ControlMent raises)
+            if not mixed:
+                raise ValueError(f"Node {node} has plane {ment.plane}, but only XY plane is supported.")
+            if node not in trainable:
+                raise ValueError("ControlledMent is not trainable, so angle must be None.")
+            cond = ment.condition
+            reads = condition_reads(cond)
+            pos = {}
+            for r in reads:
+                if r not in schedule_measure[:m]:
+                    raise ValueError(f"Node {node}: the condition reads node {r}, which is not measured before it.")
+                pos[r] = m - 1 - schedule_measure.index(r)
+            if len(reads) > 5 or any(d > 31 for d in pos.values()):
+                raise NotImplementedError(f"Node {node}: a condition reads at most 5 outcomes, at most 32 measurements back.")
+            by_bit = sorted(reads, key=lambda r: pos[r])  # lowest history bit first = lowest table-index bit
+            table = 0
+            for idx in range(1 << len(by_bit)):
+                if cond({r: (idx >> i) & 1 for i, r in enumerate(by_bit)}):
+                    table |= 1 << idx
+            if not ment.true_ment.is_trainable():
+                # taking a fixed true branch makes the reference raise: ControlMent.get_povm hands the node's
+                # angle to it (controlled_ment.py:109-111 -> ment.py:222-226); refused here for every sample
+                shown = ment.true_ment.angle
+                raise ValueError(f"Measurement has a fixed angle of {round(shown, 4) if isinstance(shown, (int, float)) else shown}")
+            f_spec, t_spec = branch_spec(node, ment.false_ment), branch_spec(node, ment.true_ment)
+            if not by_bit:  # constant condition: a plain step
+                ment = ment.true_ment if table & 1 else ment.false_ment
+            else:
+                ctl = (sum(1 << pos[r] for r in by_bit), table, f_spec, t_spec)
+        if ctl is not None:
+            mask_c, table, (pl, aidx, fixed, fc, fs, fz), (apl, aaidx, _af, afc, afs, afz) = ctl
+            slot = slot_of.pop(node)
+            done = m + 1
+            append = done + w <= n_nodes
+            new_node, mask, dropped = None, 0, []
+            if append:
+                new_node = schedule[done + w - 1]
+                for nb in circuit.graph.neighbors(new_node):
+                    if nb in slot_of:
+                        mask |= 1 << slot_of[nb]
+                    elif nb in schedule[:done]:
+                        dropped.append(nb)
+                slot_of[new_node] = slot
+            steps.append(StepRecord(node, slot, aidx, pl, fixed, fc, fs, append, new_node, mask, dropped, fz,
+                                    cond_mask=mask_c, cond_table=table, alt_plane=apl, alt_angle_idx=aaidx,
+                                    alt_cos=afc, alt_sin=afs, alt_z=afz, column=trainable.index(node)))
+            continue
         plane = ment.plane
         if plane not in _PLANE_CODE:
             raise NotImplementedError(f"Node {node}: plane {plane} is not supported on the CUDA path.")
@@ -357,6 +435,9 @@ class DevicePlan:
             arr[i].fixed_cos, arr[i].fixed_sin = st.fixed_cos, st.fixed_sin
             arr[i].nbr_mask = st.nbr_mask
             arr[i].fixed_z = st.fixed_z
+            arr[i].cond_mask, arr[i].cond_table = st.cond_mask, st.cond_table
+            arr[i].alt_plane, arr[i].alt_angle_idx = st.alt_plane, st.alt_angle_idx
+            arr[i].alt_cos, arr[i].alt_sin, arr[i].alt_z = st.alt_cos, st.alt_sin, st.alt_z
         out_slot = plan.output_slot if output_slot is None else output_slot
         in_arr = (C.c_int32 * max(len(plan.input_slot), 1))(*plan.input_slot)
         cz_arr = (C.c_uint64 * plan.window)(*plan.init_cz_mask)

@@ -151,6 +151,8 @@ class _CudaPatternBase(BaseSimulator):
             wmax = _lib.MAX_WINDOW_REG if self.mixed else _lib.MAX_WINDOW_SMEM_SV
             if self.plan.window > wmax:
                 raise NotImplementedError(f"force0=False covers window_size <= {wmax}")
+            if any(st.cond_mask for st in self.plan.steps):
+                raise NotImplementedError("force0=False does not cover outcome-controlled measurements (ControlMent).")
             feedforward(mbqcircuit, self.plan)
         if input_state is None:
             n_in = len(mbqcircuit.input_nodes)
@@ -360,7 +362,11 @@ class _CudaPatternBase(BaseSimulator):
         st = self.plan.steps[self.current_measurement]
         if st.plane == _lib.PLANE_Z:
             return st  # angle-free
-        if st.angle_idx >= 0:
+        if st.cond_mask:  # controlled node: its angle column, whichever branch ends up using it
+            if angle is None:
+                raise ValueError("Measurement is trainable, please provide an angle.")
+            self._angles_seen[st.column] = float(angle)
+        elif st.angle_idx >= 0:
             if angle is None:
                 raise ValueError("Measurement is trainable, please provide an angle.")
             self._angles_seen[st.angle_idx] = float(angle)

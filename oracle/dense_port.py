@@ -208,6 +208,11 @@ class _DenseBase:
             raise ValueError("No more measurements to be done.")
         node = self.schedule_measure[self.cm]
         plane, _ = self.pat.measurements[node]
+        if node in self.pat.controls:
+            # controlled_ment.py:96-113: the condition picks the branch; a fixed branch ignores the angle
+            plane, fixed = self.pat.control_branch(node, self.outcomes)
+            if fixed is not None:
+                angle = fixed
         outcome = self._project(plane, angle)
         self.outcomes[node] = outcome
         self.cm += 1

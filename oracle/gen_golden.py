@@ -172,11 +172,67 @@ def xyz_cases(mp):
         json.dump({"generator": "oracle/gen_golden.py (--only xyz)", "source": "bestquark/mentpy (unmodified)", "cases": cases}, f)
 
 
+# the controlled measurements of the fixture below, rebuilt identically on the reference's classes (here)
+# and on the product's (tests): name -> builder(package, ControlMent class) -> circuit
+CONTROL_CASES = {
+    "false_branch_x": lambda m, C: _with(m.templates.linear_cluster(5), lambda gs: gs.__setitem__(2, C(gs[0].outcome, None, "XY", 0, "X"))),
+    "true_branch_trainable": lambda m, C: _with(m.templates.linear_cluster(6), lambda gs: gs.__setitem__(3, C(gs[1].outcome == 0, None, "XY", 0.4, "XY"))),
+    "two_reads_xz": lambda m, C: _with(m.templates.grid_cluster(2, 4), lambda gs: gs.__setitem__(5, C(~gs[1].outcome + gs[4].outcome, None, "XZ", 0.3, "XY"))),
+    "reordered_yz": lambda m, C: _with(m.templates.grid_cluster(2, 4), lambda gs: gs.__setitem__(2, C(gs[6].outcome == 0, None, "YZ", 0.9, "XY"))),
+    "false_branch_xyz": lambda m, C: _with(m.templates.grid_cluster(3, 4), lambda gs: gs.__setitem__(6, C((gs[0].outcome + gs[4].outcome) == 1, None, "XZ", (0.5, 1.0), "XYZ"))),
+    "two_controls": lambda m, C: _with(m.templates.grid_cluster(2, 5), lambda gs: (gs.__setitem__(2, C(gs[0].outcome, None, "XY", 1.1, "XY")),
+                                                                                   gs.__setitem__(7, C((gs[5].outcome * gs[1].outcome) == 0, None, "YZ", 0.2, "XZ")))),
+    "real_outcome_1": lambda m, C: _with(m.templates.many_wires([3, 3]), lambda gs: gs.__setitem__(1, C(gs[0].outcome, None, "XY", 0, "X"))),
+}
+
+
+def _with(gs, f):
+    f(gs)
+    return gs
+
+
+def control_cases(mp):
+    """2e. outcome-controlled measurements (operators/controlled_ment.py:14-113) on the density-matrix
+    backend.  Under force0 outcomes are 0 unless prob0 < 1e-4, so the conditions are chosen to reach
+    both branches; the last case re-uses the angles of the outcome-1 fixture, where node 0 really
+    yields 1 and the condition fires on it."""
+    import warnings
+
+    from mentpy.operators import ControlMent
+
+    quirk = json.load(open(os.path.join(GOLDEN, "dm_outcome_quirk.json")))
+    cases = []
+    for seed, (name, builder) in enumerate(CONTROL_CASES.items(), start=50):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gs = builder(mp, ControlMent)
+        T = len(gs.trainable_nodes)
+        angles = np.random.default_rng(seed).uniform(0, 2 * np.pi, T)
+        inp, kw = None, {}
+        if name == "real_outcome_1":
+            angles = np.asarray(quirk["runs"][0]["angles"])
+            q = quirk["input_state"]
+            inp = (np.asarray(q["re"]) + 1j * np.asarray(q["im"])).reshape(q["shape"])
+            kw = {"window_size": quirk["window_size"]}
+        elif seed % 2:
+            inp = haar_state(len(gs.input_nodes), seed)
+        ps = mp.PatternSimulator(gs, input_state=inp, backend="numpy-dm", **kw)
+        out = ps.run(angles)
+        cases.append({"name": name, "seed": seed, "window_size": int(ps.window_size),
+                      "measurement_order": [int(v) for v in gs.measurement_order],
+                      "trainable_nodes": [int(v) for v in gs.trainable_nodes],
+                      "pattern": PatternData.from_circuit(gs).to_json(), "angles": angles.tolist(),
+                      "input_state": None if inp is None else cplx(inp), "output": cplx(out),
+                      "outcomes": {str(k): int(v) for k, v in ps.outcomes.items()}})
+    with open(os.path.join(GOLDEN, "dm_controlled.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py (--only ctl)", "source": "bestquark/mentpy (unmodified)", "cases": cases}, f)
+
+
 def main():
     mp = import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
-    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "xyz":
-        xyz_cases(mp)
+    if "--only" in sys.argv:
+        {"xyz": xyz_cases, "ctl": control_cases}[sys.argv[sys.argv.index("--only") + 1]](mp)
         return
 
     # 1. structure tables (integer indexing must be bit-exact)
@@ -264,6 +320,7 @@ def main():
         json.dump({"generator": "oracle/gen_golden.py", "source": "bestquark/mentpy (unmodified)", "cases": zcases}, f)
 
     xyz_cases(mp)
+    control_cases(mp)
 
     # 3. gradient + optimiser known answers: grid_cluster(4,5), cost 1 - <t|rho|t>
     gs = mp.templates.grid_cluster(4, 5)

@@ -245,7 +245,23 @@ def run_dm_batch(pat, angles, input_states=None, window_size=1, schedule=None,
             rho = apply_channel_first(rho, kr)
         D = rho.shape[1]
         h = D // 2
-        p00, p11, p10 = _projector(plane, th)
+        if node in pat.controls:
+            # controlled_ment.py:96-113: per row, the condition on the outcomes so far picks the branch
+            ctl = pat.controls[node]
+            col = angles[:, pat.trainable_nodes.index(node)]
+            idx = np.zeros(B, dtype=int)
+            for i, r in enumerate(ctl["reads"]):
+                idx |= (outcomes[:, sched_meas.index(r)].astype(int) & 1) << i
+            take = np.asarray(ctl["table"], dtype=bool)[idx]
+            parts = []
+            for pl, fixed in (ctl["false"], ctl["true"]):
+                if pl in ("X", "Y"):
+                    pl, fixed = "XY", (0.0 if pl == "X" else np.pi / 2)
+                ang = col if fixed is None else (np.tile(np.asarray(fixed, dtype=float), (B, 1)) if pl == "XYZ" else np.full(B, fixed))
+                parts.append(_projector(pl, ang))
+            p00, p11, p10 = (np.where(take, t, f) for f, t in zip(*parts))
+        else:
+            p00, p11, p10 = _projector(plane, th)
         r00, r01, r10, r11 = rho[:, :h, :h], rho[:, :h, h:], rho[:, h:, :h], rho[:, h:, h:]
         sig0 = (p00[:, None, None] * r00 + p11[:, None, None] * r11
                 + p10[:, None, None] * r01 + np.conj(p10)[:, None, None] * r10)

@@ -751,3 +751,49 @@ def test_plane_z_sample_mode():
         ref1, _, _ = matrix_free.run_dm_batch(pat, ang[None], input_states=ins1, window_size=c["window_size"],
                                               return_outcomes=True, mode="sample", z_outcomes=np.asarray(rec)[None])
         assert dm_distance(st, ref1[0]) < 1e-10
+
+
+def test_controlled_measurements_match_reference_golden():
+    """Outcome-controlled measurements (operators/controlled_ment.py:14-113) on the density-matrix
+    kernels (register kernel for window <= 5, shared-memory kernel at window 6): single runs against
+    outputs recorded from the reference -- including the condition fired by a real outcome 1 --,
+    batches and a channel against the oracle, and the stateful API."""
+    import warnings
+
+    from oracle.gen_golden import CONTROL_CASES
+
+    for c in load_golden("dm_controlled.json")["cases"]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gs = CONTROL_CASES[c["name"]](mb, mb.ControlMent)
+        inp = None if c["input_state"] is None else from_cplx(c["input_state"])
+        ang = np.asarray(c["angles"])
+        want = from_cplx(c["output"])
+        pat = PatternData.from_circuit(gs)
+        windows = [c["window_size"]] + ([6] if len(gs.graph.nodes()) >= 8 and c["name"] != "real_outcome_1" else [])
+        for w in windows:
+            ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=w)
+            got = ps.run(ang)
+            if w == c["window_size"]:
+                assert got.shape == want.shape and dm_distance(got, want) < 1e-10, c["name"]
+                assert {str(k): v for k, v in ps.outcomes.items()} == c["outcomes"]
+            rows = np.random.default_rng(c["seed"]).uniform(0, 2 * np.pi, (23, len(ang)))
+            rows[3] = ang
+            ins = None if inp is None else np.tile(inp, (23, 1))
+            for noise in ({}, {"circuit_noise": "amplitude_damping", "p": 0.15}):
+                pn = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=w, **noise)
+                batch, oc = pn.run_batch(rows, return_outcomes=True)
+                kw = {k: v for k, v in noise.items() if k != "circuit_noise"}
+                ref, roc = matrix_free.run_dm_batch(pat, rows, input_states=ins, window_size=w, noise=noise.get("circuit_noise"),
+                                                    noise_kwargs=kw, return_outcomes=True)
+                assert dm_distance(batch, ref) < 1e-10 and np.array_equal(oc, roc), (c["name"], w, noise)
+        ps = mb.PatternSimulator(gs, input_state=inp, backend="cuda-dm", window_size=c["window_size"])
+        ps.reset()
+        for node in ps.schedule_measure:  # step-by-step API
+            a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
+            st, o = ps.measure(a)
+            assert o == c["outcomes"][str(node)]
+        final = ps.reorder_qubits(st, ps.current_simulated_nodes(), gs.quantum_output_nodes)
+        assert dm_distance(final, want) < 1e-10
+    with pytest.raises(NotImplementedError):
+        mb.PatternSimulator(gs, backend="cuda-dm", force0=False)

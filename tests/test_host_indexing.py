@@ -130,3 +130,45 @@ def test_spturb_trainable_nodes(n_layer, n_qubits, periodic):
     assert spt.flow is None and spt.measurement_order is None   # no causal flow: needs a user schedule
     with pytest.raises(ValueError):
         mb.templates.spturb(3, 1)
+
+
+def test_controlled_measurements_host_layer():
+    """ControlMent / MentOutcome (operators/controlled_ment.py:14-113, ment.py:13-120): the measurement
+    order with the outcome dependencies, the trainable nodes and the tabulated conditions equal what
+    the reference produced (tests/golden/dm_controlled.json); lowering refuses what the reference's
+    simulator cannot run."""
+    import warnings
+
+    import mentpy_b200 as mb
+    from mentpy_b200.plan import lower
+    from oracle.gen_golden import CONTROL_CASES
+    from oracle.pattern_data import PatternData
+
+    for c in load_golden("dm_controlled.json")["cases"]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gs = CONTROL_CASES[c["name"]](mb, mb.ControlMent)
+        assert gs.measurement_order == c["measurement_order"]
+        assert gs.trainable_nodes == c["trainable_nodes"]
+        import json
+        assert json.loads(json.dumps(PatternData.from_circuit(gs).to_json())) == c["pattern"]
+        plan = lower(gs, window_size=c["window_size"], mixed=True)
+        for st in plan.steps:
+            if st.node in gs.controlled_nodes:
+                assert st.cond_mask and st.column == gs.trainable_nodes.index(st.node) and st.alt_angle_idx == st.column
+        with pytest.raises(ValueError, match="only XY plane"):
+            lower(gs, window_size=c["window_size"])  # state-vector path: like every non-XY node
+    gs = mb.templates.linear_cluster(5)
+    m = gs[0].outcome
+    assert (~m)({0: 0}) and (m + 1)({0: 0}) and not (m * 1)({0: 0}) and ((m == 0) ^ m)({0: 1})
+    gs[2] = mb.ControlMent(gs[0].outcome, 0.7, "XY", 0, "X")  # nothing trainable: the reference raises on run
+    with pytest.raises(ValueError, match="not trainable"):
+        lower(gs, mixed=True)
+    gs[2] = mb.ControlMent(gs[0].outcome, 0.7, "XY", None, "XY")  # fixed TRUE branch: get_povm hands it the angle
+    with pytest.raises(ValueError, match="fixed angle"):
+        lower(gs, mixed=True)
+    g2 = mb.templates.grid_cluster(2, 4)
+    g2[2] = mb.ControlMent(g2[6].outcome == 0, None, "XY", 0, "X")  # reads a node measured later: the order adapts
+    assert g2.measurement_order.index(6) < g2.measurement_order.index(2)
+    with pytest.raises(AttributeError):
+        gs[2] = mb.ControlMent(True, None, "XY", 0, "X")  # plain bool: mbqcircuit.py:617 fails the same way
