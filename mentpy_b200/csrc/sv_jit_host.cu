@@ -138,7 +138,7 @@ std::string make_preamble(const mbqc_plan* plan, Variant v) {
             lp.n_full, lp.n_angles, lp.n_out, lp.n_in);
     appendf(s, "#define JCTA %d\n#define JMINBLOCKS %d\n#define JOUT %d\n#define JPHASE %s\n", v.cta, minblocks, v.out_mode,
             v.out_mode == MBQC_LEAN_OUT_DM ? "false" : "true");
-    if (v.kind == kKindGrad) appendf(s, "#define JPUSH %d\n", v.out_mode == 1 ? 1 : 0);  // out_mode 1: replicated result
+    if (v.kind == kKindGrad) appendf(s, "#define JPUSH %d\n", v.out_mode);  // 1..3: replicated result (stores | bulk copies, full wait | read wait)
     appendf(s, "#define JTRIG_INV %a\n#define JTRIG_C1 %a\n#define JTRIG_C2 %a\n", (double)MBQC_TRIG128_INV, (double)MBQC_TRIG128_C1,
             (double)MBQC_TRIG128_C2);
     std::string col = "constexpr unsigned kColOfs[JM] = {", sgn = "constexpr unsigned kSignMask[JM] = {",
@@ -540,8 +540,18 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
         const char* e = getenv("MBQC_GRAD_CTA");  // 64 | 128 (kernel work)
         return (e && atoi(e) == 64) ? 64 : 128;
     }();
+    static const int push_mode = [] {
+        const char* e = getenv("MBQC_PUSH_MODE");  // stores | tma | tma_read (kernel work)
+        if (e && !strcmp(e, "stores")) return 1;
+        if (e && !strcmp(e, "tma")) return 2;
+        if (e && !strcmp(e, "tma_read")) return 3;
+        return 0;
+    }();
     const bool push = p.push_n > 0;
-    Variant v{push ? 1 : 0, cta_env, kKindGrad};
+    // measured (profiles/r02_c4_push_modes.jsonl, exposed time over the local-only kernel): one bulk copy
+    // per GPU wins up to 4 GPUs (+13 / +24 us vs +21 / +36 us at 2 / 4 GPUs), plain stores at 8 (+72 vs +90 us)
+    const int pmode = push_mode ? push_mode : (p.push_n > 4 ? 1 : 3);
+    Variant v{push ? pmode : 0, cta_env, kKindGrad};
     const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
     if (smem > 200 * 1024 || T > 64) return 0;
     if (push) {  // the gradient is staged in the (cos, sin) slots: every column must belong to exactly one measurement
@@ -683,7 +693,7 @@ int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t 
     // 200 -> the density-matrix kernel mbqc_jit_dm
     Variant v{out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : MBQC_LEAN_OUT_DIRECT, cta == 64 ? 64 : 128};
     if (out_form == 100) v = Variant{0, 128, kKindGrad};
-    if (out_form == 101) v = Variant{1, 128, kKindGrad};  // replicated-result form of the gradient kernel
+    if (out_form >= 101 && out_form <= 103) v = Variant{out_form - 100, 128, kKindGrad};  // replicated-result forms of the gradient kernel
     if (out_form == 200) {
         DmJitShape sh;
         if (!dm_jit_shape(plan, sh, cta == 1 || cta == 2 ? cta : 0)) return 0;  // cta 1 / 2: register slots per lane

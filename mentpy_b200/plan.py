@@ -68,9 +68,12 @@ class LoweredPlan:
     mixed: bool
     first_window: List[int]
     first_slots: Dict[int, int] = field(default_factory=dict)
+    dev_windows: Optional[List[List[int]]] = None  # dev_mode: window content after every measurement
 
     def window_nodes_after(self, n_done: int) -> List[int]:
         """Reference window content (position 0 first) after n_done measurements."""
+        if self.dev_windows is not None:
+            return list(self.dev_windows[n_done])
         return self.schedule[n_done: n_done + self.window]
 
     def slot_of_after(self, n_done: int) -> Dict[int, int]:
@@ -92,8 +95,44 @@ def _fixed_cos_sin(plane: str, angle):
     return float(np.cos(angle)), float(np.sin(angle))
 
 
+def _dev_mode_order(circuit, schedule, w, n_meas, wires):
+    """Measurement sequence and window contents of the reference's dev_mode scheduling
+    (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201): measure the FIRST node of the window
+    that has no later neighbour in its wire, or whose first later wire-neighbour is already in the
+    window; drop it from the window and append the next node of the schedule."""
+    if wires is None:
+        raise TypeError("dev_mode needs the wires of the pattern (wires=[[...], ...])")
+    n_nodes = len(schedule)
+
+    def later_in_wire(node):
+        for wire in wires:
+            if node in wire:
+                return [v for v in wire if circuit.graph.has_edge(node, v) and v > node]
+        raise ValueError(f"Node {node} is in no wire.")
+
+    win, seq, windows = list(schedule[:w]), [], [list(schedule[:w])]
+    while len(seq) < n_meas:
+        pick = None
+        for node in win:
+            fut = later_in_wire(node)
+            if not fut or fut[0] in win:
+                pick = node
+                break
+        if pick is None:
+            raise ValueError("WTF")  # the reference's own message (np_simulator_sv.py:268)
+        if circuit[pick] is None:
+            raise ValueError(f"dev_mode scheduling reaches node {pick}, which has no measurement.")
+        seq.append(pick)
+        win.remove(pick)
+        if len(seq) + w <= n_nodes:
+            win.append(schedule[len(seq) + w - 1])
+        windows.append(list(win))
+    return seq, windows
+
+
 def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = None,
-          mixed: bool = False, slot_order: str = "msb", shard_bits: int = 0) -> LoweredPlan:
+          mixed: bool = False, slot_order: str = "msb", shard_bits: int = 0,
+          dev_mode: bool = False, wires=None) -> LoweredPlan:
     """slot_order: "msb" puts window position p at slot w-1-p (reference layout; the measured slots
     then cycle w-1, w-2, ..., 0 and the register kernel takes its unrolled path); "lsb" puts it at
     slot p (exercises the kernels' generic slot path; results are identical); "shard-last" (with
@@ -135,7 +174,12 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
     if sorted(schedule) != sorted(nodes):
         raise ValueError("The schedule must visit every node of the graph exactly once.")
     n_meas = len(schedule_measure)
-    if schedule[:n_meas] != schedule_measure:
+    dev_windows = None
+    if dev_mode:
+        # the window decides the order: the nodes enter in schedule order, the measured one is chosen
+        # by the wire rule (any window position), so unmeasured outputs may sit anywhere
+        schedule_measure, dev_windows = _dev_mode_order(circuit, schedule, window_size, n_meas, wires)
+    elif schedule[:n_meas] != schedule_measure:
         # the reference would measure window position 0 with another node's Ment here
         # (np_simulator_sv.py:169-172 vs :130-135); refuse instead of reproducing garbage
         raise ValueError("Unmeasured output nodes must come last in the schedule.")
@@ -239,7 +283,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
                 for nb in circuit.graph.neighbors(new_node):
                     if nb in slot_of:
                         mask |= 1 << slot_of[nb]
-                    elif nb in schedule[:done]:
+                    elif nb in schedule_measure[:done]:
                         dropped.append(nb)
                 slot_of[new_node] = slot
             steps.append(StepRecord(node, slot, aidx, pl, fixed, fc, fs, append, new_node, mask, dropped, fz,
@@ -279,13 +323,13 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
             for nb in circuit.graph.neighbors(new_node):
                 if nb in slot_of:
                     mask |= 1 << slot_of[nb]
-                elif nb in schedule[:done]:
+                elif nb in schedule_measure[:done]:
                     dropped.append(nb)  # already measured: the reference silently skips this CZ
             slot_of[new_node] = slot
         steps.append(StepRecord(node, slot, angle_idx, _PLANE_CODE[plane], fixed, fc, fs, append,
                                 new_node, mask, dropped, fz))
 
-    remaining = schedule[n_meas:]
+    remaining = schedule[n_meas:] if not dev_mode else [v for v in schedule if v not in schedule_measure]
     # np_simulator_dm.py:267-273 reorders to quantum_output_nodes; np_simulator_sv.py:286-290 leaves
     # the window order alone when it already equals quantum_output_nodes and otherwise reorders to
     # output_nodes (the two lists differ in order for merged circuits) -- reproduced as is
@@ -300,7 +344,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
         raise NotImplementedError(f"more than {_lib.MAX_IO} input/output qubits")
     return LoweredPlan(w, n_nodes, schedule, schedule_measure, steps, list(circuit.input_nodes),
                        input_slot, init_cz, out_order, output_slot, len(trainable), mixed,
-                       first_window, first_slots)
+                       first_window, first_slots, dev_windows)
 
 
 @dataclass

@@ -139,11 +139,11 @@ class _CudaPatternBase(BaseSimulator):
         # outcomes and applies the flow corrections: see sample_batch
         self.seed = int(kwargs.pop("seed", 0))
         self._shots_done = 0
-        if self.dev_mode:
-            raise NotImplementedError("dev_mode scheduling is not supported by the CUDA backends.")
         self._noise = self._parse_noise(kwargs)
+        # dev_mode (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201): the window picks the measured node
+        # by the wire rule; it only changes the order of the steps, which the lowering works out up front
         self.plan: LoweredPlan = lower(mbqcircuit, self.window_size, self.schedule, mixed=self.mixed,
-                                       slot_order=self._slot_order)
+                                       slot_order=self._slot_order, dev_mode=bool(self.dev_mode), wires=self.wires)
         self.window_size = self.plan.window
         self.schedule = self.plan.schedule
         self.schedule_measure = self.plan.schedule_measure
@@ -351,7 +351,7 @@ class _CudaPatternBase(BaseSimulator):
         self._shots_done += 1  # a stateful run is one shot of the Philox stream (plane-Z draws, mode="sample")
 
     def current_simulated_nodes(self) -> List[int]:
-        return self.schedule[self.current_measurement: self.current_measurement + self.window_size]
+        return self.plan.window_nodes_after(self.current_measurement)
 
     def current_number_simulated_nodes(self) -> int:
         return min(self.window_size, len(self.mbqcircuit) - self.current_measurement)

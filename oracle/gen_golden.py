@@ -228,11 +228,50 @@ def control_cases(mp):
         json.dump({"generator": "oracle/gen_golden.py (--only ctl)", "source": "bestquark/mentpy (unmodified)", "cases": cases}, f)
 
 
+def flow_wires(gs):
+    """The wires of a pattern with causal flow: the chain input -> f(input) -> ... -> output."""
+    wires = []
+    for v in gs.input_nodes:
+        wire = [int(v)]
+        while wire[-1] not in gs.output_nodes:
+            wire.append(int(gs.flow(wire[-1])))
+        wires.append(wire)
+    return wires
+
+
+def dev_mode_cases(mp):
+    """2f. dev_mode scheduling (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201): the window
+    measures the first node whose next wire-neighbour is present.  For wires of unequal length the
+    order -- and the result -- differs from the plain schedule."""
+    cases = []
+    for spec, seed, w in ((("many_wires", [[3, 4, 2]], {}), 60, None), (("many_wires", [[3, 4, 2]], {}), 61, 5),
+                          (("many_wires", [[2, 3, 3]], {}), 62, 4), (("grid_cluster", [2, 4], {}), 63, 3),
+                          (("many_wires", [[4, 2]], {}), 64, None)):
+        gs = build(mp, spec)
+        wires = flow_wires(gs)
+        T = len(gs.trainable_nodes)
+        angles = np.random.default_rng(seed).uniform(0, 2 * np.pi, T)
+        inp = haar_state(len(gs.input_nodes), seed)
+        kw = {} if w is None else {"window_size": w}
+        rec = {"spec": spec, "seed": seed, "wires": wires, "pattern": PatternData.from_circuit(gs).to_json(),
+               "angles": angles.tolist(), "input_state": cplx(inp)}
+        for backend in ("numpy-sv", "numpy-dm"):
+            ps = mp.PatternSimulator(gs, input_state=inp, backend=backend, dev_mode=True, wires=wires, **kw)
+            out = ps.run(angles)
+            rec["window_size"] = int(ps.window_size)
+            rec[backend] = {"output": cplx(out), "order": [int(k) for k in ps.outcomes.keys()]}
+            plain = mp.PatternSimulator(gs, input_state=inp, backend=backend, **kw).run(angles)
+            rec[backend]["differs_from_plain_schedule"] = bool(np.abs(plain - out).max() > 1e-6)
+        cases.append(rec)
+    with open(os.path.join(GOLDEN, "dev_mode.json"), "w") as f:
+        json.dump({"generator": "oracle/gen_golden.py (--only dev)", "source": "bestquark/mentpy (unmodified)", "cases": cases}, f)
+
+
 def main():
     mp = import_reference()
     os.makedirs(GOLDEN, exist_ok=True)
     if "--only" in sys.argv:
-        {"xyz": xyz_cases, "ctl": control_cases}[sys.argv[sys.argv.index("--only") + 1]](mp)
+        {"xyz": xyz_cases, "ctl": control_cases, "dev": dev_mode_cases}[sys.argv[sys.argv.index("--only") + 1]](mp)
         return
 
     # 1. structure tables (integer indexing must be bit-exact)
@@ -321,6 +360,7 @@ def main():
 
     xyz_cases(mp)
     control_cases(mp)
+    dev_mode_cases(mp)
 
     # 3. gradient + optimiser known answers: grid_cluster(4,5), cost 1 - <t|rho|t>
     gs = mp.templates.grid_cluster(4, 5)

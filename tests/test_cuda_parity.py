@@ -797,3 +797,40 @@ def test_controlled_measurements_match_reference_golden():
         assert dm_distance(final, want) < 1e-10
     with pytest.raises(NotImplementedError):
         mb.PatternSimulator(gs, backend="cuda-dm", force0=False)
+
+
+def test_dev_mode_matches_reference_golden():
+    """dev_mode scheduling (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201) on both CUDA
+    backends against outputs recorded from the reference with wires of unequal length -- where the
+    order, and the result, differ from the plain schedule --, plus batch == single run and the
+    step-by-step API (window content after every measurement)."""
+    for c in load_golden("dev_mode.json")["cases"]:
+        name, args, kw = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kw)
+        inp = from_cplx(c["input_state"])
+        ang = np.asarray(c["angles"])
+        for backend, ref_name in (("cuda-sv", "numpy-sv"), ("cuda-dm", "numpy-dm")):
+            want = from_cplx(c[ref_name]["output"])
+            ps = mb.PatternSimulator(gs, input_state=inp, backend=backend, window_size=c["window_size"], dev_mode=True,
+                                     wires=c["wires"])
+            got = ps.run(ang)
+            assert list(ps.outcomes.keys()) == c[ref_name]["order"]
+            if backend == "cuda-sv":
+                assert got.shape == want.shape and np.abs(got - want).max() < 1e-9
+            else:
+                assert dm_distance(got, want) < 1e-10
+            rows = np.random.default_rng(c["seed"]).uniform(0, 2 * np.pi, (9, len(ang)))
+            rows[4] = ang
+            batch = ps.run_batch(rows) if backend == "cuda-dm" else ps.run_batch(rows, output_form="sv")
+            assert np.abs(batch[4] - got).max() < 1e-12
+            ps.reset()
+            for k, node in enumerate(ps.schedule_measure):
+                assert node in ps.current_simulated_nodes()
+                a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
+                st = ps.measure(a)[0]
+                assert node not in ps.current_simulated_nodes()
+            final = ps.reorder_qubits(st, ps.current_simulated_nodes(), gs.quantum_output_nodes)
+            assert np.abs(final - got).max() < 1e-9
+            if c[ref_name]["differs_from_plain_schedule"]:
+                plain = mb.PatternSimulator(gs, input_state=inp, backend=backend, window_size=c["window_size"]).run(ang)
+                assert np.abs(plain - got).max() > 1e-6

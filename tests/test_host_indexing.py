@@ -172,3 +172,25 @@ def test_controlled_measurements_host_layer():
     assert g2.measurement_order.index(6) < g2.measurement_order.index(2)
     with pytest.raises(AttributeError):
         gs[2] = mb.ControlMent(True, None, "XY", 0, "X")  # plain bool: mbqcircuit.py:617 fails the same way
+
+
+def test_dev_mode_schedule_matches_reference():
+    """dev_mode (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201): the measurement order the
+    window rule produces, for both simulators, against the reference (tests/golden/dev_mode.json)."""
+    from mentpy_b200.plan import lower
+
+    differs = 0
+    for c in load_golden("dev_mode.json")["cases"]:
+        name, args, kw = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kw)
+        for mixed, backend in ((False, "numpy-sv"), (True, "numpy-dm")):
+            plan = lower(gs, mixed=mixed, window_size=c["window_size"], dev_mode=True, wires=c["wires"])
+            assert plan.schedule_measure == c[backend]["order"]
+            assert plan.window_nodes_after(0) == plan.schedule[: plan.window]
+            assert sorted(plan.window_nodes_after(len(plan.steps))) == sorted(plan.output_nodes)
+            differs += plan.schedule_measure != lower(gs, mixed=mixed, window_size=c["window_size"]).schedule_measure
+    assert differs >= 4  # the fixture really exercises orders the plain schedule does not produce
+    with pytest.raises(TypeError):
+        lower(gs, dev_mode=True)
+    with pytest.raises(ValueError, match="in no wire"):
+        lower(gs, dev_mode=True, wires=[[0]])
