@@ -821,7 +821,7 @@ def test_dev_mode_matches_reference_golden():
                 assert dm_distance(got, want) < 1e-10
             rows = np.random.default_rng(c["seed"]).uniform(0, 2 * np.pi, (9, len(ang)))
             rows[4] = ang
-            batch = ps.run_batch(rows) if backend == "cuda-dm" else ps.run_batch(rows, output_form="sv")
+            batch = ps.run_batch(rows) if backend == "cuda-dm" else ps.run_batch(rows, output_form="dm")  # run() defaults to 'dm'
             assert np.abs(batch[4] - got).max() < 1e-12
             ps.reset()
             for k, node in enumerate(ps.schedule_measure):
@@ -829,7 +829,10 @@ def test_dev_mode_matches_reference_golden():
                 a = ang[gs.trainable_nodes.index(node)] if node in gs.trainable_nodes else None
                 st = ps.measure(a)[0]
                 assert node not in ps.current_simulated_nodes()
-            final = ps.reorder_qubits(st, ps.current_simulated_nodes(), gs.quantum_output_nodes)
+            target = gs.quantum_output_nodes if backend == "cuda-dm" else ps.simulator.plan.output_nodes
+            final = ps.reorder_qubits(st, ps.current_simulated_nodes(), target)
+            if backend == "cuda-sv":
+                final = np.outer(final, final.conj())
             assert np.abs(final - got).max() < 1e-9
             if c[ref_name]["differs_from_plain_schedule"]:
                 plain = mb.PatternSimulator(gs, input_state=inp, backend=backend, window_size=c["window_size"]).run(ang)
