@@ -453,6 +453,25 @@ def time_rotating(ctx, make_call, n_buf, reps):
     return float(np.median(ms)) / (reps * n_buf), outs
 
 
+# SURVEY 8d flop model of the DENSE algorithm per unit of work: SV M (8 2^w + c_sincos), DM M 10 4^w
+ALGO_FLOPS = {"C1": (4 * (8 * 4 + 70), "evaluation"), "C3": (55e3, "evaluation"), "C4": (154e3, "gradient (32 evaluations)")}
+
+
+def annotate_fp64(configs, fp64_peak, world):
+    """Second roof of the register-resident configs: algorithmic flops x rate against the
+    measured DFMA peak.  The kernels execute FEWER flops than the dense model (compressed state, linear
+    split of the shift rule), so the algorithmic fraction can exceed what the pipe counters show."""
+    for name, (flops, unit) in ALGO_FLOPS.items():
+        legs = [configs.get(name)] if name != "C3" else [configs.get("C3", {}).get("p0"), configs.get("C3", {}).get("depolarizing_p0.01"), configs.get("C3")]
+        for c in legs:
+            if not c or "value" not in c or "roofline" not in c:
+                continue
+            tf = c["value"] / world * flops / 1e12
+            c["roofline"]["fp64_algorithmic"] = {"flops_per_unit": flops, "unit": unit, "achieved_tflops": tf,
+                                                 "peak_measured_tflops": fp64_peak, "frac": tf / fp64_peak,
+                                                 "note": "per GPU; SURVEY 8d flop model of the dense algorithm"}
+
+
 def config_c1(ctx, peak):
     import mentpy_b200 as mb
 
@@ -840,6 +859,7 @@ def run_gpu_arm(args):
                 configs[name] = {"error": repr(e)[:300]}
                 torch.cuda.empty_cache()
             ctx.barrier()
+        annotate_fp64(configs, fp64_peak, world)
 
     if rank == 0:
         ms_per_step = ms / K

@@ -641,7 +641,8 @@ class CudaSimulatorDM(_CudaPatternBase):
             dim = 2 ** dplan.n_out
             out = torch.empty((batch, dim, dim), dtype=torch.complex128, device=dev)
             status = torch.empty(batch, dtype=torch.int32, device=dev)
-            outc = torch.zeros((batch, max(dplan.n_steps, 1)), dtype=torch.int8, device=dev)
+            # every kernel writes the whole record (no memset launch in front of a ~10 us kernel)
+            outc = torch.empty((batch, max(dplan.n_steps, 1)), dtype=torch.int8, device=dev)
             if expect:
                 zp = torch.empty((batch, max(dplan.n_steps, 1)), dtype=torch.float64, device=dev)
                 _lib.check(lib.mbqc_run_batch_dm_expect(dplan.handle, _ptr(a), _row_stride(a), _ptr(inp), mode,
