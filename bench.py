@@ -540,6 +540,14 @@ def config_c3(ctx, peak):
     return res
 
 
+def gather_path(ps):
+    """How the replicated result of the last psr_gradient_distributed call travels."""
+    cache = getattr(getattr(ps, "simulator", ps), "_replicated_results", {}) or {}
+    mc = any(getattr(r, "mc_ptr", 0) for r in cache.values())
+    return ("multimem stores to ONE NVSwitch multicast address (torch symmetric memory): the switch replicates them, 1/N of the "
+            "per-peer NVLink egress" if mc else "NVLink peer stores / bulk copies into CUDA-IPC mapped copies")
+
+
 def config_c4(ctx, peak):
     """2^20 angle vectors, parameter-shift gradient of grid_cluster(4,5); at N > 1 the vectors are
     split across the ranks (strong scaling) and the gather is INSIDE the timed region: the gradient
@@ -593,7 +601,7 @@ def config_c4(ctx, peak):
            "value": B / (ms * 1e-3), "unit": "gradients/s", "pattern_evals_per_s": B * 2 * T / (ms * 1e-3), "ms": ms,
            "ms_compute_only": ms_local, "scaling": "strong" if ctx.world > 1 else "single GPU",
            "collective": ("none (no collective call): the gradient kernel stores every finished tile of rows into all "
-                          "GPUs' copies of the [B,T] result (NVLink peer stores, CUDA IPC) + one flag barrier "
+                          "GPUs' copies of the [B,T] result -- " + gather_path(ps) + " -- + one flag barrier "
                           "(mbqc_peer_barrier), all inside the timed region" if ctx.world > 1 else "none"),
            "roofline": {"bound": "hbm", "achieved": per / ctx.world / (ms * 1e-3) / 1e9,
                         "frac": per / ctx.world / (ms * 1e-3) / 1e9 / peak,

@@ -250,6 +250,15 @@ int mbqc_psr_grad_batch_push(const mbqc_plan* plan, const double* d_angles, int6
                              const void* d_target, double shift, void* const* d_results, int32_t n_results,
                              int64_t first_row, double* d_cost, int32_t* d_status, void* stream);
 
+/* The replicated result through ONE NVSwitch multicast address (cuMulticast* / torch symmetric memory):
+ * every store is replicated by the switch into all GPUs' copies, so a GPU sends its rows once
+ * instead of once per peer.  MBQC_E_UNSUPPORTED when the specialised kernel is not available
+ * (multicast addresses accept multimem stores only): use mbqc_psr_grad_batch_push then. */
+int mbqc_psr_grad_batch_multicast(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                                  const void* d_inputs, int32_t input_mode, int64_t batch,
+                                  const void* d_target, double shift, void* d_result_multicast,
+                                  int64_t first_row, double* d_cost, int32_t* d_status, void* stream);
+
 /* Data-set averaged cost and its gradient in one call -- the S x 2T pattern evaluations of one
  * optimiser step of the reference's training loop (docs/tutorials/intro-to-mbqml.rst:35-86:
  * cost(x) = mean_s [1 - |<t_s|psi(x; in_s)>|^2], differentiated by gradients/_parameter_shift.py:9-25):

@@ -95,6 +95,9 @@ _SIGNATURES = {
     "mbqc_psr_grad_batch_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                            C.c_int64, C.c_void_p, C.c_double, C.POINTER(C.c_void_p), C.c_int32,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mbqc_psr_grad_batch_multicast": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                                C.c_int64, C.c_void_p, C.c_double, C.c_void_p,
+                                                C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_run_batch_dm_expect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
                                            C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mbqc_plan_set_feedforward": (C.c_int, [C.c_void_p, C.POINTER(FeedForwardC), C.c_int32]),

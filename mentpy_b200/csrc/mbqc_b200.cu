@@ -1016,6 +1016,31 @@ int mbqc_psr_grad_batch_push(const mbqc_plan* plan, const double* d_angles, int6
     return MBQC_OK;
 }
 
+int mbqc_psr_grad_batch_multicast(const mbqc_plan* plan, const double* d_angles, int64_t angle_stride,
+                                  const void* d_inputs, int32_t input_mode, int64_t batch,
+                                  const void* d_target, double shift, void* d_result_multicast,
+                                  int64_t first_row, double* d_cost, int32_t* d_status, void* stream) {
+    if (!d_result_multicast) return fail(MBQC_E_ARG, "d_result_multicast is NULL");
+    if (first_row < 0) return fail(MBQC_E_ARG, "first_row < 0");
+    int rc = check_batch_args(plan, d_angles, angle_stride, d_inputs, input_mode, batch, d_result_multicast);
+    if (rc) return rc;
+    if ((rc = check_grad_plan(plan, d_target, shift))) return rc;
+    if (batch == 0 || plan->tab.n_angles == 0) return MBQC_OK;
+    SvBatchParams p;
+    fill_sv_params(p, plan, d_angles, angle_stride, d_inputs, input_mode, batch, nullptr, d_status);
+    p.target = (const double2*)d_target;
+    p.shift = shift;
+    p.cost = d_cost;
+    p.push_n = 1;
+    p.push_multicast = 1;
+    p.push_row0 = first_row;
+    p.push_dst[0] = (double*)d_result_multicast;
+    if (mbqc_jit_grad_try_launch(plan, p, (cudaStream_t)stream, &rc)) return rc;
+    // multicast addresses take multimem stores only: without the specialised kernel the caller falls back
+    return fail(MBQC_E_UNSUPPORTED, "the multicast form needs the run-time specialised gradient kernel (MBQC_JIT, libnvrtc, "
+                                    "every angle column read by exactly one measurement)");
+}
+
 int64_t mbqc_psr_grad_dataset_workspace_bytes(const mbqc_plan* plan, int64_t n_vectors, int64_t n_data) {
     if (!plan || n_vectors < 0 || n_data < 0) return -1;
     const int64_t n = n_vectors * n_data;

@@ -550,7 +550,7 @@ int mbqc_jit_grad_try_launch(const mbqc_plan* plan, const SvBatchParams& p, cuda
     const bool push = p.push_n > 0;
     // measured (profiles/r02_c4_push_modes.jsonl, exposed time over the local-only kernel): one bulk copy
     // per GPU wins up to 4 GPUs (+13 / +24 us vs +21 / +36 us at 2 / 4 GPUs), plain stores at 8 (+72 vs +90 us)
-    const int pmode = push_mode ? push_mode : (p.push_n > 4 ? 1 : 3);
+    const int pmode = p.push_multicast ? 4 : (push_mode ? push_mode : (p.push_n > 4 ? 1 : 3));
     Variant v{push ? pmode : 0, cta_env, kKindGrad};
     const size_t smem = (size_t)v.cta * ((size_t)T + ((size_t)1 << p.tab.n_out) + ((size_t)1 << (p.tab.window - 1))) * sizeof(double2);
     if (smem > 200 * 1024 || T > 64) return 0;
@@ -693,7 +693,7 @@ int64_t mbqc_jit_compile_check(const mbqc_plan* plan, int32_t out_form, int32_t 
     // 200 -> the density-matrix kernel mbqc_jit_dm
     Variant v{out_form == MBQC_OUT_DM ? MBQC_LEAN_OUT_DM : MBQC_LEAN_OUT_DIRECT, cta == 64 ? 64 : 128};
     if (out_form == 100) v = Variant{0, 128, kKindGrad};
-    if (out_form >= 101 && out_form <= 103) v = Variant{out_form - 100, 128, kKindGrad};  // replicated-result forms of the gradient kernel
+    if (out_form >= 101 && out_form <= 104) v = Variant{out_form - 100, 128, kKindGrad};  // replicated-result forms of the gradient kernel
     if (out_form == 200) {
         DmJitShape sh;
         if (!dm_jit_shape(plan, sh, cta == 1 || cta == 2 ? cta : 0)) return 0;  // cta 1 / 2: register slots per lane

@@ -29,6 +29,7 @@ struct SvBatchParams {
     double* push_dst[8];
     int64_t push_row0;
     int32_t push_n;
+    int32_t push_multicast;  // push_dst[0] is an NVSwitch multicast address covering every copy
 };
 
 // (angle row, data item) of sample b

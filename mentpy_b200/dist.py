@@ -7,6 +7,7 @@ communication is ONE all_gather of the results at the end (or none when the call
 sharded).  The reference's only parallelism is a process pool over input states in a docs snippet
 (docs/tutorials/intro-to-mbqml-parallel.rst:23-51); this is its multi-GPU counterpart.
 """
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -88,7 +89,10 @@ class ReplicatedResult:
 
     _FLAG_BYTES = 256
 
-    def __init__(self, rows: int, cols: int, group=None, device=None):
+    def __init__(self, rows: int, cols: int, group=None, device=None, multicast: Optional[bool] = None):
+        """multicast: None = use an NVSwitch multicast mapping when torch's symmetric memory provides
+        one (every store replicated by the switch: 1/world of the NVLink egress), else peer pointers
+        from CUDA IPC; True = require it; False = CUDA IPC only."""
         import ctypes as C
 
         import torch
@@ -107,6 +111,13 @@ class ReplicatedResult:
         self._flag_ptrs = None
         self._dst = [None, None]
         self._imported = []
+        self.mc_ptr = 0
+        self._symm = None
+        want_mc = multicast if multicast is not None else os.environ.get("MBQC_MULTICAST", "1") != "0"
+        if want_mc and self.world > 1 and self._try_symmetric_memory():
+            return
+        if multicast:
+            raise RuntimeError("no multicast mapping available (torch symmetric memory / NVSwitch multicast)")
         with torch.cuda.device(self.device):
             p = C.c_void_p()
             _lib.check(self.lib.mbqc_device_alloc(2 * self.nbytes + self._FLAG_BYTES, C.byref(p)))
@@ -132,6 +143,37 @@ class ReplicatedResult:
                 dist.barrier(group=group)  # every flag array is zeroed and mapped before the first use
         self.copy = 0  # the copy the last producing call filled
         self.tensors = [self.as_tensor(self._own + c * self.nbytes, (self.rows, self.cols), torch.float64) for c in (0, 1)]
+
+    def _try_symmetric_memory(self) -> bool:
+        """Allocate copies + flags as ONE torch symmetric-memory tensor: peer pointers and, on NVSwitch
+        systems, a multicast address come out of its rendezvous.  False (and no side effects) when
+        that is not available; the CUDA-IPC path takes over."""
+        torch = self.torch
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+
+            grp = self.group if self.group is not None else dist.group.WORLD
+            words = (2 * self.nbytes + self._FLAG_BYTES) // 8
+            with torch.cuda.device(self.device):
+                t = symm.empty(words, dtype=torch.float64, device=self.device)
+                hdl = symm.rendezvous(t, grp)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if mc == 0 or len(ptrs) != self.world:
+                return False
+            t.zero_()
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        except Exception:
+            return False
+        self._symm, self._symm_hdl = t, hdl
+        self.mc_ptr = mc
+        self.ptrs = ptrs
+        self._own = ptrs[self.rank]
+        self.copy = 0
+        self.tensors = [self.as_tensor(self._own + c * self.nbytes, (self.rows, self.cols), torch.float64) for c in (0, 1)]
+        return True
 
     @property
     def tensor(self):
@@ -181,6 +223,10 @@ class ReplicatedResult:
         if getattr(self, "_own", None) is None:
             return
         self.torch.cuda.synchronize(self.device)
+        if self._symm is not None:  # torch owns the symmetric allocation
+            self._symm, self._symm_hdl = None, None
+            self._own, self.tensors = None, [None, None]
+            return
         for q in self._imported:
             self.lib.mbqc_ipc_close(C.c_void_p(q))
         self._imported = []
@@ -244,11 +290,20 @@ def psr_gradient_distributed(simulator, angles, target, shift: float = 1.5, grou
             if not isinstance(target, torch.Tensor) else target.to(device=dev, dtype=torch.complex128).contiguous()
         status = torch.empty(max(batch, 1), dtype=torch.int32, device=dev)
         result.next_copy()
-        dst, n = result.destinations()
         st = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(lib.mbqc_psr_grad_batch_push(dplan.handle, a.data_ptr(), (a.stride(0) if batch > 1 else max(T, 1)),
-                                                None if inp is None else inp.data_ptr(), mode, batch, tgt.data_ptr(),
-                                                C.c_double(shift), dst, n, lo, None, status.data_ptr(), st))
+        rc = _lib.MBQC_E_UNSUPPORTED
+        if result.mc_ptr:  # one store per row, replicated by the switch into every GPU's copy
+            rc = lib.mbqc_psr_grad_batch_multicast(dplan.handle, a.data_ptr(), (a.stride(0) if batch > 1 else max(T, 1)),
+                                                   None if inp is None else inp.data_ptr(), mode, batch, tgt.data_ptr(),
+                                                   C.c_double(shift), C.c_void_p(result.mc_ptr + result.copy * result.nbytes),
+                                                   lo, None, status.data_ptr(), st)
+            if rc not in (0, _lib.MBQC_E_UNSUPPORTED):
+                _lib.check(rc)
+        if rc == _lib.MBQC_E_UNSUPPORTED:
+            dst, n = result.destinations()
+            _lib.check(lib.mbqc_psr_grad_batch_push(dplan.handle, a.data_ptr(), (a.stride(0) if batch > 1 else max(T, 1)),
+                                                    None if inp is None else inp.data_ptr(), mode, batch, tgt.data_ptr(),
+                                                    C.c_double(shift), dst, n, lo, None, status.data_ptr(), st))
         result.barrier(st)
         sim.last_status = status[:batch]
         return result.tensor

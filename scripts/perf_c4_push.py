@@ -51,6 +51,10 @@ def main():
         _lib.check(lib.mbqc_psr_grad_batch_push(plan.handle, part.data_ptr(), T, None, 0, n, tgt.data_ptr(), C.c_double(1.5),
                                                 dst, min(cnt, n_dst), lo, None, status.data_ptr(), stream))
 
+    def push_mc():
+        _lib.check(lib.mbqc_psr_grad_batch_multicast(plan.handle, part.data_ptr(), T, None, 0, n, tgt.data_ptr(), C.c_double(1.5),
+                                                     C.c_void_p(res.mc_ptr + res.copy * res.nbytes), lo, None, status.data_ptr(), stream))
+
     def timed(fn, reps=10, rounds=5):
         out = []
         for _ in range(rounds):
@@ -73,6 +77,14 @@ def main():
     rows["local"] = timed(lambda: psr_gradient_batched(ps, part, tgt))
     rows["push1"] = timed(lambda: push(1))
     rows["pushN"] = timed(lambda: push(world))
+    if res.mc_ptr:
+        push_mc()
+        res.barrier()
+        torch.cuda.synchronize()
+        ref = psr_gradient_batched(ps, full[:4096], tgt)
+        rows["multicast_max_abs_diff_rows_0_4095"] = float((res.tensor[:4096] - ref).abs().max().item()) if rank == 0 else 0.0
+        rows["pushMC"] = timed(push_mc)
+        rows["pushMC+barrier"] = timed(lambda: (push_mc(), res.barrier()))
     rows["barrier"] = timed(lambda: res.barrier(), reps=50)
     rows["pushN+barrier"] = timed(lambda: (push(world), res.barrier()))
     rows["step"] = timed(lambda: psr_gradient_distributed(ps, full, tgt))
@@ -85,7 +97,7 @@ def main():
     rows["host_enqueue_ms_per_step"] = (time.perf_counter() - t0) * 1e3 / 50
     torch.cuda.synchronize()
     if rank == 0:
-        print(json.dumps({"gpus": world, "rows_per_gpu": n, "cta": os.environ.get("MBQC_GRAD_CTA", "128"),
+        print(json.dumps({"gpus": world, "rows_per_gpu": n, "cta": os.environ.get("MBQC_GRAD_CTA", "128"), "multicast": bool(res.mc_ptr),
                           "ms": {k: round(v, 4) for k, v in rows.items()}}), flush=True)
     dist.barrier()
     res.release()
