@@ -5,7 +5,8 @@ that simulates needs the in-tree CUDA library and a CUDA device and raises other
 """
 from . import mbqc
 from .mbqc import (ControlledMent, ControlMent, GraphState, MBQCircuit, Measurement, Ment, MentOutcome, hstack, merge, templates, vstack)
-from . import calculator, gates, gradients, optimizers, simulators, utils
+from . import calculator, gates, gradients, optimizers, simulators, tooling, utils
+from .tooling import PauliOp
 from .simulators import BaseSimulator, CudaSimulatorDM, CudaSimulatorSV, PatternSimulator
 
 

@@ -24,7 +24,7 @@ def sample_probability_density_of_fidelities(circuit, n_samples: int = 1000, bac
         raise ValueError("the fidelity between input and output needs as many outputs as inputs")
     rng = np.random.default_rng(seed)
     n_in = len(circuit.input_nodes)
-    states = np.asarray(generate_haar_random_states(n_in, n_samples, seed=None if seed is None else int(rng.integers(1 << 31))))
+    states = np.asarray(generate_haar_random_states(n_in, n_samples, None if seed is None else int(rng.integers(1 << 31))))
     angles = rng.uniform(0, 2 * np.pi, (n_samples, len(circuit.trainable_nodes)))
     ps = simulator if simulator is not None else PatternSimulator(circuit, backend=backend)
     out = ps.run_batch(angles, input_states=states)

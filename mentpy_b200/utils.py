@@ -43,3 +43,13 @@ def generate_random_dataset(unitary: np.ndarray, n_samples: int, test_size: floa
     n_qubits = int(np.log2(unitary.shape[0]))
     x = np.atleast_2d(generate_haar_random_states(n_qubits, n_samples, random_state=random_state))
     return train_test_split(x, x @ unitary.T, test_size=test_size)
+
+
+def __getattr__(name):
+    # the reference keeps its Lie-algebra / expressivity helpers in mentpy.utils (utils/lie_algebra.py,
+    # utils/expressivity.py): same names here, implemented in mentpy_b200.tooling
+    from . import tooling
+
+    if name in tooling.__all__:
+        return getattr(tooling, name)
+    raise AttributeError(name)
