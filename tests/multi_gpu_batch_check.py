@@ -42,6 +42,19 @@ def main():
     for _ in range(3):
         gbig = psr_gradient_distributed(ps, ang, tgt)  # ragged split: 2050 + 2049 rows
         ok = ok and bool((gbig - gbig_ref).abs().max() < 1e-12)
+    # the same through CUDA-IPC mapped peer copies (what runs where no multicast mapping exists)
+    from mentpy_b200.dist import ReplicatedResult
+    ipc = ReplicatedResult(B, T, multicast=False)
+    ok = ok and ipc.mc_ptr == 0
+    for _ in range(3):
+        gipc = psr_gradient_distributed(ps, ang, tgt, result=ipc)
+        ok = ok and bool((gipc - gbig_ref).abs().max() < 1e-12)
+    lib.mbqc_jit_set_mode(0)  # general kernels + peer copies
+    gipc = psr_gradient_distributed(ps, ang, tgt, result=ipc)
+    ok = ok and bool((gipc - gbig_ref).abs().max() < 1e-12)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ipc.release()
     lib.mbqc_jit_set_mode(1)
     ok = ok and "failures=0" in lib.mbqc_jit_info().decode()
     # sampled shots: the Philox stream is indexed by the global shot number -> identical records

@@ -860,3 +860,37 @@ def test_expressivity_samples_through_the_batched_simulator():
     frozen = tl.expressivity_with_histogram(gs, n_bins=50, samples=np.full(1000, 0.999))  # a pattern acting as the identity
     assert 0 <= deep < 0.05 < frozen
     assert mb.utils.dim_su(4) == 15 and mb.PauliOp("XZ").txt == "XZ"
+
+
+def test_full_size_c3_c4_against_the_oracle():
+    """BASELINE configs 3 and 4 at FULL size (4,096 DM angle sets with and without depolarizing noise;
+    2^20 gradient vectors) compared with the numpy oracle on strided subsamples of the very batch the
+    kernels ran -- every kernel path the batch size selects (specialised kernels), every CTA region."""
+    from mentpy_b200.gradients import psr_gradient_batched
+
+    gs = mb.templates.grid_cluster(3, 8)
+    pat = PatternData.from_circuit(gs)
+    ang = np.random.default_rng(12).uniform(0, 2 * np.pi, (4096, 21))
+    idx = np.arange(5, 4096, 131)
+    for kw, okw in (({}, {}), ({"circuit_noise": "depolarizing", "p": 0.01}, {"noise": "depolarizing", "noise_kwargs": {"p": 0.01}})):
+        rho, oc = mb.PatternSimulator(gs, backend="cuda-dm", **kw).run_batch(ang, return_outcomes=True)
+        want, woc = matrix_free.run_dm_batch(pat, ang[idx], return_outcomes=True, **okw)
+        assert dm_distance(rho[idx], want) < 1e-10 and np.array_equal(oc[idx], woc)
+
+    gs = mb.templates.grid_cluster(4, 5)
+    pat = PatternData.from_circuit(gs)
+    ps = mb.PatternSimulator(gs, backend="cuda-sv")
+    B = 1 << 20
+    X = torch.rand((B, 16), dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8)) * (2 * np.pi)
+    tgt = np.exp(1j * np.arange(16)) / 4.0
+    g, c = psr_gradient_batched(ps, X, tgt, return_cost=True)
+    assert g.shape == (B, 16) and bool(torch.isfinite(g).all())
+    idx = np.array([0, 127, 128, 65_537, 524_288, 1_000_003, B - 1])
+    xs = X[torch.from_numpy(idx).cuda()].cpu().numpy()
+    cost = lambda a: 1 - np.abs(matrix_free.run_sv_batch(pat, a) @ tgt.conj()) ** 2  # noqa: E731
+    assert np.abs(c[torch.from_numpy(idx).cuda()].cpu().numpy() - cost(xs)).max() < 1e-11
+    for i in range(16):
+        e = np.zeros(16)
+        e[i] = 1.5
+        want = (cost(xs + e) - cost(xs - e)) / 3.0
+        assert np.abs(g[torch.from_numpy(idx).cuda(), i].cpu().numpy() - want).max() < 1e-10
