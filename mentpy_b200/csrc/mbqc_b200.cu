@@ -401,7 +401,7 @@ static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form
     const int tps = 1 << tps_log2;
     int spb = 256 / tps;
     if (spb < 1) spb = 1;
-    const size_t smem = (size_t)spb * (16ull << w);
+    const size_t smem = (size_t)spb * ((16ull << w) + 16ull * tps);  // amplitudes + a strip of staged (cos, sin)
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sv_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (unsigned)((p.batch + spb - 1) / spb);
     sv_smem_kernel<<<blocks, tps * spb, smem, st>>>(p, tps_log2, spb, out_form == MBQC_OUT_DM ? 1 : 0);
@@ -892,7 +892,7 @@ int mbqc_run_batch_sv_sampled(const mbqc_plan* plan, const double* d_angles, int
         const int tps = 1 << tps_log2;
         int spb = 256 / tps;
         if (spb < 1) spb = 1;
-        const size_t smem = (size_t)spb * (16ull << w);
+        const size_t smem = (size_t)spb * ((16ull << w) + 16ull * tps);
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sv_smem_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned blocks = (unsigned)((batch + spb - 1) / spb);
         sv_smem_sample_kernel<<<blocks, tps * spb, smem, (cudaStream_t)stream>>>(p, sp, tps_log2, spb);

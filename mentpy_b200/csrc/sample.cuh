@@ -228,6 +228,7 @@ __global__ void sv_smem_sample_kernel(const __grid_constant__ SvBatchParams p, c
     const bool live = b < p.batch;
     const int64_t be = live ? b : 0;
     double2* psi = smem + ((size_t)ls << w);
+    double2* cs = smem + ((size_t)spb << w) + ((size_t)ls << tps_log2);  // staged (cos, sin), as in sv_smem_kernel
     const uint64_t n = 1ull << w, half = n >> 1;
     double nrm = 0.0;
     {
@@ -258,8 +259,11 @@ __global__ void sv_smem_sample_kernel(const __grid_constant__ SvBatchParams p, c
     int took1 = 0;
     for (int m = 0; m < M; ++m) {
         const StepDev st = p.steps[m];
-        double c = st.fc, s = st.fs;
-        if (st.angle_idx >= 0) sincos(__ldg(row + st.angle_idx), &s, &c);
+        if ((m & (tps - 1)) == 0) {
+            stage_group_angles(p, row, m, tid, cs);
+            group_barrier(tps_log2);
+        }
+        double c = cs[m & (tps - 1)].x, s = cs[m & (tps - 1)].y;
         const FeedForwardDev ff = sp.ff[m];
         const uint32_t a = __popc(hist & ff.xdep) & 1u, z = __popc(hist & ff.zdep) & 1u;
         c = flip_sign(c, z << 31);

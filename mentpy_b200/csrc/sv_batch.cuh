@@ -32,6 +32,24 @@ __device__ __forceinline__ double group_sum(double v, int tps_log2, int ls, doub
     return tot;
 }
 
+// barrier over the threads of one sample: a warp-level sync is enough when the group fits a warp
+__device__ __forceinline__ void group_barrier(int tps_log2) {
+    if (tps_log2 <= 5) __syncwarp();
+    else __syncthreads();
+}
+
+// (cos, sin) of the next 2^tps_log2 measurements, one per thread of the sample's group, into the
+// group's shared-memory strip `cs` (every thread evaluating every angle was ~80 % of the kernel)
+__device__ __forceinline__ void stage_group_angles(const SvBatchParams& p, const double* row, int m, int tid, double2* cs) {
+    const int mm = m + tid;
+    if (mm < p.tab.n_steps) {
+        const StepDev sx = p.steps[mm];
+        double c = sx.fc, s = sx.fs;
+        if (sx.angle_idx >= 0) sincos_cw(__ldg(row + sx.angle_idx), s, c);
+        cs[tid] = make_double2(c, s);
+    }
+}
+
 __global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_log2, int spb, int dm_out) {
     extern __shared__ double2 smem[];
     __shared__ double red[32];
@@ -43,6 +61,7 @@ __global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_
     const int64_t b = (int64_t)blockIdx.x * spb + ls;
     const bool live = b < p.batch;
     double2* psi = smem + ((size_t)ls << w);
+    double2* cs = smem + ((size_t)spb << w) + ((size_t)ls << tps_log2);  // staged (cos, sin) of 2^tps_log2 steps
     const uint64_t n = 1ull << w;
     if (live) {
         const double2* in = (p.input_mode == MBQC_INPUT_PLUS)
@@ -69,8 +88,12 @@ __global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_
     const uint64_t half = n >> 1;
     for (int m = 0; m < t.n_steps; ++m) {
         const StepDev st = p.steps[m];
-        double c = st.fc, s = st.fs;
-        if (st.angle_idx >= 0) sincos(__ldg(row + st.angle_idx), &s, &c);
+        if ((m & (tps - 1)) == 0) {
+            stage_group_angles(p, row, m, tid, cs);
+            group_barrier(tps_log2);
+        }
+        const double2 csv = cs[m & (tps - 1)];
+        const double c = csv.x, s = csv.y;
         const double pr = 1.0 + c, pi = s;
         const double nzr = zr * pr - zi * pi;
         zi = zr * pi + zi * pr;
@@ -91,7 +114,7 @@ __global__ void sv_smem_kernel(const __grid_constant__ SvBatchParams p, int tps_
                 psi[i0 | bit] = tt;
             }
         }
-        __syncthreads();
+        group_barrier(tps_log2);
         if ((m & 7) == 7) {  // keep magnitudes bounded on long patterns
             double n2 = 0.0;
             if (live)
