@@ -41,7 +41,7 @@ class PatternData:
         return out
 
     def to_json(self) -> dict:
-        return {
+        d = {
             "n_nodes": self.n_nodes,
             "edges": [list(e) for e in self.edges],
             "input_nodes": list(self.input_nodes),
@@ -52,8 +52,10 @@ class PatternData:
             "trainable_nodes": list(self.trainable_nodes),
             "measurement_order": None if self.measurement_order is None else list(self.measurement_order),
             "quantum_output_nodes": list(self.quantum_output_nodes),
-            "controls": {str(k): v for k, v in self.controls.items()},
         }
+        if self.controls:  # only patterns with controlled measurements carry the key
+            d["controls"] = {str(k): v for k, v in self.controls.items()}
+        return d
 
     @staticmethod
     def from_json(d: dict) -> "PatternData":
