@@ -395,8 +395,8 @@ static int launch_sv(const SvBatchParams& p, const mbqc_plan* plan, int out_form
         return out_form == MBQC_OUT_DM ? launch_sv_reg<true>(p, plan, st, true) : launch_sv_reg<false>(p, plan, st, coalesced_out);
     if (w > MBQC_MAX_WINDOW_SMEM_SV)
         return fail(MBQC_E_UNSUPPORTED, "batched SV covers window <= %d (got %d); use the streaming calls", MBQC_MAX_WINDOW_SMEM_SV, w);
-    // threads per sample: one per pair up to 256
-    int tps_log2 = w - 1;
+    // threads per sample: one per group of 8 amplitudes (three measurements per pass) up to 256
+    int tps_log2 = w - 3;
     if (tps_log2 > 8) tps_log2 = 8;
     const int tps = 1 << tps_log2;
     int spb = 256 / tps;

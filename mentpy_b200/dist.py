@@ -79,10 +79,11 @@ def run_batch_distributed(simulator, angles, group=None, gather: bool = True, **
 
 class ReplicatedResult:
     """A [rows, cols] float64 result that every GPU of the node holds a full copy of, filled by
-    kernels that store their rows into ALL copies (peer-mapped memory, CUDA IPC over NVLink) --
-    the gather is part of the producing launch instead of a collective after it.  One process per
-    GPU; buffers come from plain cudaMalloc (IPC-exportable), handles travel once through
-    torch.distributed's object all_gather.  `barrier()` is the stream-ordered flag barrier that
+    kernels that store their rows into ALL copies -- the gather is part of the producing launch
+    instead of a collective after it.  One process per GPU.  Two transports: an NVSwitch multicast
+    address over a torch symmetric-memory allocation (one `multimem.st` stream, replicated by the
+    switch), or peer pointers from CUDA IPC over plain cudaMalloc buffers whose handles travel once
+    through torch.distributed's object all_gather.  `barrier()` is the stream-ordered flag barrier that
     makes the remote rows visible (mbqc_peer_barrier).  Two copies alternate (`next_copy`), so ONE
     barrier per producing call is enough: a rank can only start overwriting copy c two calls later,
     after a barrier that every rank entered behind its own reads of copy c."""
@@ -149,8 +150,11 @@ class ReplicatedResult:
         systems, a multicast address come out of its rendezvous.  False (and no side effects) when
         that is not available; the CUDA-IPC path takes over."""
         torch = self.torch
+        import torch.distributed as dist
+
+        t = hdl = None
+        mc, ptrs = 0, []
         try:
-            import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
 
             grp = self.group if self.group is not None else dist.group.WORLD
@@ -160,12 +164,15 @@ class ReplicatedResult:
                 hdl = symm.rendezvous(t, grp)
             mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
             ptrs = [int(x) for x in hdl.buffer_ptrs]
-            if mc == 0 or len(ptrs) != self.world:
-                return False
-            t.zero_()
-            torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)
+            if mc and len(ptrs) == self.world:
+                t.zero_()
+                torch.cuda.synchronize(self.device)
         except Exception:
+            mc = 0
+        # every rank takes the same transport: one failure sends all of them to the CUDA-IPC path
+        votes = [None] * self.world
+        dist.all_gather_object(votes, bool(mc and len(ptrs) == self.world), group=self.group)
+        if not all(votes):
             return False
         self._symm, self._symm_hdl = t, hdl
         self.mc_ptr = mc
