@@ -76,3 +76,21 @@ def test_specialised_dm_kernel_compiles_for_golden_patterns(case):
         assert size > 1000
     else:
         assert size == 0
+
+
+def test_gradient_kernel_variants_and_dm_layouts_compile():
+    """Every form of the specialised gradient kernel -- plain, and the replicated-result forms that
+    store into all GPUs' copies (coalesced stores, bulk copies with full / read-only wait, multimem
+    stores to a multicast address) -- and both register / lane layouts of the density-matrix kernel."""
+    if not _nvrtc_available():
+        pytest.skip("libnvrtc not found: " + _lib.load().mbqc_jit_info().decode())
+    dp = plan_mod.DevicePlan(plan_mod.lower(mb.templates.grid_cluster(4, 5)), host_only=True)
+    for form in (100, 101, 102, 103, 104):
+        assert dp.jit_compile_check(out_form=form) > 1000
+    dm = plan_mod.DevicePlan(plan_mod.lower(mb.templates.grid_cluster(3, 8), mixed=True), host_only=True)
+    sizes = {lb: dm.jit_compile_check(out_form=200, cta=lb) for lb in (1, 2)}
+    assert sizes[1] > 1000 and sizes[2] > sizes[1]  # 16 entries per lane unroll to more code than 4
+    gs = mb.templates.linear_cluster(5)
+    gs[2] = mb.ControlMent(gs[0].outcome, None, "XY", 0, "X")
+    ctl = plan_mod.DevicePlan(plan_mod.lower(gs, mixed=True), host_only=True)
+    assert ctl.jit_compile_check(out_form=200) == 0  # controlled steps stay on the general kernels
