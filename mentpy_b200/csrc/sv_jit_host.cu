@@ -135,8 +135,8 @@ std::string make_preamble(const mbqc_plan* plan, Variant v) {
     // gradient kernel: two working buffers; at w = 5 its shared memory (96 KB per 128 threads) admits 256
     // threads per SM anyway, so the register cap is lifted to match (1.82 -> 1.69 ms on C4)
     if (v.kind == kKindGrad) minblocks = (w <= 3) ? 1024 / v.cta : (w == 4 ? 640 / v.cta : 256 / v.cta);
-    if (v.kind == kKindGrad)
-        if (const char* e = getenv("MBQC_GRAD_MINBLOCKS")) minblocks = atoi(e) > 0 ? atoi(e) : minblocks;  // kernel work
+    if (const char* e = getenv(v.kind == kKindGrad ? "MBQC_GRAD_MINBLOCKS" : "MBQC_SV_MINBLOCKS"))  // kernel work
+        minblocks = atoi(e) > 0 ? atoi(e) : minblocks;
     std::string s;
     appendf(s, "#define JW %d\n#define JM %d\n#define JNFULL %d\n#define JT %d\n#define JNOUT %d\n#define JNIN %d\n", w, M,
             lp.n_full, lp.n_angles, lp.n_out, lp.n_in);
