@@ -31,8 +31,12 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierArgs a) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
     const unsigned long long* mine = a.flags[a.me] + d;
     unsigned long long v;
+    const long long t0 = clock64();
     do {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        // a rank that never arrives (crashed process, mismatched call sequence) must not park the GPU for
+        // ever: after ~30 s of SM clocks the kernel faults, which the next CUDA call reports
+        if (v < epoch && clock64() - t0 > 60000000000ll) __trap();
     } while (v < epoch);
 }
 
