@@ -54,6 +54,17 @@ def random_pattern(lib, seed: int, mixed: bool):
             gs[int(v)] = lib.Ment(float(rng.uniform(0, 2 * np.pi)), choice) if rng.integers(0, 2) else lib.Ment(choice)
         else:
             gs[int(v)] = lib.Ment(choice)
+    if mixed:
+        # every third density-matrix pattern also gets a fixed two-angle XYZ node (ment.py:239-251); drawn from
+        # its own stream so that the patterns of the other seeds stay what they were
+        r2 = np.random.default_rng(20_000 + seed)
+        free = [int(v) for v in gs.trainable_nodes if v not in gs.output_nodes]
+        if r2.integers(0, 3) == 0 and len(free) > 2:
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                gs[free[int(r2.integers(0, len(free)))]] = lib.Ment((float(r2.uniform(0, 2 * np.pi)), float(r2.uniform(-1.5, 1.5))), "XYZ")
     n_in = len(gs.input_nodes)
     n_meas = len(gs.measurement_order) - len(gs.quantum_output_nodes if mixed else gs.output_nodes)
     hi = min(n_meas, 6 if mixed else 8)   # register, shared-memory and (SV) streaming kernels

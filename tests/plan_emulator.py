@@ -65,11 +65,21 @@ def run_dm(pl, ang, inp):
     psi = _seed(pl, inp)
     rho = np.outer(psi, psi.conj())
     outcomes = []
-    for st in pl.steps:
+    for m, st in enumerate(pl.steps):
         c, s = _cos_sin(st, ang)
-        if st.plane == _lib.PLANE_XY:
+        plane, z = st.plane, st.fixed_z
+        if st.cond_mask:  # outcome-controlled step: bit j of the mask = the outcome j + 1 measurements back
+            bits = [j for j in range(32) if (st.cond_mask >> j) & 1]
+            idx = sum(outcomes[m - 1 - j] << i for i, j in enumerate(bits))
+            alt = (st.cond_table >> idx) & 1
+            plane, z = (st.alt_plane, st.alt_z) if alt else (st.plane, st.fixed_z)
+            aidx = st.alt_angle_idx if alt else st.angle_idx
+            c, s = (np.cos(ang[aidx]), np.sin(ang[aidx])) if aidx >= 0 else ((st.alt_cos, st.alt_sin) if alt else (st.fixed_cos, st.fixed_sin))
+        if plane == _lib.PLANE_XYZ:
+            p00, p11, p10 = (1 + z) / 2, (1 - z) / 2, 0.5 * (c + 1j * s)
+        elif plane == _lib.PLANE_XY:
             p00, p11, p10 = 0.5, 0.5, 0.5 * (c + 1j * s)
-        elif st.plane == _lib.PLANE_XZ:
+        elif plane == _lib.PLANE_XZ:
             p00, p11, p10 = (1 + s) / 2, (1 - s) / 2, 0.5 * c + 0j
         else:
             p00, p11, p10 = (1 + s) / 2, (1 - s) / 2, 0.5j * c

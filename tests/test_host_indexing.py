@@ -1,6 +1,7 @@
 """CPU: host-side indexing (templates, relabelling, causal flow, layers, measurement order,
 trainable order) must be bit-exact with tables dumped from the unmodified reference
 (tests/golden/structures.json; mentpy/mbqc/mbqcircuit.py:325-422, flow.py:115-185)."""
+import numpy as np
 import pytest
 
 import mentpy_b200 as mb
@@ -194,3 +195,49 @@ def test_dev_mode_schedule_matches_reference():
         lower(gs, dev_mode=True)
     with pytest.raises(ValueError, match="in no wire"):
         lower(gs, dev_mode=True, wires=[[0]])
+
+
+def test_lowered_plans_of_the_new_fixtures_execute_to_the_reference_outputs():
+    """The step records the kernels consume -- slots, masks, XYZ axes, condition masks / truth tables,
+    dev_mode orders -- executed in numpy (tests/plan_emulator.py) against the outputs recorded from
+    the reference: lowering errors surface on the CPU, before any kernel runs."""
+    import warnings
+
+    from conftest import from_cplx
+    from mentpy_b200.plan import lower
+    from oracle.gen_golden import CONTROL_CASES
+    from plan_emulator import run_dm, run_sv
+
+    def close(a, b, tol=1e-10):
+        return np.abs(np.asarray(a) - np.asarray(b)).max() < tol
+
+    for c in load_golden("dm_xyz_plane.json")["cases"]:
+        name, args, kw = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kw)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for v, a2 in c["xyz"].items():
+                gs[int(v)] = mb.Ment(tuple(a2), "XYZ")
+        n_in = len(gs.input_nodes)
+        inp = np.full(2**n_in, 2.0 ** (-n_in / 2), dtype=complex) if c["input_state"] is None else from_cplx(c["input_state"])
+        rho, oc = run_dm(lower(gs, window_size=c["window_size"], mixed=True), np.asarray(c["angles"]), inp)
+        assert close(rho, from_cplx(c["output"]))
+    for c in load_golden("dm_controlled.json")["cases"]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            gs = CONTROL_CASES[c["name"]](mb, mb.ControlMent)
+        n_in = len(gs.input_nodes)
+        inp = np.full(2**n_in, 2.0 ** (-n_in / 2), dtype=complex) if c["input_state"] is None else from_cplx(c["input_state"])
+        pl = lower(gs, window_size=c["window_size"], mixed=True)
+        rho, oc = run_dm(pl, np.asarray(c["angles"]), inp)
+        assert close(rho, from_cplx(c["output"])), c["name"]
+        assert oc == [c["outcomes"][str(st.node)] for st in pl.steps]
+    for c in load_golden("dev_mode.json")["cases"]:
+        name, args, kw = c["spec"]
+        gs = getattr(mb.templates, name)(*args, **kw)
+        inp, ang = from_cplx(c["input_state"]), np.asarray(c["angles"])
+        rho, _ = run_dm(lower(gs, window_size=c["window_size"], mixed=True, dev_mode=True, wires=c["wires"]), ang, inp)
+        assert close(rho, from_cplx(c["numpy-dm"]["output"]))
+        psi = run_sv(lower(gs, window_size=c["window_size"], dev_mode=True, wires=c["wires"]), ang, inp)
+        want = from_cplx(c["numpy-sv"]["output"])  # run() default: |psi><psi|
+        assert close(np.outer(psi, psi.conj()), want, 1e-9)
