@@ -144,3 +144,55 @@ def test_distributed_sampling_and_dataset_gradient_gloo(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def _worker_batch_split(rank, world, port, q):
+    import torch.distributed as dist
+
+    import mentpy_b200.gradients as grads
+    from mentpy_b200 import dist as mdist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        class Sim(_FakeSim):
+            def run_batch(self, angles, **kw):  # row b -> [sum of its angles, first angle]
+                return torch.stack([angles.sum(dim=1), angles[:, 0]], dim=1).to(torch.complex128)
+
+        sim = Sim()
+        B, T = 11, 3  # ragged over 2 and 3 ranks
+        ang = np.arange(B * T, dtype=np.float64).reshape(B, T)
+        full = mdist.run_batch_distributed(sim, ang)
+        want = sim.run_batch(torch.from_numpy(ang))
+        ok = torch.equal(full, want)
+        part, (lo, hi) = mdist.run_batch_distributed(sim, ang, gather=False)
+        ok = ok and (lo, hi) == mdist.slice_bounds(B, rank, world) and torch.equal(part, want[lo:hi])
+        # gradient split, NCCL / gloo all_gather form: g[b, i] = x[b, i] * (i + 1)
+        grads.psr_gradient_batched = lambda s, a, target, shift=1.5: a * torch.arange(1, a.shape[1] + 1, dtype=a.dtype)
+        g = mdist.psr_gradient_distributed(sim, ang, np.zeros(2), fused=False)
+        ok = ok and torch.equal(g, torch.from_numpy(ang) * torch.arange(1, T + 1, dtype=torch.float64))
+        gl, (lo2, hi2) = mdist.psr_gradient_distributed(sim, ang, np.zeros(2), gather=False)
+        ok = ok and (lo2, hi2) == (lo, hi) and torch.equal(gl, g[lo:hi])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_batch_split_and_gradient_split_gloo(world):
+    """Host logic of run_batch_distributed / psr_gradient_distributed (contiguous ragged slices, the
+    all_gather form of the final gather, gather=False) on CPU, world 2 and 3.  The peer-memory form
+    of the gather needs GPUs: tests/multi_gpu_batch_check.py under torchrun."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 1000) + world
+    procs = [ctx.Process(target=_worker_batch_split, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
