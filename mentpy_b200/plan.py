@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .mbqc.measurement import ControlMent, condition_reads
+from .mbqc.measurement import Ment, condition_reads
 
 _PLANE_CODE = {"XY": _lib.PLANE_XY, "X": _lib.PLANE_XY, "Y": _lib.PLANE_XY,
                "XZ": _lib.PLANE_XZ, "YZ": _lib.PLANE_YZ, "Z": _lib.PLANE_Z, "XYZ": _lib.PLANE_XYZ}
@@ -95,6 +95,11 @@ def _fixed_cos_sin(plane: str, angle):
     return float(np.cos(angle)), float(np.sin(angle))
 
 
+def _is_controlled(ment) -> bool:
+    """ControlMent of this package or of the reference (a mentpy.MBQCircuit is accepted as it is)."""
+    return hasattr(ment, "_true_ment") and hasattr(ment, "condition")
+
+
 def _dev_mode_order(circuit, schedule, w, n_meas, wires):
     """Measurement sequence and window contents of the reference's dev_mode scheduling
     (np_simulator_sv.py:173-203, np_simulator_dm.py:160-201): measure the FIRST node of the window
@@ -146,7 +151,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
     if not mixed:
         for v in nodes:
             m = circuit[v]
-            if m is not None and (isinstance(m, ControlMent) or m.plane not in ("X", "Y", "XY")):
+            if m is not None and (_is_controlled(m) or m.plane not in ("X", "Y", "XY")):
                 raise ValueError(f"Node {v} has plane {m.plane}, but only XY plane is supported.")
 
     if schedule is not None:
@@ -241,7 +246,7 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
     for m, node in enumerate(schedule_measure):
         ment = circuit[node]
         ctl = None
-        if isinstance(ment, ControlMent):
+        if _is_controlled(ment):
             # controlled_ment.py:96-113 through np_simulator_dm.py:307-346: only the density-matrix simulator
             # evaluates conditions, and only for nodes that receive an angle (a fixed-fixed ControlMent raises)
             if not mixed:
@@ -262,14 +267,15 @@ def lower(circuit, window_size: int = 1, schedule: Optional[Sequence[int]] = Non
             for idx in range(1 << len(by_bit)):
                 if cond({r: (idx >> i) & 1 for i, r in enumerate(by_bit)}):
                     table |= 1 << idx
-            if not ment.true_ment.is_trainable():
+            true_ment, false_ment = ment._true_ment, Ment(ment._angle, ment._plane)
+            if not true_ment.is_trainable():
                 # taking a fixed true branch makes the reference raise: ControlMent.get_povm hands the node's
                 # angle to it (controlled_ment.py:109-111 -> ment.py:222-226); refused here for every sample
-                shown = ment.true_ment.angle
+                shown = true_ment.angle
                 raise ValueError(f"Measurement has a fixed angle of {round(shown, 4) if isinstance(shown, (int, float)) else shown}")
-            f_spec, t_spec = branch_spec(node, ment.false_ment), branch_spec(node, ment.true_ment)
+            f_spec, t_spec = branch_spec(node, false_ment), branch_spec(node, true_ment)
             if not by_bit:  # constant condition: a plain step
-                ment = ment.true_ment if table & 1 else ment.false_ment
+                ment = true_ment if table & 1 else false_ment
             else:
                 ctl = (sum(1 << pos[r] for r in by_bit), table, f_spec, t_spec)
         if ctl is not None:

@@ -104,3 +104,28 @@ def test_user_schedules_equal_live_reference(seed):
         got = matrix_free.run_sv_batch(pat, ang[None], input_states=inp[None], window_size=w, schedule=sched)[0]
         assert infidelity_pure(got, want) < 1e-10
         assert 1 - abs(np.vdot(run_sv(pl, ang, inp), want)) ** 2 < 1e-10
+
+
+def test_reference_circuits_with_controlled_and_xyz_nodes_lower_like_ours():
+    """INTEGRATION.md promises that a mentpy.MBQCircuit works with the CUDA backends as it is: the
+    lowering of the REFERENCE's circuit objects (its own ControlMent / MentOutcome / XYZ Ment classes)
+    must equal the lowering of this package's mirror, step record by step record."""
+    from dataclasses import asdict
+
+    from mentpy_b200.plan import lower
+    from oracle.gen_golden import CONTROL_CASES
+
+    mp = import_reference()
+    from mentpy.operators import ControlMent as RefControlMent
+
+    import mentpy_b200 as mb
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, build in CONTROL_CASES.items():
+            a, b = lower(build(mp, RefControlMent), mixed=True), lower(build(mb, mb.ControlMent), mixed=True)
+            assert a.schedule_measure == b.schedule_measure and a.output_slot == b.output_slot, name
+            assert [asdict(s) for s in a.steps] == [asdict(s) for s in b.steps], name
+        ra, rb = mp.templates.grid_cluster(2, 4), mb.templates.grid_cluster(2, 4)
+        ra[2], rb[2] = mp.Ment((0.3, 1.1), "XYZ"), mb.Ment((0.3, 1.1), "XYZ")
+        assert [asdict(s) for s in lower(ra, mixed=True).steps] == [asdict(s) for s in lower(rb, mixed=True).steps]
