@@ -400,3 +400,44 @@ def test_specialised_dm_kernel_full_size_c3(jit_forced):
         assert np.allclose(np.trace(got, axis1=1, axis2=2), 1.0, atol=1e-12)
         assert np.linalg.eigvalsh(got[::64]).min() > -1e-12
     assert "failures=0" in _launched(jit_forced)
+
+
+@pytest.mark.parametrize("wires,w", [([3, 3, 3], 3), ([3, 3, 3, 3], 4), ([3, 3, 3, 3, 3], 5)])
+def test_specialised_dm_kernel_exact_path_with_lanes(wires, w, jit_forced):
+    """The lazily evaluated outcome rule on the multi-lane layouts (4 and 16 lanes per sample): with a
+    window as small as the input register the first CZs are dropped (as in the reference), so an
+    input qubit prepared orthogonal to its measurement direction gives prob0 = 0 -> outcome 1.  Rows
+    with and without such a qubit share warps; compared with the oracle and the general kernel."""
+    from conftest import dm_distance
+
+    gs = mb.templates.many_wires(wires)
+    pat = PatternData.from_circuit(gs)
+    n_in, T = len(gs.input_nodes), len(gs.trainable_nodes)
+    rng = np.random.default_rng(17)
+    B = 70
+    ang = rng.uniform(0, 2 * np.pi, (B, T))
+    ins = np.zeros((B, 2**n_in), dtype=complex)
+    hit = rng.random(B) < 0.3
+    first = gs.trainable_nodes.index(gs.input_nodes[0])
+    for b in range(B):
+        qubits = []
+        for q in range(n_in):
+            v = rng.normal(size=2) + 1j * rng.normal(size=2)
+            if q == 0 and hit[b]:  # orthogonal to (|0> + e^{i theta}|1>)/sqrt2 of the first measurement
+                v = np.array([1.0, -np.exp(1j * ang[b, first])])
+            qubits.append(v / np.linalg.norm(v))
+        st = qubits[0]
+        for v in qubits[1:]:
+            st = np.kron(st, v)
+        ins[b] = st
+    ps = mb.PatternSimulator(gs, backend="cuda-dm", window_size=w)
+    got, oc = ps.run_batch(ang, input_states=ins, return_outcomes=True)
+    assert "failures=0" in _launched(jit_forced)
+    want, woc = matrix_free.run_dm_batch(pat, ang, input_states=ins, window_size=w, return_outcomes=True)
+    assert woc[:, 0].astype(bool).tolist() == hit.tolist()  # the construction does what it says
+    assert np.array_equal(oc, woc) and dm_distance(got, want) < 1e-10
+    assert np.array_equal((ps.last_status & 2) != 0, woc.any(axis=1))
+    jit_forced.mbqc_jit_set_mode(0)
+    ref, roc = ps.run_batch(ang, input_states=ins, return_outcomes=True)
+    jit_forced.mbqc_jit_set_mode(2)
+    assert np.abs(got - ref).max() < 1e-12 and np.array_equal(oc, roc)
