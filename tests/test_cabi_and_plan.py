@@ -234,3 +234,22 @@ def test_entry_points_validate_arguments_before_touching_cuda():
     assert lib.mbqc_host_wait(10**6, None) == _lib.MBQC_E_ARG
     assert lib.mbqc_psr_grad_dataset_workspace_bytes(None, 1, 1) == -1
     assert lib.mbqc_host_workspace_bytes(None, 1, 0) == -1
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under mentpy_b200/ may import it or /root/reference, and
+    in bench.py only the cpu_baseline / --impl reference legs may."""
+    pkg = os.path.join(ROOT, "mentpy_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|/root/reference|ref_shim", re.M)
+    for dirpath, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
+                text = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert not pat.search(text), os.path.join(dirpath, f)
+    bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    uses = [m.start() for m in re.finditer(r"^\s*(from|import)\s+oracle\b", bench, re.M)]
+    assert uses, "bench.py lost its cpu_baseline leg"
+    for pos in uses:  # every import sits inside the CPU-port helpers
+        head = bench[:pos]
+        fn = re.findall(r"^def (\w+)\(", head, re.M)[-1]
+        assert fn in ("_cpu_worker", "_pattern_json"), fn  # the CPU-port worker and its pattern description
