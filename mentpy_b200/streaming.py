@@ -595,6 +595,9 @@ class CudaSimulatorSVStream:
         self.force0 = kwargs.pop("force0", True)
         if not self.force0:
             raise NotImplementedError("Numpy simulator does not support force0=False.")
+        if kwargs.pop("dev_mode", False):
+            # the streaming passes fuse measurements by slot; dev_mode orders are served by cuda-sv / cuda-dm
+            raise NotImplementedError("dev_mode scheduling is not supported by the streaming backend.")
         # Sharded runs keep the window positions measured LAST in the shard slots: a shard slot costs
         # an NVLink exchange every time it is measured, so the first w - g measurements are all
         # local (and start on the high, coalesced local slots); for patterns not much longer than
