@@ -160,6 +160,12 @@ def test_noisy_branches_average_to_the_pennylane_semantics(noise):
                                          noise_kwargs=kw)
         assert abs(total - 1) < 1e-12
         assert np.abs(avg - want).max() < 1e-12
+        # the same through the public entry point (what the reference's PennyLane backend returns)
+        assert np.abs(ps.simulator.outcome_averaged(ang, input_state=inp) - want).max() < 1e-12
+        if shape == [2, 3]:  # without a channel the corrected branches coincide: the force0 state comes back
+            clean = mb.PatternSimulator(gs, backend="cuda-sv", force0=False, window_size=w)
+            pure = mb.PatternSimulator(gs, backend="cuda-dm", window_size=w).run_batch(ang[None], input_states=inp)[0]
+            assert np.abs(clean.simulator.outcome_averaged(ang, input_state=inp) - pure).max() < 1e-10
         # sampled frequencies follow the branch probabilities (chi-square-ish on the first outcome)
         shots = ps.sample_batch(np.repeat(ang[None], 20000, 0), input_states=inp, seed=1)
         p_first1 = res.prob[recs[:, 0] == 1].sum()
